@@ -1,0 +1,71 @@
+"""Shared case table for oracle cross-checks and CUDA parity tests (test infrastructure)."""
+import numpy as np
+
+ZIGZAG, BPS, FECMC, BOOMERANG = 0, 1, 2, 3
+GAUSS_STD, GAUSS_DIAG, GAUSS_EQUICORR, BANANA, BANANA_README, LOGREG, GAUSS_DENSE = range(7)
+
+# name, sampler, potential, pot_params, dim, config kwargs, n_sk
+CASES = [
+    ("zz_gauss10", ZIGZAG, GAUSS_STD, None, 10, dict(), 2000),
+    ("zz_gauss10_fd", ZIGZAG, GAUSS_STD, None, 10, dict(deriv_mode=1), 1000),
+    ("zz_gauss_unsigned", ZIGZAG, GAUSS_STD, None, 5, dict(signed_bound=False), 1000),
+    ("zz_gauss_scalar", ZIGZAG, GAUSS_STD, None, 5, dict(vectorized_bound=False), 1000),
+    ("zz_gauss_scalar_fd", ZIGZAG, GAUSS_STD, None, 3, dict(vectorized_bound=False, deriv_mode=1, grid_size=4), 600),
+    ("zz_gauss1d_g2", ZIGZAG, GAUSS_STD, None, 1, dict(grid_size=2, tmax=0.0), 600),
+    ("zz_banana50_brent", ZIGZAG, BANANA, None, 50, dict(grid_size=0), 1000),
+    ("zz_banana5_grid_fd", ZIGZAG, BANANA, None, 5, dict(grid_size=8, deriv_mode=1), 1000),
+    ("zz_banana40_jvp", ZIGZAG, BANANA, None, 40, dict(grid_size=6), 800),
+    ("zz_readme_scalar", ZIGZAG, BANANA_README, None, 6, dict(grid_size=0), 7),
+    ("zz_equicorr33", ZIGZAG, GAUSS_EQUICORR, [0.5], 33, dict(grid_size=5, adaptive=False, tmax=0.3), 800),
+    ("zz_diag70", ZIGZAG, GAUSS_DIAG, "linspace", 70, dict(grid_size=10), 800),
+    ("bps_equi100", BPS, GAUSS_EQUICORR, [0.9], 100, dict(tmax=1.0, refresh_rate=0.1), 1000),
+    ("bps_gv_nonadapt", BPS, GAUSS_STD, None, 7,
+     dict(tmax=1.0, refresh_rate=0.5, gaussian_velocity=True, adaptive=False, signed_bound=False), 1000),
+    ("bps_brent", BPS, BANANA, None, 12, dict(tmax=1.0, refresh_rate=0.2, grid_size=0), 600),
+    ("bps_fd", BPS, BANANA, None, 9, dict(tmax=1.0, refresh_rate=0.1, deriv_mode=1), 600),
+    ("fecmc1000", FECMC, GAUSS_STD, None, 1000, dict(), 300),
+    ("fecmc_ranp", FECMC, BANANA, None, 6, dict(ran_p=True, mix_p=0.7), 1000),
+    ("fecmc_full_speed", FECMC, GAUSS_STD, None, 4, dict(switch=False, speed_factor=1.5, positive=False), 1000),
+    ("fecmc_d2", FECMC, GAUSS_STD, None, 2, dict(), 500),
+    ("fecmc_unsigned65", FECMC, GAUSS_DIAG, "linspace", 65, dict(signed_bound=False, grid_size=7), 500),
+    ("boom20_fd", BOOMERANG, GAUSS_STD, None, 20, dict(tmax=1.0, refresh_rate=0.1, deriv_mode=1), 1000),
+    ("boom_banana_jvp", BOOMERANG, BANANA, None, 4, dict(tmax=1.0, refresh_rate=0.1), 1000),
+    ("boom_diag_brent", BOOMERANG, GAUSS_DIAG, "linspace", 6, dict(tmax=1.0, refresh_rate=0.1, grid_size=0), 500),
+    ("boom_equi64", BOOMERANG, GAUSS_EQUICORR, [0.3], 64, dict(tmax=1.0, refresh_rate=0.3), 500),
+]
+
+
+def pot_params(pp, d):
+    if isinstance(pp, str) and pp == "linspace":
+        return np.linspace(0.5, 2.0, d)
+    return None if pp is None else np.asarray(pp, dtype=np.float64)
+
+
+def case_inputs(name, sampler, d, n_sk, n_chains=1, seed=0):
+    """Deterministic initial conditions + draw tapes for a case: (x0[C,d], v0[C,d], (E,U,N)[C,*])."""
+    import zlib
+    g = np.random.default_rng([zlib.crc32(name.encode()), seed])
+    x0 = 0.5 * g.standard_normal((n_chains, d))
+    if name.startswith("zz_readme"):
+        x0 = np.ones((n_chains, d))
+    if sampler == ZIGZAG:
+        v0 = np.where(g.random((n_chains, d)) < 0.5, -1.0, 1.0)
+    else:
+        v0 = g.standard_normal((n_chains, d))
+        if sampler in (BPS, FECMC):
+            v0 /= np.linalg.norm(v0, axis=1, keepdims=True)
+    nE, nU = 8 * n_sk + 64, 4 * n_sk + 64
+    nN = {ZIGZAG: 1, BPS: d * (n_sk // 2 + 8), FECMC: 2 * d * n_sk + 64, BOOMERANG: d * n_sk + 64}[sampler]
+    E = g.standard_exponential((n_chains, nE))
+    U = g.random((n_chains, nU))
+    N = g.standard_normal((n_chains, nN))
+    return x0, v0, (E, U, N)
+
+
+def tier_tolerance(kw, base=1e-10):
+    """Parity tiers: analytic-derivative grid bounds are held to `base` (the north_star's 1e-10);
+    Brent (grid_size=0) and sqrt(eps) finite differences amplify last-bit summation-order differences by up
+    to 1/sqrt(eps) ~ 7e7, so their one-step tolerance is 1e-6."""
+    if kw.get("grid_size", 10) == 0 or kw.get("deriv_mode", 0) == 1:
+        return 1e-6
+    return base
