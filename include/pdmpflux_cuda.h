@@ -1,0 +1,204 @@
+/*
+ * libpdmpflux_cuda.so -- C ABI of the B200-native grid-based Poisson-thinning engine.
+ *
+ * Drop-in boundary for PDMPFlux.jl's hot path.  The reference has NO native/FFI layer (pure Julia,
+ * SURVEY.md 8b): these entry points are what a Julia `ccall` binding (julia/PDMPFluxCUDA.jl) or a ctypes
+ * binding (pdmpflux_b200/_lib.py) binds in place of the Julia functions cited on each declaration
+ * (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the ABI: every call returns PDMPFLUX_OK (0) or a negative
+ *     pdmpflux_error code; pdmpflux_last_error() returns a thread-local message.
+ *   - all floating point is IEEE binary64; counters are int32 as in PDMPHistory (Composites.jl:138-149).
+ *   - "chain-major" skeleton layout: chain c's slab of X is a column-major d x n_cols matrix starting at
+ *     X + c*d*n_cols, i.e. exactly a Julia Matrix{Float64}(d, n_cols) (zero-copy unsafe_wrap).
+ *   - caller owns every buffer; the library never retains caller pointers past return.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with PDMPFLUX_ERR_CUDA.
+ */
+#ifndef PDMPFLUX_CUDA_H
+#define PDMPFLUX_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDMPFLUX_VERSION 100 /* 0.1.0 */
+
+typedef enum pdmpflux_error {
+    PDMPFLUX_OK = 0,
+    PDMPFLUX_ERR_ARGUMENT = -1,           /* Julia ArgumentError (dim<=0, grid_size<0, n_sk<=0, N<=0 ...) */
+    PDMPFLUX_ERR_DIMENSION_MISMATCH = -2, /* Julia DimensionMismatch (AbstractPDMP.jl:96-98) */
+    PDMPFLUX_ERR_UNSUPPORTED = -3,        /* sampler/potential/option outside the device path (no fallback) */
+    PDMPFLUX_ERR_CUDA = -4,               /* CUDA runtime error, or no device */
+    PDMPFLUX_ERR_CHAIN = -5               /* at least one chain stopped; see per-chain status */
+} pdmpflux_error;
+
+/* src/Samplers/{ZigZagSamplers,BouncyParticleSamplers,ForwardEventChainMonteCarlo,BoomerangSamplers}.jl */
+typedef enum pdmpflux_sampler_kind {
+    PDMPFLUX_ZIGZAG = 0, PDMPFLUX_BPS = 1, PDMPFLUX_FECMC = 2, PDMPFLUX_BOOMERANG = 3
+} pdmpflux_sampler_kind;
+
+/* Device potential plugins (replace the Julia closure `grad U`).  params layout:
+ *   GAUSS_STD            -                      U = |x|^2/2                      (README.md:36-38)
+ *   GAUSS_DIAG           p[d]                   U = sum p_i x_i^2 / 2
+ *   GAUSS_EQUICORR       rho                    Sigma = (1-rho) I + rho 11^T ("slanted Gaussian")
+ *   BANANA               -                      test/test_config.jl:33-36
+ *   BANANA_README_SCALAR -                      README.md:62-65 (scalar "gradient" broadcast to all coords)
+ *   LOGREG               n, sigma0, X[n*d] row-major, y[n]
+ *   GAUSS_DENSE          P[d*d] (symmetric precision, row-major)
+ */
+typedef enum pdmpflux_potential_kind {
+    PDMPFLUX_GAUSS_STD = 0, PDMPFLUX_GAUSS_DIAG = 1, PDMPFLUX_GAUSS_EQUICORR = 2, PDMPFLUX_BANANA = 3,
+    PDMPFLUX_BANANA_README_SCALAR = 4, PDMPFLUX_LOGREG = 5, PDMPFLUX_GAUSS_DENSE = 6
+} pdmpflux_potential_kind;
+
+/* How d/dt of the rate is obtained on the time grid: JVP = analytic (what AD_backend="ForwardDiff" computes,
+ * UpperBound.jl:102,210); FD = the reference's finite_difference_derivative (UpperBound.jl:50-76). */
+typedef enum pdmpflux_deriv_mode { PDMPFLUX_DERIV_JVP = 0, PDMPFLUX_DERIV_FD = 1 } pdmpflux_deriv_mode;
+
+/* per-chain status written to pdmpflux_history.status */
+typedef enum pdmpflux_chain_status {
+    PDMPFLUX_CHAIN_OK = 0,
+    PDMPFLUX_CHAIN_TAPE_EXHAUSTED = 1, /* injected draw tape ran out */
+    PDMPFLUX_CHAIN_NOT_PROBVEC = 2,    /* ZigZag jump with sum(lambda)==0/NaN: the reference's Categorical throws */
+    PDMPFLUX_CHAIN_STEP_LIMIT = 3      /* more than max_steps thinning steps inside one event */
+} pdmpflux_chain_status;
+
+/* Keyword arguments of the reference constructors (ZigZagSamplers.jl:58-60, BouncyParticleSamplers.jl:21-24,
+ * ForwardEventChainMonteCarlo.jl:301-303, BoomerangSamplers.jl:21-23).  pdmpflux_sampler_create applies the
+ * same rewrites the constructors do (tmax==0 -> 1 & adaptive; ZigZag signed&&!vectorized -> unsigned;
+ * non-ZigZag -> vectorized_bound=0; FECMC -> refresh_rate=0, dim==2 -> mix_p=0). */
+typedef struct pdmpflux_config {
+    int32_t grid_size;        /* 0 = constant bound via Brent (UpperBound.jl:18-36); otherwise >= 2 */
+    int32_t vectorized_bound; /* UpperBound.jl:203-247 vs :92-137 */
+    int32_t signed_bound;     /* AbstractPDMP.jl:104-112 */
+    int32_t adaptive;         /* horizon adaptation, SamplingLoopInplace.jl:98,140,194 */
+    int32_t deriv_mode;       /* pdmpflux_deriv_mode */
+    int32_t gaussian_velocity;/* BPS */
+    int32_t ran_p;            /* FECMC */
+    int32_t switch_;          /* FECMC `switch` */
+    int32_t positive;         /* FECMC */
+    int32_t max_steps;        /* 0 -> default 100000 thinning steps per event before STEP_LIMIT */
+    double tmax;
+    double refresh_rate;
+    double mix_p;             /* FECMC */
+    double speed_factor;      /* FECMC */
+} pdmpflux_config;
+
+/* Injected draws (parity mode): three typed streams per chain, consumed in the reference's order
+ * (SURVEY.md 8a "RNG draw order").  Chain c reads E + c*nE, U + c*nU, N + c*nN.  NULL tape -> Philox4x32-10
+ * keyed by (seed, global chain id, event index), see pdmpflux.jl_b200/csrc/philox.cuh. */
+typedef struct pdmpflux_tape {
+    const double* E; /* randexp  draws */
+    const double* U; /* rand     draws */
+    const double* N; /* randn    draws */
+    int64_t nE, nU, nN;
+    int32_t on_device; /* pointers are device pointers */
+} pdmpflux_tape;
+
+/* Output columns of PDMPHistory (Composites.jl:138-149), chain-major; any pointer may be NULL (not stored).
+ * is_active is not materialised: it is all-true for the non-sticky samplers on this path. */
+typedef struct pdmpflux_history {
+    double* X;               /* [C][n_cols][d] */
+    double* V;               /* [C][n_cols][d] */
+    double* t;               /* [C][n_cols]    */
+    double* horizon;         /* [C][n_cols]    */
+    double* ar;              /* [C][n_cols]    */
+    double* error_value_ar;  /* [C][n_cols][5] */
+    int32_t* errored_bound;  /* [C][n_cols]    */
+    int32_t* rejected;       /* [C][n_cols]    */
+    int32_t* hitting_horizon;/* [C][n_cols]    */
+    int32_t* status;         /* [C] pdmpflux_chain_status */
+    int64_t* tape_pos;       /* [C][3] draws consumed from (E,U,N) (tape mode) */
+    int64_t* counters;       /* [C][2] (bound builds, rate evaluations) -- instrumentation */
+    int64_t n_cols;          /* leading dimension (columns per chain slab) */
+    int32_t on_device;       /* all pointers above are device pointers */
+} pdmpflux_history;
+
+typedef struct pdmpflux_potential_s* pdmpflux_potential_t;
+typedef struct pdmpflux_sampler_s* pdmpflux_sampler_t;
+typedef struct pdmpflux_chains_s* pdmpflux_chains_t;
+
+int pdmpflux_version(void);
+const char* pdmpflux_last_error(void);
+int pdmpflux_device_count(int* count);
+int pdmpflux_set_device(int device);
+
+/* replaces the `grad U` closure argument of the constructors; copies params to the device */
+int pdmpflux_potential_create(int kind, int dim, const double* params, int64_t n_params,
+                              pdmpflux_potential_t* out);
+int pdmpflux_potential_destroy(pdmpflux_potential_t pot);
+
+/* replaces ZigZag(dim, grad U; kw...) / BPS / ForwardECMC / Boomerang constructors */
+int pdmpflux_sampler_create(int sampler_kind, int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg,
+                            pdmpflux_sampler_t* out);
+int pdmpflux_sampler_destroy(pdmpflux_sampler_t s);
+/* the config after constructor rewrites */
+int pdmpflux_sampler_get_config(pdmpflux_sampler_t s, pdmpflux_config* out);
+
+/* replaces sample_skeleton(sampler, n_sk, xinit, vinit; seed) (src/sample.jl:253-284) for n_chains chains:
+ * column 0 = initial state (t=0, horizon=tmax, ar=0), columns 1..n_sk-1 = successive accepted events
+ * (init_state AbstractPDMP.jl:93-153 + get_event_state! SamplingLoopInplace.jl:27-217 + record!
+ * Composites.jl:239-260).  xinit/vinit: d x n_chains column-major (host, or device when hist->on_device).
+ * hist->n_cols must be >= n_sk.  Global chain id = chain_offset + c (multi-GPU sharding).
+ * Returns PDMPFLUX_ERR_CHAIN if any chain stopped (outputs of healthy chains are still valid). */
+int pdmpflux_sample_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, const double* xinit,
+                             const double* vinit, uint64_t seed, int64_t chain_offset,
+                             const pdmpflux_tape* tape_or_null, const pdmpflux_history* hist, void* cuda_stream);
+
+/* Same, continuing from a saved PDMPState instead of init_state: x/v as xinit/vinit, per-chain t0 and
+ * horizon0 (NULL -> 0 / tmax) and the number of events already generated (Philox event index offset).
+ * The last column of a previous history (X, V, t, horizon) is a complete checkpoint: the reference keeps
+ * the final state in `sampler.state` (src/sample.jl:281) but offers no resume call. */
+int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, const double* xinit,
+                                    const double* vinit, const double* t0, const double* horizon0, int64_t event0,
+                                    uint64_t seed, int64_t chain_offset, const pdmpflux_tape* tape_or_null,
+                                    const pdmpflux_history* hist, void* cuda_stream);
+
+/* Streaming form of the same loop: device-resident PDMPState array (the analogue of `sampler.state`,
+ * src/sample.jl:281) that can be advanced in slices; lets skeletons larger than HBM stream to the host. */
+int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double* xinit, const double* vinit,
+                           int32_t init_on_device, uint64_t seed, int64_t chain_offset,
+                           const pdmpflux_tape* tape_or_null, pdmpflux_chains_t* out);
+/* overwrite / read the per-chain clock, horizon and event counter (resume, teacher-forced parity tests) */
+int pdmpflux_chains_set_state(pdmpflux_chains_t ch, const double* t, const double* horizon, int64_t event0,
+                              int32_t on_device);
+int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double* t, double* horizon,
+                              int32_t on_device);
+/* generate n_events more events per chain; column j of this call goes to hist column col0 + j (device view) */
+int pdmpflux_chains_advance(pdmpflux_chains_t ch, int64_t n_events, const pdmpflux_history* device_hist,
+                            int64_t col0, void* cuda_stream);
+/* write the current state as one history column (used for column 0) */
+int pdmpflux_chains_record(pdmpflux_chains_t ch, const pdmpflux_history* device_hist, int64_t col,
+                           void* cuda_stream);
+/* copy per-chain status / tape positions / counters out (host pointers, any may be NULL); returns
+ * PDMPFLUX_ERR_CHAIN if any status != 0 */
+int pdmpflux_chains_status(pdmpflux_chains_t ch, int32_t* status, int64_t* tape_pos, int64_t* counters);
+int pdmpflux_chains_destroy(pdmpflux_chains_t ch);
+
+/* replaces sample_from_skeleton(sampler, N, history; discard_vt) (src/sample.jl:475-513), per chain:
+ * out is [C][N][d] (or [C][N][2d+1]); flow_kind 0 = linear (ZigZag/BPS/FECMC), 1 = rotation (Boomerang). */
+int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, const double* X,
+                                  const double* V, const double* t, int64_t N, int32_t discard_vt, double* out,
+                                  int32_t on_device, void* cuda_stream);
+
+/* Closed-form time integrals over each chain's skeleton (no reference equivalent; feeds moments / ESS,
+ * SURVEY.md 8d): m1[C][d] = int x_i dt, m2[C][d] = int x_i^2 dt over [t[col_begin], t[n_sk-1]], T[C] = length. */
+int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, int64_t col_begin,
+                              const double* X, const double* V, const double* t, double* m1, double* m2,
+                              double* T, int32_t on_device, void* cuda_stream);
+
+/* pinned host memory for the host-buffer (end-to-end) path */
+int pdmpflux_host_alloc(void** ptr, size_t bytes);
+int pdmpflux_host_free(void* ptr);
+
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+int64_t pdmpflux_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDMPFLUX_CUDA_H */

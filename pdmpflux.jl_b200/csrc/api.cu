@@ -1,0 +1,628 @@
+// C ABI of libpdmpflux_cuda.so (see include/pdmpflux_cuda.h).  Host orchestration only: handles, argument
+// validation mirroring the reference constructors / drivers, kernel dispatch, and the host-buffer pipeline
+// (device double buffering + pinned D2H copies overlapped with the next slice of events).
+//
+// There is no CPU fallback anywhere in this file: without a usable CUDA device every compute entry point
+// returns PDMPFLUX_ERR_CUDA.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "launch.cuh"
+
+using namespace pdmpflux;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(PDMPFLUX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+struct DevBuf {  // RAII device allocation
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&p, n);
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct pdmpflux_potential_s {
+    int kind = 0, dim = 0;
+    PotParams pp{};
+    DevBuf params;
+};
+
+struct pdmpflux_sampler_s {
+    int kind = 0, dim = 0;
+    pdmpflux_config cfg{};
+    pdmpflux_potential_s* pot = nullptr;
+};
+
+struct pdmpflux_chains_s {
+    pdmpflux_sampler_s* s = nullptr;
+    int64_t n_chains = 0, chain_offset = 0, event0 = 0;
+    uint64_t seed = 0;
+    int team = 32, n_own = 0, scratch_in_smem = 1;
+    size_t smem = 0;
+    unsigned grid = 0;
+    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch;
+    // draws
+    int draw_mode = 1;
+    DevBuf tE, tU, tN;  // owned device copies when the tape was given on the host
+    const double *dE = nullptr, *dU = nullptr, *dN = nullptr;
+    int64_t nE = 0, nU = 0, nN = 0;
+};
+
+namespace {
+
+int pick_team(int d, int64_t n_chains) {
+    if (const char* e = std::getenv("PDMPFLUX_TEAM")) {
+        const int t = std::atoi(e);
+        if (t == 1 || t == 8 || t == 32) return t;
+    }
+    // Enough chains to fill the machine with one thread each and few coordinates: thread per chain.
+    const int64_t fill = 148LL * 1024;
+    if (d <= 16 && n_chains >= fill / 4) return 1;
+    if (d <= 96 && n_chains * 8 >= fill) return 8;
+    if (d < 8) return 1;
+    if (d < 32) return 8;
+    return 32;
+}
+
+int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, int64_t col0, cudaStream_t stream) {
+    const pdmpflux_sampler_s* s = ch->s;
+    const pdmpflux_config& c = s->cfg;
+    KernelParams p{};
+    p.d = s->dim; p.G = c.grid_size; p.vectorized = c.vectorized_bound; p.signed_bound = c.signed_bound;
+    p.adaptive = c.adaptive; p.deriv_mode = c.deriv_mode; p.gaussian_velocity = c.gaussian_velocity;
+    p.ran_p = c.ran_p; p.switch_ = c.switch_; p.positive = c.positive;
+    p.max_steps = c.max_steps > 0 ? c.max_steps : 100000;
+    p.tmax = c.tmax; p.refresh_rate = c.refresh_rate;
+    p.bound_refresh = c.signed_bound ? c.refresh_rate : 0.0;  // AbstractPDMP.jl:104-112
+    p.mix_p = c.mix_p; p.speed_factor = c.speed_factor;
+    p.pot = s->pot->pp;
+    p.n_chains = ch->n_chains; p.chain_offset = ch->chain_offset; p.seed = ch->seed;
+    p.event0 = ch->event0; p.n_events = n_events;
+    p.sx = ch->x.as<double>(); p.sv = ch->v.as<double>(); p.st = ch->t.as<double>();
+    p.shorizon = ch->horizon.as<double>(); p.sar = ch->ar.as<double>();
+    p.tape_pos = ch->tape_pos.as<int64_t>(); p.status = ch->status.as<int32_t>();
+    p.counters = ch->counters.as<int64_t>();
+    p.draw_mode = ch->draw_mode; p.tE = ch->dE; p.tU = ch->dU; p.tN = ch->dN;
+    p.nE = ch->nE; p.nU = ch->nU; p.nN = ch->nN;
+    if (h) {
+        p.X = h->X; p.V = h->V; p.T = h->t; p.H = h->horizon; p.AR = h->ar; p.EVA = h->error_value_ar;
+        p.EB = h->errored_bound; p.REJ = h->rejected; p.HH = h->hitting_horizon;
+        p.ld_cols = h->n_cols;
+    }
+    p.col0 = col0;
+    p.scratch = ch->scratch.as<double>(); p.scratch_in_smem = ch->scratch_in_smem; p.n_own = ch->n_own;
+    cudaError_t e;
+    switch (s->kind) {
+    case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_BPS: e = launch_skeleton_bps(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_FECMC: e = launch_skeleton_fecmc(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_BOOMERANG: e = launch_skeleton_boomerang(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
+    default: e = cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("skeleton kernel launch: ") + cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return PDMPFLUX_OK;
+}
+
+// ---- sample_from_skeleton (src/sample.jl:475-513) -------------------------------------------------------
+// One thread per output element (sample j, coordinate a) of one chain; neighbouring threads share j, so the
+// binary search over the chain's event times is a broadcast and X/V/out accesses are coalesced.
+__global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64_t n_sk, int64_t N, int discard_vt,
+                                                     const double* __restrict__ X, const double* __restrict__ V,
+                                                     const double* __restrict__ T, double* __restrict__ out) {
+    const int64_t c = blockIdx.y;
+    const double* t = T + c * n_sk;
+    const double dt = t[n_sk - 1] / (double)N;
+    const int ld = discard_vt ? d : 2 * d + 1;
+    const int64_t total = N * (int64_t)ld;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / ld;
+        const int a = (int)(e - j * ld);
+        const double tm = (double)(j + 1) * dt;
+        // largest i with t[i] <= tm (the reference's monotone pointer walk `while t[i+1] <= tm`)
+        int64_t lo = 0, hi = n_sk - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (t[mid] <= tm) lo = mid; else hi = mid - 1;
+        }
+        const double tau = tm - t[lo];
+        const double* x0 = X + (c * n_sk + lo) * d;
+        const double* v0 = V + (c * n_sk + lo) * d;
+        double r;
+        if (a == 2 * d) r = tm;
+        else {
+            const int b = a < d ? a : a - d;
+            const double xi = x0[b], vi = v0[b];
+            if (flow_kind == 1) {
+                double s, co;
+                sincos(tau, &s, &co);
+                r = a < d ? xi * co + vi * s : -xi * s + vi * co;
+            } else r = a < d ? xi + vi * tau : vi;
+        }
+        out[(c * N + j) * ld + a] = r;
+    }
+}
+
+// Closed-form time integrals of x_i and x_i^2 along each chain's piecewise flow (feeds moments / ESS).
+__global__ void __launch_bounds__(256) moments_kernel(int flow_kind, int d, int64_t n_sk, int64_t n_chains,
+                                                      int64_t col_begin, const double* __restrict__ X,
+                                                      const double* __restrict__ V, const double* __restrict__ T,
+                                                      double* __restrict__ m1, double* __restrict__ m2,
+                                                      double* __restrict__ Tlen) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_chains * d) return;
+    const int64_t c = e / d;
+    const int a = (int)(e - c * d);
+    const double* t = T + c * n_sk;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t k = col_begin; k + 1 < n_sk; ++k) {
+        const double tau = t[k + 1] - t[k];
+        const double x = X[(c * n_sk + k) * d + a], v = V[(c * n_sk + k) * d + a];
+        if (flow_kind == 1) {
+            double s, co;
+            sincos(tau, &s, &co);
+            const double s2t = 2.0 * s * co;  // sin(2 tau)
+            s1 += x * s + v * (1.0 - co);
+            s2 += x * x * (0.5 * tau + 0.25 * s2t) + v * v * (0.5 * tau - 0.25 * s2t) + x * v * s * s;
+        } else {
+            s1 += tau * (x + 0.5 * v * tau);
+            s2 += tau * (x * x + tau * (x * v + v * v * tau * (1.0 / 3.0)));
+        }
+    }
+    m1[e] = s1;
+    m2[e] = s2;
+    if (a == 0 && Tlen) Tlen[c] = t[n_sk - 1] - t[col_begin];
+}
+
+int normalise_config(int kind, int dim, pdmpflux_config& c) {
+    // constructor rewrites: ZigZagSamplers.jl:73-78, BouncyParticleSamplers.jl:29-37,
+    // ForwardEventChainMonteCarlo.jl:306-323, BoomerangSamplers.jl:27-36
+    if (c.tmax == 0.0) { c.tmax = 1.0; c.adaptive = 1; }
+    if (kind == PDMPFLUX_ZIGZAG) {
+        if (c.signed_bound && !c.vectorized_bound) c.signed_bound = 0;
+    } else c.vectorized_bound = 0;
+    if (kind == PDMPFLUX_FECMC) {
+        c.refresh_rate = 0.0;
+        if (dim == 2) c.mix_p = 0.0;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int pdmpflux_version(void) { return PDMPFLUX_VERSION; }
+const char* pdmpflux_last_error(void) { return g_err.c_str(); }
+int64_t pdmpflux_launch_count(void) { return g_launches.load(); }
+
+int pdmpflux_device_count(int* count) {
+    if (!count) return fail(PDMPFLUX_ERR_ARGUMENT, "count is NULL");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return PDMPFLUX_OK;
+}
+int pdmpflux_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_potential_create(int kind, int dim, const double* params, int64_t n_params, pdmpflux_potential_t* out) {
+    if (!out) return fail(PDMPFLUX_ERR_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (dim <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "dimension dim must be positive. Current value: " + std::to_string(dim));
+    auto pot = new pdmpflux_potential_s();
+    pot->kind = kind; pot->dim = dim;
+    auto need = [&](int64_t n) { return params != nullptr && n_params >= n; };
+    int rc = PDMPFLUX_OK;
+    switch (kind) {
+    case PDMPFLUX_GAUSS_STD: break;
+    case PDMPFLUX_BANANA:
+    case PDMPFLUX_BANANA_README_SCALAR:
+        if (dim < 2) rc = fail(PDMPFLUX_ERR_ARGUMENT, "banana potentials need dim >= 2");
+        break;
+    case PDMPFLUX_GAUSS_DIAG:
+        if (!need(dim)) { rc = fail(PDMPFLUX_ERR_ARGUMENT, "GAUSS_DIAG needs dim precisions"); break; }
+        if (pot->params.alloc(sizeof(double) * dim) != cudaSuccess ||
+            cudaMemcpy(pot->params.p, params, sizeof(double) * dim, cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail(PDMPFLUX_ERR_CUDA, "GAUSS_DIAG parameter upload failed (is a CUDA device present?)");
+        pot->pp.vec = pot->params.as<double>();
+        break;
+    case PDMPFLUX_GAUSS_EQUICORR: {
+        if (!need(1)) { rc = fail(PDMPFLUX_ERR_ARGUMENT, "GAUSS_EQUICORR needs rho"); break; }
+        const double rho = params[0];
+        if (!(rho < 1.0) || !(1.0 - rho + dim * rho > 0.0)) { rc = fail(PDMPFLUX_ERR_ARGUMENT, "rho outside (-1/(d-1), 1)"); break; }
+        pot->pp.alpha = 1.0 / (1.0 - rho);
+        pot->pp.beta = rho / ((1.0 - rho) * (1.0 - rho + dim * rho));
+    } break;
+    case PDMPFLUX_LOGREG:
+    case PDMPFLUX_GAUSS_DENSE:
+        rc = fail(PDMPFLUX_ERR_UNSUPPORTED, "potential kind not available on the device path yet (no CPU fallback)");
+        break;
+    default: rc = fail(PDMPFLUX_ERR_ARGUMENT, "unknown potential kind " + std::to_string(kind));
+    }
+    if (rc != PDMPFLUX_OK) { delete pot; return rc; }
+    *out = pot;
+    return PDMPFLUX_OK;
+}
+int pdmpflux_potential_destroy(pdmpflux_potential_t pot) { delete pot; return PDMPFLUX_OK; }
+
+int pdmpflux_sampler_create(int kind, int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg, pdmpflux_sampler_t* out) {
+    if (!out) return fail(PDMPFLUX_ERR_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!pot || !cfg) return fail(PDMPFLUX_ERR_ARGUMENT, "potential / config is NULL");
+    if (kind < PDMPFLUX_ZIGZAG || kind > PDMPFLUX_BOOMERANG)
+        return fail(PDMPFLUX_ERR_UNSUPPORTED, "sampler kind outside the device path (Sticky/SpeedUp/RHMC are not ported; no CPU fallback)");
+    if (dim <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "dimension dim must be positive. Current value: " + std::to_string(dim));
+    if (dim != pot->dim) return fail(PDMPFLUX_ERR_DIMENSION_MISMATCH, "potential dim " + std::to_string(pot->dim) + " != sampler dim " + std::to_string(dim));
+    if (cfg->grid_size < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "grid_size must be non-negative. Current value: " + std::to_string(cfg->grid_size));
+    if (cfg->grid_size == 1) return fail(PDMPFLUX_ERR_ARGUMENT, "grid_size == 1 is invalid upstream (t[2] out of bounds, UpperBound.jl:95,205); use 0 or >= 2");
+    if (cfg->grid_size > kMaxGrid) return fail(PDMPFLUX_ERR_UNSUPPORTED, "grid_size > " + std::to_string(kMaxGrid) + " not supported on the device path");
+    if (kind == PDMPFLUX_FECMC && dim < 2)
+        return fail(PDMPFLUX_ERR_ARGUMENT, "The dimension must be at least 2 to use the ForwardEventChain. Got dimension " + std::to_string(dim));
+    if (!(cfg->tmax >= 0.0) || !std::isfinite(cfg->tmax)) return fail(PDMPFLUX_ERR_ARGUMENT, "tmax must be finite and >= 0");
+    auto s = new pdmpflux_sampler_s();
+    s->kind = kind; s->dim = dim; s->cfg = *cfg; s->pot = pot;
+    normalise_config(kind, dim, s->cfg);
+    *out = s;
+    return PDMPFLUX_OK;
+}
+int pdmpflux_sampler_destroy(pdmpflux_sampler_t s) { delete s; return PDMPFLUX_OK; }
+int pdmpflux_sampler_get_config(pdmpflux_sampler_t s, pdmpflux_config* out) {
+    if (!s || !out) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
+    *out = s->cfg;
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double* xinit, const double* vinit,
+                           int32_t init_on_device, uint64_t seed, int64_t chain_offset,
+                           const pdmpflux_tape* tape, pdmpflux_chains_t* out) {
+    if (!out) return fail(PDMPFLUX_ERR_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!s || !xinit || !vinit) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
+    if (n_chains <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "n_chains must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: libpdmpflux_cuda has no CPU fallback");
+    auto ch = new pdmpflux_chains_s();
+    struct Guard { pdmpflux_chains_s* c; ~Guard() { delete c; } } guard{ch};
+    ch->s = s; ch->n_chains = n_chains; ch->chain_offset = chain_offset; ch->seed = seed;
+    const int d = s->dim;
+    ch->team = pick_team(d, n_chains);
+    ch->n_own = (d + ch->team - 1) / ch->team;
+    const int cpb = kBlockThreads / ch->team;
+    ch->grid = (unsigned)((n_chains + cpb - 1) / cpb);
+    const size_t vec_bytes = (size_t)ch->n_own * kBlockThreads * sizeof(double);
+    ch->smem = 2 * vec_bytes;
+    if (s->kind == PDMPFLUX_FECMC) {
+        if (5 * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = 5 * vec_bytes; }
+        else {
+            ch->scratch_in_smem = 0;
+            CUDA_TRY(ch->scratch.alloc((size_t)ch->grid * 3 * vec_bytes));
+        }
+    }
+    if (ch->smem > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "dimension too large for the shared-memory state layout");
+    CUDA_TRY(ch->x.alloc(sizeof(double) * d * n_chains));
+    CUDA_TRY(ch->v.alloc(sizeof(double) * d * n_chains));
+    CUDA_TRY(ch->t.alloc(sizeof(double) * n_chains));
+    CUDA_TRY(ch->horizon.alloc(sizeof(double) * n_chains));
+    CUDA_TRY(ch->ar.alloc(sizeof(double) * n_chains));
+    CUDA_TRY(ch->tape_pos.alloc(sizeof(int64_t) * 3 * n_chains));
+    CUDA_TRY(ch->status.alloc(sizeof(int32_t) * n_chains));
+    CUDA_TRY(ch->counters.alloc(sizeof(int64_t) * 2 * n_chains));
+    const cudaMemcpyKind k = init_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpy(ch->x.p, xinit, sizeof(double) * d * n_chains, k));
+    CUDA_TRY(cudaMemcpy(ch->v.p, vinit, sizeof(double) * d * n_chains, k));
+    CUDA_TRY(cudaMemset(ch->t.p, 0, sizeof(double) * n_chains));
+    CUDA_TRY(cudaMemset(ch->ar.p, 0, sizeof(double) * n_chains));
+    CUDA_TRY(cudaMemset(ch->tape_pos.p, 0, sizeof(int64_t) * 3 * n_chains));
+    CUDA_TRY(cudaMemset(ch->status.p, 0, sizeof(int32_t) * n_chains));
+    CUDA_TRY(cudaMemset(ch->counters.p, 0, sizeof(int64_t) * 2 * n_chains));
+    {
+        std::vector<double> h0((size_t)n_chains, s->cfg.tmax);  // init_state: horizon = tmax (AbstractPDMP.jl:141-149)
+        CUDA_TRY(cudaMemcpy(ch->horizon.p, h0.data(), sizeof(double) * n_chains, cudaMemcpyHostToDevice));
+    }
+    if (tape) {
+        if (!tape->E || !tape->U || !tape->N || tape->nE <= 0 || tape->nU <= 0 || tape->nN <= 0)
+            return fail(PDMPFLUX_ERR_ARGUMENT, "tape streams must be non-empty");
+        ch->draw_mode = 0; ch->nE = tape->nE; ch->nU = tape->nU; ch->nN = tape->nN;
+        if (tape->on_device) { ch->dE = tape->E; ch->dU = tape->U; ch->dN = tape->N; }
+        else {
+            CUDA_TRY(ch->tE.alloc(sizeof(double) * tape->nE * n_chains));
+            CUDA_TRY(ch->tU.alloc(sizeof(double) * tape->nU * n_chains));
+            CUDA_TRY(ch->tN.alloc(sizeof(double) * tape->nN * n_chains));
+            CUDA_TRY(cudaMemcpy(ch->tE.p, tape->E, ch->tE.bytes, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(ch->tU.p, tape->U, ch->tU.bytes, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(ch->tN.p, tape->N, ch->tN.bytes, cudaMemcpyHostToDevice));
+            ch->dE = ch->tE.as<double>(); ch->dU = ch->tU.as<double>(); ch->dN = ch->tN.as<double>();
+        }
+    }
+    guard.c = nullptr;
+    *out = ch;
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_set_state(pdmpflux_chains_t ch, const double* t, const double* horizon, int64_t event0,
+                              int32_t on_device) {
+    if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
+    if (event0 < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "event0 must be >= 0");
+    const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (t) CUDA_TRY(cudaMemcpy(ch->t.p, t, sizeof(double) * ch->n_chains, k));
+    if (horizon) CUDA_TRY(cudaMemcpy(ch->horizon.p, horizon, sizeof(double) * ch->n_chains, k));
+    ch->event0 = event0;
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double* t, double* horizon, int32_t on_device) {
+    if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
+    const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t nd = sizeof(double) * ch->s->dim * ch->n_chains;
+    if (x) CUDA_TRY(cudaMemcpy(x, ch->x.p, nd, k));
+    if (v) CUDA_TRY(cudaMemcpy(v, ch->v.p, nd, k));
+    if (t) CUDA_TRY(cudaMemcpy(t, ch->t.p, sizeof(double) * ch->n_chains, k));
+    if (horizon) CUDA_TRY(cudaMemcpy(horizon, ch->horizon.p, sizeof(double) * ch->n_chains, k));
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_advance(pdmpflux_chains_t ch, int64_t n_events, const pdmpflux_history* h, int64_t col0, void* stream) {
+    if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
+    if (n_events <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "n_events must be positive");
+    if (h && (!h->on_device || col0 < 0 || col0 + n_events > h->n_cols))
+        return fail(PDMPFLUX_ERR_ARGUMENT, "chains_advance needs a device history view with col0 + n_events <= n_cols");
+    const int rc = launch(ch, n_events, h, col0, static_cast<cudaStream_t>(stream));
+    if (rc == PDMPFLUX_OK) ch->event0 += n_events;
+    return rc;
+}
+
+int pdmpflux_chains_record(pdmpflux_chains_t ch, const pdmpflux_history* h, int64_t col, void* stream) {
+    if (!ch || !h) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
+    if (!h->on_device || col < 0 || col >= h->n_cols) return fail(PDMPFLUX_ERR_ARGUMENT, "chains_record needs a device view and a valid column");
+    return launch(ch, 0, h, col, static_cast<cudaStream_t>(stream));
+}
+
+int pdmpflux_chains_status(pdmpflux_chains_t ch, int32_t* status, int64_t* tape_pos, int64_t* counters) {
+    if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
+    std::vector<int32_t> st((size_t)ch->n_chains);
+    CUDA_TRY(cudaMemcpy(st.data(), ch->status.p, sizeof(int32_t) * ch->n_chains, cudaMemcpyDeviceToHost));
+    if (status) std::memcpy(status, st.data(), sizeof(int32_t) * ch->n_chains);
+    if (tape_pos) CUDA_TRY(cudaMemcpy(tape_pos, ch->tape_pos.p, sizeof(int64_t) * 3 * ch->n_chains, cudaMemcpyDeviceToHost));
+    if (counters) CUDA_TRY(cudaMemcpy(counters, ch->counters.p, sizeof(int64_t) * 2 * ch->n_chains, cudaMemcpyDeviceToHost));
+    int64_t bad = 0, first = -1;
+    for (int64_t c = 0; c < ch->n_chains; ++c)
+        if (st[c] != 0) { if (first < 0) first = c; ++bad; }
+    if (bad) return fail(PDMPFLUX_ERR_CHAIN, std::to_string(bad) + " chain(s) stopped; first: chain " + std::to_string(first) + " status " + std::to_string(st[first]));
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_destroy(pdmpflux_chains_t ch) { delete ch; return PDMPFLUX_OK; }
+
+int pdmpflux_sample_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, const double* xinit,
+                             const double* vinit, uint64_t seed, int64_t chain_offset, const pdmpflux_tape* tape,
+                             const pdmpflux_history* hist, void* stream_) {
+    return pdmpflux_sample_skeleton_resume(s, n_chains, n_sk, xinit, vinit, nullptr, nullptr, 0, seed, chain_offset,
+                                           tape, hist, stream_);
+}
+
+int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, const double* xinit,
+                                    const double* vinit, const double* t0, const double* horizon0, int64_t event0,
+                                    uint64_t seed, int64_t chain_offset, const pdmpflux_tape* tape,
+                                    const pdmpflux_history* hist, void* stream_) {
+    if (!s || !hist) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
+    if (n_sk <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "n_sk must be positive. Current value: " + std::to_string(n_sk));
+    if (hist->n_cols < n_sk) return fail(PDMPFLUX_ERR_ARGUMENT, "history n_cols < n_sk");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    pdmpflux_chains_t ch = nullptr;
+    int rc = pdmpflux_chains_create(s, n_chains, xinit, vinit, hist->on_device, seed, chain_offset, tape, &ch);
+    if (rc != PDMPFLUX_OK) return rc;
+    struct Guard { pdmpflux_chains_t c; ~Guard() { pdmpflux_chains_destroy(c); } } guard{ch};
+    const int d = s->dim;
+    if (t0 || horizon0 || event0) {
+        rc = pdmpflux_chains_set_state(ch, t0, horizon0, event0, hist->on_device);
+        if (rc != PDMPFLUX_OK) return rc;
+    }
+
+    if (hist->on_device) {
+        pdmpflux_history h = *hist;
+        rc = pdmpflux_chains_record(ch, &h, 0, stream);
+        if (rc == PDMPFLUX_OK && n_sk > 1) rc = pdmpflux_chains_advance(ch, n_sk - 1, &h, 1, stream);
+        if (rc != PDMPFLUX_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (hist->status) CUDA_TRY(cudaMemcpy(hist->status, ch->status.p, sizeof(int32_t) * n_chains, cudaMemcpyDeviceToDevice));
+        if (hist->tape_pos) CUDA_TRY(cudaMemcpy(hist->tape_pos, ch->tape_pos.p, sizeof(int64_t) * 3 * n_chains, cudaMemcpyDeviceToDevice));
+        if (hist->counters) CUDA_TRY(cudaMemcpy(hist->counters, ch->counters.p, sizeof(int64_t) * 2 * n_chains, cudaMemcpyDeviceToDevice));
+        return pdmpflux_chains_status(ch, nullptr, nullptr, nullptr);
+    }
+
+    // ---- host-buffer path: slices of columns, two device slabs, D2H of slice i overlaps the kernel of slice i+1
+    const size_t per_col = (size_t)n_chains * ((hist->X ? 8 * d : 0) + (hist->V ? 8 * d : 0) + (hist->t ? 8 : 0) +
+                                               (hist->horizon ? 8 : 0) + (hist->ar ? 8 : 0) + (hist->error_value_ar ? 40 : 0) +
+                                               (hist->errored_bound ? 4 : 0) + (hist->rejected ? 4 : 0) + (hist->hitting_horizon ? 4 : 0));
+    size_t budget = 4ull << 30;  // bytes per device slab
+    if (const char* e = std::getenv("PDMPFLUX_SLAB_BYTES")) budget = std::max<size_t>(1 << 20, std::strtoull(e, nullptr, 10));
+    int64_t slice = per_col ? (int64_t)std::max<size_t>(1, budget / per_col) : n_sk;
+    slice = std::min<int64_t>(slice, n_sk);
+    if (slice < n_sk) slice = std::min<int64_t>(slice, (n_sk + 3) / 4);  // at least a few slices so copies overlap
+    slice = std::max<int64_t>(slice, 1);
+
+    struct Slab {
+        DevBuf X, V, t, horizon, ar, eva, eb, rej, hh;
+        pdmpflux_history view{};
+        cudaEvent_t done = nullptr, copied = nullptr;
+    } slab[2];
+    cudaStream_t copy_stream = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    struct SGuard { cudaStream_t s; Slab* sl; ~SGuard() { for (int i = 0; i < 2; ++i) { if (sl[i].done) cudaEventDestroy(sl[i].done); if (sl[i].copied) cudaEventDestroy(sl[i].copied); } cudaStreamDestroy(s); } } sguard{copy_stream, slab};
+    const int n_slabs = slice < n_sk ? 2 : 1;
+    for (int i = 0; i < n_slabs; ++i) {
+        Slab& b = slab[i];
+        if (hist->X) CUDA_TRY(b.X.alloc(sizeof(double) * d * n_chains * slice));
+        if (hist->V) CUDA_TRY(b.V.alloc(sizeof(double) * d * n_chains * slice));
+        if (hist->t) CUDA_TRY(b.t.alloc(sizeof(double) * n_chains * slice));
+        if (hist->horizon) CUDA_TRY(b.horizon.alloc(sizeof(double) * n_chains * slice));
+        if (hist->ar) CUDA_TRY(b.ar.alloc(sizeof(double) * n_chains * slice));
+        if (hist->error_value_ar) CUDA_TRY(b.eva.alloc(sizeof(double) * 5 * n_chains * slice));
+        if (hist->errored_bound) CUDA_TRY(b.eb.alloc(sizeof(int32_t) * n_chains * slice));
+        if (hist->rejected) CUDA_TRY(b.rej.alloc(sizeof(int32_t) * n_chains * slice));
+        if (hist->hitting_horizon) CUDA_TRY(b.hh.alloc(sizeof(int32_t) * n_chains * slice));
+        b.view.X = b.X.as<double>(); b.view.V = b.V.as<double>(); b.view.t = b.t.as<double>();
+        b.view.horizon = b.horizon.as<double>(); b.view.ar = b.ar.as<double>(); b.view.error_value_ar = b.eva.as<double>();
+        b.view.errored_bound = b.eb.as<int32_t>(); b.view.rejected = b.rej.as<int32_t>(); b.view.hitting_horizon = b.hh.as<int32_t>();
+        b.view.n_cols = slice; b.view.on_device = 1;
+        CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
+    }
+    auto copy2d = [&](void* dst, const void* src, size_t elem, int64_t k0, int64_t n) -> cudaError_t {
+        // chain c: host dst + (c*n_cols + k0)*elem  <-  device src + c*slice*elem, n*elem bytes
+        return cudaMemcpy2DAsync(static_cast<char*>(dst) + (size_t)k0 * elem, (size_t)hist->n_cols * elem, src,
+                                 (size_t)slice * elem, (size_t)n * elem, (size_t)n_chains, cudaMemcpyDeviceToHost, copy_stream);
+    };
+    int64_t k0 = 0;
+    int it = 0;
+    while (k0 < n_sk) {
+        Slab& b = slab[it % n_slabs];
+        const int64_t n = std::min<int64_t>(slice, n_sk - k0);
+        if (it >= n_slabs) CUDA_TRY(cudaStreamWaitEvent(stream, b.copied, 0));  // slab free again
+        int64_t col = 0, nev = n;
+        if (k0 == 0) {
+            rc = pdmpflux_chains_record(ch, &b.view, 0, stream);
+            if (rc != PDMPFLUX_OK) return rc;
+            col = 1; nev = n - 1;
+        }
+        if (nev > 0) {
+            rc = pdmpflux_chains_advance(ch, nev, &b.view, col, stream);
+            if (rc != PDMPFLUX_OK) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(b.done, stream));
+        CUDA_TRY(cudaStreamWaitEvent(copy_stream, b.done, 0));
+        if (hist->X) CUDA_TRY(copy2d(hist->X, b.view.X, sizeof(double) * d, k0, n));
+        if (hist->V) CUDA_TRY(copy2d(hist->V, b.view.V, sizeof(double) * d, k0, n));
+        if (hist->t) CUDA_TRY(copy2d(hist->t, b.view.t, sizeof(double), k0, n));
+        if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, b.view.horizon, sizeof(double), k0, n));
+        if (hist->ar) CUDA_TRY(copy2d(hist->ar, b.view.ar, sizeof(double), k0, n));
+        if (hist->error_value_ar) CUDA_TRY(copy2d(hist->error_value_ar, b.view.error_value_ar, sizeof(double) * 5, k0, n));
+        if (hist->errored_bound) CUDA_TRY(copy2d(hist->errored_bound, b.view.errored_bound, sizeof(int32_t), k0, n));
+        if (hist->rejected) CUDA_TRY(copy2d(hist->rejected, b.view.rejected, sizeof(int32_t), k0, n));
+        if (hist->hitting_horizon) CUDA_TRY(copy2d(hist->hitting_horizon, b.view.hitting_horizon, sizeof(int32_t), k0, n));
+        CUDA_TRY(cudaEventRecord(b.copied, copy_stream));
+        k0 += n;
+        ++it;
+    }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaStreamSynchronize(copy_stream));
+    return pdmpflux_chains_status(ch, hist->status, hist->tape_pos, hist->counters);
+}
+
+int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, const double* X,
+                                  const double* V, const double* t, int64_t N, int32_t discard_vt, double* out,
+                                  int32_t on_device, void* stream_) {
+    if (N <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "N must be positive. Current value: " + std::to_string(N));
+    if (!X || !V || !t || !out || dim <= 0 || n_sk <= 0 || n_chains <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
+    if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear) or 1 (rotation)");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int ld = discard_vt ? dim : 2 * dim + 1;
+    DevBuf dX, dV, dt, dout;
+    const double *pX = X, *pV = V, *pt = t;
+    double* po = out;
+    if (!on_device) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: no CPU fallback");
+        const size_t nx = sizeof(double) * dim * n_sk * n_chains;
+        CUDA_TRY(dX.alloc(nx)); CUDA_TRY(dV.alloc(nx)); CUDA_TRY(dt.alloc(sizeof(double) * n_sk * n_chains));
+        CUDA_TRY(dout.alloc(sizeof(double) * ld * N * n_chains));
+        CUDA_TRY(cudaMemcpyAsync(dX.p, X, nx, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dV.p, V, nx, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dt.p, t, sizeof(double) * n_sk * n_chains, cudaMemcpyHostToDevice, stream));
+        pX = dX.as<double>(); pV = dV.as<double>(); pt = dt.as<double>(); po = dout.as<double>();
+    }
+    const int64_t total = N * (int64_t)ld;
+    dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, 65535), (unsigned)n_chains);
+    if (n_chains > 65535) return fail(PDMPFLUX_ERR_UNSUPPORTED, "sample_from_skeleton: more than 65535 chains per call");
+    interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, N, discard_vt, pX, pV, pt, po);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    if (!on_device) {
+        CUDA_TRY(cudaMemcpyAsync(out, po, sizeof(double) * ld * N * n_chains, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, int64_t col_begin,
+                              const double* X, const double* V, const double* t, double* m1, double* m2, double* T,
+                              int32_t on_device, void* stream_) {
+    if (!X || !V || !t || !m1 || !m2 || dim <= 0 || n_sk <= 1 || n_chains <= 0 || col_begin < 0 || col_begin >= n_sk - 1)
+        return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevBuf dX, dV, dt, d1, d2, dT;
+    const double *pX = X, *pV = V, *pt = t;
+    double *p1 = m1, *p2 = m2, *pT = T;
+    if (!on_device) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: no CPU fallback");
+        const size_t nx = sizeof(double) * dim * n_sk * n_chains;
+        CUDA_TRY(dX.alloc(nx)); CUDA_TRY(dV.alloc(nx)); CUDA_TRY(dt.alloc(sizeof(double) * n_sk * n_chains));
+        CUDA_TRY(d1.alloc(sizeof(double) * dim * n_chains)); CUDA_TRY(d2.alloc(sizeof(double) * dim * n_chains));
+        CUDA_TRY(dT.alloc(sizeof(double) * n_chains));
+        CUDA_TRY(cudaMemcpyAsync(dX.p, X, nx, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dV.p, V, nx, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dt.p, t, sizeof(double) * n_sk * n_chains, cudaMemcpyHostToDevice, stream));
+        pX = dX.as<double>(); pV = dV.as<double>(); pt = dt.as<double>();
+        p1 = d1.as<double>(); p2 = d2.as<double>(); pT = dT.as<double>();
+    }
+    const int64_t total = n_chains * dim;
+    moments_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(flow_kind, dim, n_sk, n_chains, col_begin, pX, pV, pt, p1, p2, pT);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    if (!on_device) {
+        CUDA_TRY(cudaMemcpyAsync(m1, p1, sizeof(double) * dim * n_chains, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(m2, p2, sizeof(double) * dim * n_chains, cudaMemcpyDeviceToHost, stream));
+        if (T) CUDA_TRY(cudaMemcpyAsync(T, pT, sizeof(double) * n_chains, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(PDMPFLUX_ERR_ARGUMENT, "ptr is NULL");
+    CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return PDMPFLUX_OK;
+}
+int pdmpflux_host_free(void* ptr) {
+    CUDA_TRY(cudaFreeHost(ptr));
+    return PDMPFLUX_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,919 @@
+// Per-chain device logic of the grid-based Poisson-thinning loop.
+//
+// One *team* of TEAM consecutive lanes (TEAM = 1: thread per chain, small d; TEAM = 32: warp per chain)
+// owns one chain.  Coordinate i is owned by team lane i % TEAM; x and v live in shared memory as
+// per-thread-owned strided arrays (bank-conflict free, no cross-thread hazards), all cross-lane traffic is
+// shuffle reductions/scans, and every scalar of the thinning state machine is team-uniform in registers.
+//
+// Reference behaviour replaced (file:line relative to the reference root):
+//   build_bound      state.upper_bound_func: AbstractPDMP.jl:121-136 -> UpperBound.jl:18-36 / 92-137 / 203-247
+//   fd derivative    UpperBound.jl:50-76
+//   next_event       UpperBound.jl:264-273
+//   thinning         SamplingLoopInplace.jl:27-39, 65-217
+//   jumps            ZigZagSamplers.jl:101-107, BouncyParticleSamplers.jl:50-74,
+//                    ForwardEventChainMonteCarlo.jl:60-113,132-218, BoomerangSamplers.jl:49-67
+//   record           Composites.jl:239-260
+// Quirks of the reference are kept on purpose (SURVEY.md 8a "gotchas"); each is marked QUIRK below.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+#include "potentials.cuh"
+
+namespace pdmpflux {
+
+template <int TEAM, int SAMPLER, int POT>
+struct Chain {
+    using P = Pot<POT>;
+    static constexpr int K = P::K;
+    static constexpr int KK = K > 0 ? K : 1;
+    static constexpr bool kRot = (SAMPLER == PDMPFLUX_BOOMERANG);
+    static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG);
+
+    const KernelParams& p;
+    double* xs;  // owned coordinate j at xs[j * stride]
+    double* vs;
+    double* sc0; // scratch owned vectors (FECMC)
+    double* sc1;
+    double* sc2;
+    int stride, sstride;
+    int tl, d, nown;
+    unsigned mask;
+    int64_t chain;
+
+    double Lx[KK], Lv[KK];  // functionals of the current (x, v)
+
+    // PDMPState scalars (Composites.jl:59-83), team-uniform
+    double t, horizon, tp, ts, exp_rv, lambda_bar, ar;
+    int eb, rej, hh;
+    double eva[5];
+    bool accept;
+    int status;
+    int64_t n_builds, n_rates;
+
+    // BoundBox (Composites.jl:15-20), team-uniform, thread-local storage
+    double grid[kMaxGrid], box[kMaxGrid], cum[kMaxGrid];
+    double step;
+    int nb;
+
+    // draws
+    DrawKey key;
+    uint32_t sE, sU, sN;
+    int64_t pE, pU, pN;
+    const double *tE, *tU, *tN;
+    bool exhausted;
+
+    __device__ Chain(const KernelParams& p_) : p(p_) {}
+
+    // ------------------------------------------------------------------------------------------------
+    // draws: tape (parity mode) or Philox
+    // ------------------------------------------------------------------------------------------------
+    __device__ double rand_exp() {
+        if (p.draw_mode) return draw_exp(key, sE++);
+        if (pE >= p.nE) { exhausted = true; return 1.0; }
+        return __ldg(tE + pE++);
+    }
+    __device__ double rand_uniform() {
+        if (p.draw_mode) return draw_uniform(key, sU++);
+        if (pU >= p.nU) { exhausted = true; return 0.5; }
+        return __ldg(tU + pU++);
+    }
+    // normal number `off` of a block of `count` consecutive normals (call normals_reserve first)
+    __device__ double rand_normal_at(int64_t off) {
+        if (p.draw_mode) return draw_normal(key, sN + (uint32_t)off);
+        return exhausted ? 1.0 : __ldg(tN + pN + off);
+    }
+    __device__ void normals_reserve(int64_t count) {
+        if (!p.draw_mode && pN + count > p.nN) exhausted = true;
+    }
+    __device__ void normals_advance(int64_t count) {
+        if (p.draw_mode) sN += (uint32_t)count;
+        else if (!exhausted) pN += count;
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // helpers
+    // ------------------------------------------------------------------------------------------------
+    __device__ __forceinline__ bool owns(int j) const { return tl + TEAM * j < d; }
+    __device__ __forceinline__ int coord(int j) const { return tl + TEAM * j; }
+
+    // functionals of the current x and v (one fused multi-value reduction)
+    __device__ void compute_functionals() {
+        if constexpr (K > 0) {
+            double acc[2 * KK];
+#pragma unroll
+            for (int k = 0; k < 2 * KK; ++k) acc[k] = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    P::accum(p.pot, coord(j), xs[j * stride], acc);
+                    P::accum(p.pot, coord(j), vs[j * stride], acc + KK);
+                }
+            team_sum_n<TEAM, 2 * KK>(acc, mask);
+#pragma unroll
+            for (int k = 0; k < KK; ++k) { Lx[k] = acc[k]; Lv[k] = acc[KK + k]; }
+        }
+    }
+
+    struct Flow {  // x_t = a x + b v ; v_t = c x + e v
+        double a, b, c, e;
+    };
+    __device__ __forceinline__ Flow flow_coef(double tt) const {
+        Flow f;
+        if constexpr (kRot) {  // BoomerangSamplers.jl:31
+            double s, c;
+            sincos(tt, &s, &c);
+            f.a = c; f.b = s; f.c = -s; f.e = c;
+        } else {               // ZigZagSamplers.jl:80 (same for BPS, FECMC)
+            f.a = 1.0; f.b = tt; f.c = 0.0; f.e = 1.0;
+        }
+        return f;
+    }
+    __device__ __forceinline__ void flow_point(const Flow& f, double xi, double vi, double& xt, double& vt) const {
+        if constexpr (kRot) { xt = xi * f.a + vi * f.b; vt = xi * f.c + vi * f.e; }
+        else { xt = xi + vi * f.b; vt = vi; }
+    }
+    __device__ __forceinline__ void flow_functionals(const Flow& f, double* Lxt, double* Lvt) const {
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            if constexpr (kRot) { Lxt[k] = Lx[k] * f.a + Lv[k] * f.b; Lvt[k] = Lx[k] * f.c + Lv[k] * f.e; }
+            else { Lxt[k] = Lx[k] + Lv[k] * f.b; Lvt[k] = Lv[k]; }
+        }
+    }
+
+    __device__ void flow_inplace(double tt) {
+        const Flow f = flow_coef(tt);
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                double xt, vt;
+                flow_point(f, xs[j * stride], vs[j * stride], xt, vt);
+                xs[j * stride] = xt;
+                if constexpr (kRot) vs[j * stride] = vt;
+            }
+    }
+
+    __device__ __forceinline__ double extra_rate() const {
+        return SAMPLER == PDMPFLUX_FECMC ? 0.0 : p.refresh_rate;
+    }
+
+    // `sampler.rate` (always the unsigned rate): ZigZagSamplers.jl:83-86, BouncyParticleSamplers.jl:39-42,
+    // ForwardEventChainMonteCarlo.jl:20-23, BoomerangSamplers.jl:38-41.  Uses Lx/Lv of the current (x, v).
+    __device__ double rate_unsigned(double tt) {
+        const Flow f = flow_coef(tt);
+        double Lxt[KK], Lvt[KK];
+        flow_functionals(f, Lxt, Lvt);
+        double s = 0.0;
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                double xt, vt;
+                flow_point(f, xs[j * stride], vs[j * stride], xt, vt);
+                const double y = P::grad(p.pot, coord(j), xt, Lxt) * vt;
+                if constexpr (kZZ) s += (y > 0.0 ? y : 0.0);
+                else s += y;
+            }
+        s = team_sum<TEAM>(s, mask);
+        if constexpr (kZZ) return s;
+        else return (s > 0.0 ? s : 0.0) + extra_rate();
+    }
+
+    // range(0, stop=h, length=G) (UpperBound.jl:94,204): ~correctly rounded k*h/(G-1); last node == h
+    __device__ void make_grid(double h, int G) {
+        const double m = (double)(G - 1);
+        for (int k = 0; k < G; ++k) {
+            const double kk = (double)k;
+            const double pr = kk * h, e = fma(kk, h, -pr);
+            const double q = pr / m;
+            const double r = fma(-q, m, pr) + e;
+            grid[k] = q + r / m;
+        }
+        grid[G - 1] = h;
+    }
+
+    __device__ static __forceinline__ double clamp_pos(double pos, double stp) {
+        if (pos != pos) pos = 0.0;              // replace(NaN => 0.0)
+        return fmin(fmax(pos, 0.0), stp);       // clamp.(pos, 0, step)
+    }
+
+    // ---- vectorised (ZigZag) bound: value and d/dt of (signed_)rate_vect for one owned coordinate ----
+    __device__ __forceinline__ double vect_value(int i, double xi, double vi, double tt) const {
+        double Lxt[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
+        const double y = P::grad(p.pot, i, xi + vi * tt, Lxt) * vi;
+        return p.signed_bound ? y : (y > 0.0 ? y : 0.0);
+    }
+    __device__ __forceinline__ void vect_node(int i, double xi, double vi, double tt, double h, double& val,
+                                              double& dval) const {
+        if (p.deriv_mode == PDMPFLUX_DERIV_JVP) {
+            double Lxt[KK];
+#pragma unroll
+            for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
+            double g, hv;
+            P::eval(p.pot, i, xi + vi * tt, vi, Lxt, Lv, g, hv);
+            const double y = g * vi, dy = hv * vi;
+            if (p.signed_bound) { val = y; dval = dy; }
+            else { val = (y > 0.0 ? y : 0.0); dval = (0.0 > y) ? 0.0 : dy; }
+        } else {  // finite_difference_derivative, UpperBound.jl:50-76 with start = 0
+            val = vect_value(i, xi, vi, tt);
+            const double hh_ = kSqrtEps * fmax(1.0, fabs(tt));
+            const double xm = fmax(0.0, tt - hh_), xp = fmin(h, tt + hh_);
+            if (xp == xm) dval = val - val;
+            else {
+                const double fp = (xp == tt) ? val : vect_value(i, xi, vi, xp);
+                const double fm = (xm == tt) ? val : vect_value(i, xi, vi, xm);
+                dval = (fp - fm) / (xp - xm);
+            }
+        }
+    }
+
+    // upper_bound_grid_vect, UpperBound.jl:203-247
+    __device__ void build_bound_vect(double h) {
+        const int G = p.G;
+        make_grid(h, G);
+        step = grid[1] - grid[0];
+        nb = G;
+        for (int k0 = 0; k0 < G - 1; k0 += kChunk) {
+            const int nc = min(kChunk, G - 1 - k0);
+            double bacc[kChunk];
+#pragma unroll
+            for (int u = 0; u < kChunk; ++u) bacc[u] = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const int i = coord(j);
+                    const double xi = xs[j * stride], vi = vs[j * stride];
+                    double vl, gl;
+                    vect_node(i, xi, vi, grid[k0], h, vl, gl);
+#pragma unroll
+                    for (int u = 0; u < kChunk; ++u)
+                        if (u < nc) {
+                            double vr, gr;
+                            vect_node(i, xi, vi, grid[k0 + u + 1], h, vr, gr);
+                            // QUIRK (UpperBound.jl:229-237): the tangent intersection is computed as an ABSOLUTE
+                            // time, clamped to [0, step] and then used as an OFFSET from the left node.
+                            double pos = (vl - vr + gr * grid[k0 + u + 1] - gl * grid[k0 + u]) / (gr - gl);
+                            pos = clamp_pos(pos, step);
+                            const double inter = vl + gl * pos;
+                            bacc[u] += fmax(fmax(fmax(vl, vr), inter), 0.0);
+                            vl = vr; gl = gr;
+                        }
+                }
+            team_sum_n<TEAM, kChunk>(bacc, mask);
+#pragma unroll
+            for (int u = 0; u < kChunk; ++u)
+                if (u < nc) box[k0 + u] = bacc[u];
+        }
+        // sum_i cumsum_k(box[i,k]) * step  ==  cumsum_k(sum_i box[i,k]) * step   (UpperBound.jl:243-246)
+        double cs = 0.0;
+        cum[0] = 0.0;
+        for (int k = 0; k < G - 1; ++k) { cs += box[k]; cum[k + 1] = cs * step; }
+    }
+
+    // ---- scalar bound function: `signed_rate` / `rate` (AbstractPDMP.jl:104-112) at n <= kChunk times ----
+    // outv[u] = value, outd[u] = analytic d/dt (when want_d)
+    __device__ void scalar_nodes(const double* tt, int n, bool want_d, double* outv, double* outd) {
+        double av[kChunk], ad[kChunk];
+        Flow fl[kChunk];
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u) {
+            av[u] = 0.0; ad[u] = 0.0;
+            fl[u] = flow_coef(u < n ? tt[u] : 0.0);
+        }
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const int i = coord(j);
+                const double xi = xs[j * stride], vi = vs[j * stride];
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u)
+                    if (u < n) {
+                        double Lxt[KK], Lvt[KK];
+                        flow_functionals(fl[u], Lxt, Lvt);
+                        double xt, vt;
+                        flow_point(fl[u], xi, vi, xt, vt);
+                        if (want_d) {
+                            double g, hv;
+                            P::eval(p.pot, i, xt, vt, Lxt, Lvt, g, hv);  // dx_t/dt = v_t for both flows
+                            const double y = g * vt;
+                            double dy = hv * vt;
+                            if constexpr (kRot) dy -= g * xt;              // dv_t/dt = -x_t
+                            if constexpr (kZZ) {                           // scalar ZigZag: sum(max.(0, g.*v))
+                                av[u] += (y > 0.0 ? y : 0.0);
+                                ad[u] += (0.0 > y) ? 0.0 : dy;
+                            } else { av[u] += y; ad[u] += dy; }
+                        } else {
+                            const double y = P::grad(p.pot, i, xt, Lxt) * vt;
+                            if constexpr (kZZ) av[u] += (y > 0.0 ? y : 0.0);
+                            else av[u] += y;
+                        }
+                    }
+            }
+        team_sum_n<TEAM, kChunk>(av, mask);
+        if (want_d) team_sum_n<TEAM, kChunk>(ad, mask);
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)
+            if (u < n) {
+                if constexpr (kZZ) { outv[u] = av[u]; if (want_d) outd[u] = ad[u]; }
+                else if (p.signed_bound) { outv[u] = av[u] + extra_rate(); if (want_d) outd[u] = ad[u]; }
+                else {
+                    outv[u] = (av[u] > 0.0 ? av[u] : 0.0) + extra_rate();
+                    if (want_d) outd[u] = (0.0 > av[u]) ? 0.0 : ad[u];
+                }
+            }
+    }
+
+    // upper_bound_grid, UpperBound.jl:92-137 (vals/grads reuse box/cum as temporaries? no: separate arrays)
+    __device__ void build_bound_scalar(double h) {
+        const int G = p.G;
+        double vals[kMaxGrid], grads[kMaxGrid];
+        make_grid(h, G);
+        step = grid[1] - grid[0];
+        nb = G;
+        const bool jvp = (p.deriv_mode == PDMPFLUX_DERIV_JVP);
+        for (int k0 = 0; k0 < G; k0 += kChunk) {
+            const int n = min(kChunk, G - k0);
+            double ov[kChunk], od[kChunk];
+            scalar_nodes(grid + k0, n, jvp, ov, od);
+#pragma unroll
+            for (int u = 0; u < kChunk; ++u)
+                if (u < n) { vals[k0 + u] = ov[u]; grads[k0 + u] = jvp ? od[u] : 0.0; }
+        }
+        if (!jvp) {  // finite_difference_derivative, UpperBound.jl:50-76 (start = 0, horizon = h)
+            for (int k0 = 0; k0 < G; k0 += kChunk) {
+                const int n = min(kChunk, G - k0);
+                double tp_[kChunk], tm_[kChunk], fp[kChunk], fm[kChunk], dummy[kChunk];
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) {
+                    const double tt = (u < n) ? grid[k0 + u] : 0.0;
+                    const double hh_ = kSqrtEps * fmax(1.0, fabs(tt));
+                    tm_[u] = fmax(0.0, tt - hh_);
+                    tp_[u] = fmin(h, tt + hh_);
+                }
+                scalar_nodes(tp_, n, false, fp, dummy);
+                scalar_nodes(tm_, n, false, fm, dummy);
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u)
+                    if (u < n) {
+                        const double tt = grid[k0 + u], fx = vals[k0 + u];
+                        if (tp_[u] == tm_[u]) grads[k0 + u] = fx - fx;
+                        else {
+                            const double a = (tp_[u] == tt) ? fx : fp[u];
+                            const double b = (tm_[u] == tt) ? fx : fm[u];
+                            grads[k0 + u] = (a - b) / (tp_[u] - tm_[u]);
+                        }
+                    }
+            }
+        }
+        double cs = 0.0;
+        cum[0] = 0.0;
+        for (int k = 0; k < G - 1; ++k) {
+            double pos = (vals[k] - vals[k + 1] + grads[k + 1] * step) / (grads[k + 1] - grads[k]);
+            pos = clamp_pos(pos, step);
+            const double inter = vals[k] + grads[k] * pos;
+            double b = fmax(fmax(fmax(vals[k], vals[k + 1]), inter), 0.0);
+            b += p.bound_refresh;  // QUIRK: BPS/Boomerang signed bound counts the refresh rate twice (:131)
+            box[k] = b;
+            cs += b;
+            cum[k + 1] = cs * step;
+        }
+    }
+
+    // upper_bound_constant, UpperBound.jl:18-36: Optim.jl Brent on t -> -rate(t) over [0, h]
+    __device__ void build_bound_brent(double h) {
+        const double golden = 0.5 * (3.0 - sqrt(5.0));
+        double lo = 0.0, hi = h;
+        double x = lo + golden * (hi - lo);
+        double fx = -rate_unsigned(x);
+        double stp = 0.0, old_step = 0.0, w = x, vv = x, fw = fx, fv = fx;
+        for (int it = 0; it < 1000;) {
+            double pp = 0.0, q = 0.0;
+            const double tol = kSqrtEps * fabs(x) + kEps;
+            const double mid = (hi + lo) / 2;
+            if (fabs(x - mid) <= 2 * tol - (hi - lo) / 2) break;
+            ++it;
+            if (fabs(old_step) > tol) {
+                const double r = (x - w) * (fx - fv);
+                q = (x - vv) * (fx - fw);
+                pp = (x - vv) * q - (x - w) * r;
+                q = 2 * (q - r);
+                if (q > 0) pp = -pp; else q = -q;
+            }
+            if (fabs(pp) < fabs(q * old_step / 2) && pp < q * (hi - x) && pp < q * (x - lo)) {
+                old_step = stp;
+                stp = pp / q;
+                const double xt = x + stp;
+                if ((xt - lo) < 2 * tol || (hi - xt) < 2 * tol) stp = (x < mid) ? tol : -tol;
+            } else {
+                old_step = (x < mid) ? hi - x : lo - x;
+                stp = golden * old_step;
+            }
+            const double u = (fabs(stp) >= tol) ? x + stp : x + ((stp > 0) ? tol : -tol);
+            const double fu = -rate_unsigned(u);
+            if (fu < fx) {
+                if (u < x) hi = x; else lo = x;
+                vv = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+            } else {
+                if (u < x) lo = u; else hi = u;
+                if (fu <= fw || w == x) { vv = w; fv = fw; w = u; fw = fu; }
+                else if (fu <= fv || vv == x || vv == w) { vv = u; fv = fu; }
+            }
+        }
+        grid[0] = 0.0; grid[1] = h;
+        box[0] = -fx + 0.0;  // init_state passes no refresh here (AbstractPDMP.jl:122-125)
+        cum[0] = 0.0; cum[1] = box[0] * (h - 0.0);
+        step = h - 0.0;
+        nb = 2;
+    }
+
+    __device__ void build_bound(double h) {
+        ++n_builds;
+        if (p.G == 0) build_bound_brent(h);
+        else if (kZZ && p.vectorized) build_bound_vect(h);
+        else build_bound_scalar(h);
+    }
+
+    // next_event, UpperBound.jl:264-273
+    __device__ void next_event(double e, double& tp_out, double& lb_out) const {
+        int idx = 0;
+        while (idx < nb && cum[idx] < e) ++idx;  // searchsortedfirst
+        if (idx >= nb) { tp_out = CUDART_INF; lb_out = box[nb - 2]; return; }
+        if (idx == 0) { tp_out = CUDART_NAN; lb_out = box[0]; return; }  // e <= 0 cannot happen (randexp > 0)
+        tp_out = grid[idx - 1] + (e - cum[idx - 1]) / (cum[idx] - cum[idx - 1]) * step;
+        lb_out = box[idx - 1];
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // velocity jumps (x already moved; functionals of x are recomputed here)
+    // ------------------------------------------------------------------------------------------------
+    __device__ void jump_zigzag() {  // ZigZagSamplers.jl:101-107 + Distributions.jl categorical CDF scan
+        double S = 0.0;
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const double y = P::grad(p.pot, coord(j), xs[j * stride], Lx) * vs[j * stride];
+                S += (y > 0.0 ? y : 0.0);
+            }
+        S = team_sum<TEAM>(S, mask);
+        // isprobvec(p): all(p .>= 0) && sum(p) ~ 1, else the reference's Categorical constructor throws
+        double chk[2] = {0.0, 0.0};
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const double y = P::grad(p.pot, coord(j), xs[j * stride], Lx) * vs[j * stride];
+                const double pj = (y > 0.0 ? y : 0.0) / S;
+                if (!(pj >= 0.0)) chk[0] += 1.0;
+                chk[1] += pj;
+            }
+        team_sum_n<TEAM, 2>(chk, mask);
+        if (chk[0] > 0.0 || !(fabs(chk[1] - 1.0) <= kSqrtEps * fmax(fabs(chk[1]), 1.0))) {
+            status = PDMPFLUX_CHAIN_NOT_PROBVEC;
+            return;
+        }
+        const double u = rand_uniform();
+        // first index with cumulative p > u, else the last index
+        double carry = 0.0;
+        int m = d - 1;
+        for (int j = 0; j < nown; ++j) {
+            double pj = 0.0;
+            if (owns(j)) {
+                const double y = P::grad(p.pot, coord(j), xs[j * stride], Lx) * vs[j * stride];
+                pj = (y > 0.0 ? y : 0.0) / S;
+            }
+            const double incl = team_scan_incl<TEAM>(pj, mask, tl) + carry;
+            const bool hit = owns(j) && (incl > u);
+            int first = -1;
+            if constexpr (TEAM == 1) first = hit ? 0 : -1;
+            else {
+                unsigned b = __ballot_sync(mask, hit) & mask;
+                b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
+                first = b ? (__ffs(b) - 1) : -1;
+            }
+            if (first >= 0) { m = first + TEAM * j; break; }
+            carry = team_bcast<TEAM>(incl, TEAM - 1, mask);
+        }
+        if (m % TEAM == tl) { const int j = m / TEAM; vs[j * stride] = -vs[j * stride]; }
+    }
+
+    __device__ void jump_bps() {  // BouncyParticleSamplers.jl:50-74
+        double r2[2] = {0.0, 0.0};
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
+                r2[0] += g * vs[j * stride];
+                r2[1] += g * g;
+            }
+        team_sum_n<TEAM, 2>(r2, mask);
+        const double gv = r2[0], gg = r2[1];
+        const double bounce = (gv > 0.0 ? gv : 0.0);
+        const double prob = bounce / (bounce + p.refresh_rate);
+        const double u = rand_uniform();
+        if (u < prob) {
+            if (gg == 0) return;
+            const double scale = 2 * gv / gg;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
+                    vs[j * stride] = vs[j * stride] - scale * g;
+                }
+        } else {
+            normals_reserve(d);
+            double nn = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double z = rand_normal_at(coord(j));
+                    vs[j * stride] = z;
+                    nn += z * z;
+                }
+            normals_advance(d);
+            if (!p.gaussian_velocity) {
+                nn = sqrt(team_sum<TEAM>(nn, mask));
+                for (int j = 0; j < nown; ++j)
+                    if (owns(j)) vs[j * stride] = vs[j * stride] / nn;
+            }
+        }
+    }
+
+    __device__ void jump_boomerang() {  // BoomerangSamplers.jl:49-67
+        // QUIRK: the jump uses grad U(x) - x although the rates use grad U (BoomerangSamplers.jl:38-46 vs :51-52)
+        double r2[2] = {0.0, 0.0};
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx) - xs[j * stride];
+                r2[0] += g * vs[j * stride];
+                r2[1] += g * g;
+            }
+        team_sum_n<TEAM, 2>(r2, mask);
+        const double gv = r2[0];
+        const double bounce = (gv > 0.0 ? gv : 0.0);
+        const double prob = bounce / (bounce + p.refresh_rate);
+        const double u = rand_uniform();
+        if (u < prob) {
+            const double ng = sqrt(r2[1]);
+            double ve = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double e = (P::grad(p.pot, coord(j), xs[j * stride], Lx) - xs[j * stride]) / ng;
+                    ve += vs[j * stride] * e;
+                }
+            ve = team_sum<TEAM>(ve, mask);
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double e = (P::grad(p.pot, coord(j), xs[j * stride], Lx) - xs[j * stride]) / ng;
+                    vs[j * stride] = vs[j * stride] - 2 * ve * e;
+                }
+        } else {  // QUIRK: refresh draws from the global RNG in the reference (:65); on a tape it is the N stream
+            normals_reserve(d);
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) vs[j * stride] = rand_normal_at(coord(j));
+            normals_advance(d);
+        }
+    }
+
+    __device__ void jump_fecmc() {  // ForwardEventChainMonteCarlo.jl:132-218 (+ :60-88, :105-113)
+        const double sf = p.speed_factor;
+        const double u = rand_uniform();
+        double rho = -sqrt(1 - pow(u, 2.0 / (d - 1)));
+        if (sf != 1.0) rho = sf * rho;
+        double* vo = sc0;
+        // n = grad U(x) / |grad U(x)| (zero vector if the norm is 0)
+        double r2[2] = {0.0, 0.0};
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
+                r2[0] += g * g;
+            }
+        const double ng = sqrt(team_sum<TEAM>(r2[0], mask));
+        auto nvec = [&](int j) -> double {
+            const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
+            return ng == 0 ? 0.0 : g / ng;
+        };
+        double vn = 0.0;
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) vn += vs[j * stride] * nvec(j);
+        vn = team_sum<TEAM>(vn, mask);
+        double nvo = 0.0;
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const double o = vs[j * stride] - vn * nvec(j);
+                vo[j * sstride] = o;
+                nvo += o * o;
+            }
+        nvo = team_sum<TEAM>(nvo, mask);
+        if (sqrt(nvo) < 1e-10) {  // degenerate orthogonal part: redraw
+            normals_reserve(d);
+            double a = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double z = rand_normal_at(coord(j));
+                    vo[j * sstride] = z;
+                    a += z * nvec(j);
+                }
+            normals_advance(d);
+            a = team_sum<TEAM>(a, mask);
+            nvo = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double o = vo[j * sstride] - a * nvec(j);
+                    vo[j * sstride] = o;
+                    nvo += o * o;
+                }
+            nvo = team_sum<TEAM>(nvo, mask);
+        }
+        const double u2 = rand_uniform();
+        const double rad = (sf != 1.0) ? sqrt(sf * sf - rho * rho) : sqrt(1 - rho * rho);
+        if (u2 >= p.mix_p) {
+            const double nrm = sqrt(nvo);
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) vs[j * stride] = vo[j * sstride] / nrm * rad + rho * nvec(j);
+            return;
+        }
+        double* prop = sc1;
+        if (p.switch_) {  // _orthogonal_switch; randn(key, 2, dim) is column-major: g1[i] = N[2i], g2[i] = N[2i+1]
+            double* e1 = sc1;
+            double* e2 = sc2;
+            normals_reserve(2 * (int64_t)d);
+            double a[2] = {0.0, 0.0};
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double z1 = rand_normal_at(2 * (int64_t)coord(j));
+                    const double z2 = rand_normal_at(2 * (int64_t)coord(j) + 1);
+                    e1[j * sstride] = z1; e2[j * sstride] = z2;
+                    const double n = nvec(j);
+                    a[0] += z1 * n; a[1] += z2 * n;
+                }
+            normals_advance(2 * (int64_t)d);
+            team_sum_n<TEAM, 2>(a, mask);
+            double n1 = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double n = nvec(j);
+                    const double g1 = e1[j * sstride] - a[0] * n;
+                    e1[j * sstride] = g1;
+                    e2[j * sstride] = e2[j * sstride] - a[1] * n;
+                    n1 += g1 * g1;
+                }
+            n1 = sqrt(team_sum<TEAM>(n1, mask));
+            double b = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double q = e1[j * sstride] / n1;
+                    e1[j * sstride] = q;
+                    b += e2[j * sstride] * q;
+                }
+            b = team_sum<TEAM>(b, mask);
+            double n2 = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double q = e2[j * sstride] - b * e1[j * sstride];
+                    e2[j * sstride] = q;
+                    n2 += q * q;
+                }
+            n2 = sqrt(team_sum<TEAM>(n2, mask));
+            double c[2] = {0.0, 0.0};
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double q = e2[j * sstride] / n2;
+                    e2[j * sstride] = q;
+                    c[0] += vo[j * sstride] * e1[j * sstride];
+                    c[1] += vo[j * sstride] * q;
+                }
+            team_sum_n<TEAM, 2>(c, mask);
+            double ct = 0.0, st = 0.0;
+            if (p.ran_p) {
+                const double th = rand_uniform() * 2 * 3.14159265358979323846;
+                sincos(th, &st, &ct);
+            }
+            double r3[2] = {0.0, 0.0};  // <vo, prop>, <prop, prop>
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double q1 = e1[j * sstride], q2 = e2[j * sstride], o = vo[j * sstride];
+                    const double vr = o - c[0] * q1 - c[1] * q2;
+                    double pr;
+                    if (p.ran_p) pr = vr + (ct * q1 + st * q2) * c[0] + (st * q1 - ct * q2) * c[1];
+                    else pr = vr + q2 * c[0] + q1 * c[1];
+                    prop[j * sstride] = pr;  // prop aliases e1: e1[j] is dead from here on
+                    r3[0] += o * pr;
+                    r3[1] += pr * pr;
+                }
+            team_sum_n<TEAM, 2>(r3, mask);
+            double sgn = 1.0;
+            if (p.positive) sgn = (r3[0] > 0) ? 1.0 : ((r3[0] < 0) ? -1.0 : r3[0]);  // sign(0)=0, sign(NaN)=NaN
+            const double nrm = sqrt(r3[1] * (sgn * sgn));
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) vs[j * stride] = (prop[j * sstride] * sgn) / nrm * rad + rho * nvec(j);
+        } else {  // _full_refresh
+            normals_reserve(d);
+            double nw = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double z = rand_normal_at(coord(j));
+                    prop[j * sstride] = z;
+                    nw += z * z;
+                }
+            normals_advance(d);
+            nw = sqrt(team_sum<TEAM>(nw, mask));
+            double a = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double q = prop[j * sstride] / nw;
+                    prop[j * sstride] = q;
+                    a += q * nvec(j);
+                }
+            a = team_sum<TEAM>(a, mask);
+            double np_ = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double q = prop[j * sstride] - a * nvec(j);
+                    prop[j * sstride] = q;
+                    np_ += q * q;
+                }
+            np_ = sqrt(team_sum<TEAM>(np_, mask));
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) vs[j * stride] = prop[j * sstride] / np_ * rad + rho * nvec(j);
+        }
+    }
+
+    __device__ void velocity_jump() {
+        // functionals of the moved x (v's are refreshed by the next compute_functionals before a bound build)
+        compute_functionals();
+        if constexpr (SAMPLER == PDMPFLUX_ZIGZAG) jump_zigzag();
+        else if constexpr (SAMPLER == PDMPFLUX_BPS) jump_bps();
+        else if constexpr (SAMPLER == PDMPFLUX_FECMC) jump_fecmc();
+        else jump_boomerang();
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // thinning state machine: SamplingLoopInplace.jl
+    // ------------------------------------------------------------------------------------------------
+    __device__ void one_step_of_thinning() {  // :65-85
+        compute_functionals();
+        build_bound(horizon);
+        const double e = rand_exp();
+        next_event(e, tp, lambda_bar);
+        exp_rv = e;
+        if (tp > horizon) {  // move_to_horizon!, :87-101
+            flow_inplace(horizon);
+            ts += horizon;
+            hh += 1;
+            horizon = p.adaptive ? horizon * 1.01 : horizon;
+            return;
+        }
+        accept = false;  // moves_until_horizon!, :103-111
+        while (tp < horizon && !accept && status == 0 && !exhausted) {
+            // ac_step!, :113-129
+            ++n_rates;
+            const double lt = rate_unsigned(tp);
+            ar = lt / lambda_bar;
+            if (ar > 1.0) {  // erroneous_acceptance_rate!, :131-151
+                const double h2 = horizon / 2;
+                build_bound(h2);
+                const double e2 = rand_exp();
+                next_event(e2, tp, lambda_bar);
+                exp_rv = e2;
+                // QUIRK: a non-adaptive chain keeps the full horizon although the live bound covers half of it
+                horizon = p.adaptive ? h2 : horizon;
+                eb += 1;
+                eva[eb % 5] = ar;
+            } else {  // ac_step_with_proxy!, :153-168
+                accept = rand_uniform() < ar;
+                if (accept) {  // if_accept!, :170-186
+                    flow_inplace(tp);
+                    velocity_jump();
+                    t = t + tp + ts;
+                    ts = 0.0;
+                    tp = 0.0;
+                } else {  // if_reject!, :188-203
+                    const double e3 = exp_rv + rand_exp();
+                    next_event(e3, tp, lambda_bar);
+                    horizon = p.adaptive ? horizon / 1.04 : horizon;  // QUIRK: shrink before the horizon check
+                    exp_rv = e3;
+                    rej += 1;
+                    if (tp > horizon) {  // move_to_horizon2!, :205-217 (no horizon growth here)
+                        flow_inplace(horizon);
+                        ts += horizon;
+                        hh += 1;
+                    }
+                }
+            }
+        }
+    }
+
+    __device__ void get_event_state() {  // :27-39
+        eb = 0; rej = 0; hh = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) eva[k] = 0.0;
+        int steps = 0;
+        accept = false;
+        while (!accept) {
+            one_step_of_thinning();
+            if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; return; }
+            if (status != 0) return;
+            if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; return; }
+        }
+    }
+
+    // record!, Composites.jl:239-260 (chain-major slabs)
+    __device__ void record(int64_t c_local_global, int64_t col) {
+        const int64_t o = c_local_global * p.ld_cols + col;
+        if (p.X)
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) p.X[o * d + coord(j)] = xs[j * stride];
+        if (p.V)
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) p.V[o * d + coord(j)] = vs[j * stride];
+        if (tl == 0) {
+            if (p.T) p.T[o] = t;
+            if (p.H) p.H[o] = horizon;
+            if (p.AR) p.AR[o] = ar;
+            if (p.EB) p.EB[o] = eb;
+            if (p.REJ) p.REJ[o] = rej;
+            if (p.HH) p.HH[o] = hh;
+            if (p.EVA) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) p.EVA[o * 5 + k] = eva[k];
+            }
+        }
+    }
+};
+
+// One launch advances every chain by p.n_events accepted events (or just records the current state when
+// n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
+template <int TEAM, int SAMPLER, int POT>
+__global__ void __launch_bounds__(kBlockThreads) skeleton_kernel(const KernelParams p) {
+    extern __shared__ double smem[];
+    constexpr int CPB = kBlockThreads / TEAM;  // chains per block
+    const int c_local = threadIdx.x / TEAM;
+    const int64_t c = (int64_t)blockIdx.x * CPB + c_local;
+    if (c >= p.n_chains) return;  // teams never synchronise across the block
+
+    Chain<TEAM, SAMPLER, POT> ch(p);
+    ch.tl = threadIdx.x % TEAM;
+    ch.mask = team_mask<TEAM>();
+    ch.d = p.d;
+    ch.nown = p.n_own;
+    ch.chain = c;
+    ch.stride = kBlockThreads;
+    ch.xs = smem + threadIdx.x;
+    ch.vs = smem + (size_t)p.n_own * kBlockThreads + threadIdx.x;
+    if (p.scratch_in_smem) {
+        ch.sstride = kBlockThreads;
+        double* base = smem + 2 * (size_t)p.n_own * kBlockThreads + threadIdx.x;
+        ch.sc0 = base;
+        ch.sc1 = base + (size_t)p.n_own * kBlockThreads;
+        ch.sc2 = base + 2 * (size_t)p.n_own * kBlockThreads;
+    } else {
+        ch.sstride = kBlockThreads;
+        double* base = p.scratch ? p.scratch + (size_t)blockIdx.x * 3 * p.n_own * kBlockThreads + threadIdx.x : nullptr;
+        ch.sc0 = base;
+        ch.sc1 = base + (size_t)p.n_own * kBlockThreads;
+        ch.sc2 = base + 2 * (size_t)p.n_own * kBlockThreads;
+    }
+    // load PDMPState
+    for (int j = 0; j < ch.nown; ++j)
+        if (ch.owns(j)) {
+            ch.xs[j * ch.stride] = p.sx[c * p.d + ch.coord(j)];
+            ch.vs[j * ch.stride] = p.sv[c * p.d + ch.coord(j)];
+        }
+    ch.t = p.st[c];
+    ch.horizon = p.shorizon[c];
+    ch.ar = p.sar[c];
+    ch.tp = 0.0; ch.ts = 0.0; ch.exp_rv = 0.0; ch.lambda_bar = 0.0;
+    ch.eb = 0; ch.rej = 0; ch.hh = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) ch.eva[k] = 0.0;
+    ch.accept = false;
+    ch.status = p.status[c];
+    ch.n_builds = p.counters[2 * c];
+    ch.n_rates = p.counters[2 * c + 1];
+    ch.exhausted = false;
+    const uint64_t gchain = (uint64_t)(p.chain_offset + c);
+    ch.key.k0 = (uint32_t)p.seed; ch.key.k1 = (uint32_t)(p.seed >> 32);
+    ch.key.chain_lo = (uint32_t)gchain; ch.key.chain_hi8 = (uint32_t)(gchain >> 32) << 8;
+    ch.tE = p.tE + c * p.nE; ch.tU = p.tU + c * p.nU; ch.tN = p.tN + c * p.nN;
+    ch.pE = p.tape_pos[3 * c]; ch.pU = p.tape_pos[3 * c + 1]; ch.pN = p.tape_pos[3 * c + 2];
+
+    if (p.n_events == 0) {
+        ch.record(c, p.col0);
+        return;
+    }
+    if (ch.status == 0) {
+        for (int64_t ev = 0; ev < p.n_events; ++ev) {
+            ch.key.event = (uint32_t)(p.event0 + ev + 1);
+            ch.sE = ch.sU = ch.sN = 0;
+            ch.get_event_state();
+            if (ch.status != 0) break;
+            ch.record(c, p.col0 + ev);
+        }
+    }
+    // store PDMPState
+    for (int j = 0; j < ch.nown; ++j)
+        if (ch.owns(j)) {
+            p.sx[c * p.d + ch.coord(j)] = ch.xs[j * ch.stride];
+            p.sv[c * p.d + ch.coord(j)] = ch.vs[j * ch.stride];
+        }
+    if (ch.tl == 0) {
+        p.st[c] = ch.t;
+        p.shorizon[c] = ch.horizon;
+        p.sar[c] = ch.ar;
+        p.status[c] = ch.status;
+        p.counters[2 * c] = ch.n_builds;
+        p.counters[2 * c + 1] = ch.n_rates;
+        p.tape_pos[3 * c] = ch.pE; p.tape_pos[3 * c + 1] = ch.pU; p.tape_pos[3 * c + 2] = ch.pN;
+    }
+}
+
+}  // namespace pdmpflux

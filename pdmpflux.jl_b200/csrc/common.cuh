@@ -1,0 +1,106 @@
+// Shared declarations for the thinning kernels: launch parameters, team (sub-warp) collectives.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/pdmpflux_cuda.h"
+
+namespace pdmpflux {
+
+constexpr int kBlockThreads = 128;
+constexpr int kMaxGrid = 64;        // largest supported grid_size (per-thread local arrays)
+constexpr int kChunk = 8;           // grid nodes / cells processed per register chunk
+constexpr double kSqrtEps = 1.4901161193847656e-08;
+constexpr double kEps = 2.220446049250313e-16;
+
+// Device-side potential parameters (owned by pdmpflux_potential_s).
+struct PotParams {
+    const double* vec;   // GAUSS_DIAG: p[d]; GAUSS_DENSE: P[d*d]; LOGREG: X[n*d]
+    const double* vec2;  // LOGREG: y[n]
+    double alpha, beta;  // GAUSS_EQUICORR
+    double inv_s2;       // LOGREG prior precision
+    int64_t n;           // LOGREG rows
+};
+
+// Everything a skeleton launch needs; passed by value (constant bank).
+struct KernelParams {
+    // sampler config after constructor rewrites
+    int d, G, vectorized, signed_bound, adaptive, deriv_mode;
+    int gaussian_velocity, ran_p, switch_, positive, max_steps;
+    double tmax, refresh_rate, bound_refresh, mix_p, speed_factor;
+    PotParams pot;
+    // chains
+    int64_t n_chains, chain_offset;
+    uint64_t seed;
+    int64_t event0;    // events already generated per chain (the next event has index event0+1)
+    int64_t n_events;  // events to generate in this launch
+    // PDMPState arrays (in/out)
+    double* sx;        // [C][d]
+    double* sv;        // [C][d]
+    double* st;        // [C]
+    double* shorizon;  // [C]
+    double* sar;       // [C] last acceptance ratio (recorded in column 0 as 0)
+    int64_t* tape_pos; // [C][3]
+    int32_t* status;   // [C]
+    int64_t* counters; // [C][2]
+    // draws
+    int draw_mode;  // 0 tape, 1 philox
+    const double *tE, *tU, *tN;
+    int64_t nE, nU, nN;
+    // outputs (any may be null)
+    double *X, *V, *T, *H, *AR, *EVA;
+    int32_t *EB, *REJ, *HH;
+    int64_t ld_cols, col0;
+    // per-block scratch vectors in global memory (used when they do not fit in shared memory)
+    double* scratch;
+    int scratch_in_smem;
+    int n_own;  // ceil(d / TEAM)
+};
+
+// ---- team collectives: TEAM consecutive lanes of a warp cooperate on one chain --------------------------
+template <int TEAM>
+__device__ __forceinline__ unsigned team_mask() {
+    if constexpr (TEAM == 32) return 0xffffffffu;
+    else {
+        const unsigned lane = threadIdx.x & 31u;
+        return ((1u << TEAM) - 1u) << (lane & ~(unsigned)(TEAM - 1));
+    }
+}
+
+template <int TEAM>
+__device__ __forceinline__ double team_sum(double v, unsigned mask) {
+#pragma unroll
+    for (int o = TEAM / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;  // butterfly: bitwise identical in every lane of the team
+}
+
+template <int TEAM, int N>
+__device__ __forceinline__ void team_sum_n(double (&v)[N], unsigned mask) {
+    if constexpr (TEAM > 1) {
+#pragma unroll
+        for (int o = TEAM / 2; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(mask, v[i], o);
+        }
+    }
+}
+
+// inclusive scan over the team's lanes (in lane order)
+template <int TEAM>
+__device__ __forceinline__ double team_scan_incl(double v, unsigned mask, int tl) {
+#pragma unroll
+    for (int o = 1; o < TEAM; o <<= 1) {
+        const double u = __shfl_up_sync(mask, v, o, TEAM);
+        if (tl >= o) v += u;
+    }
+    return v;
+}
+
+template <int TEAM>
+__device__ __forceinline__ double team_bcast(double v, int src_tl, unsigned mask) {
+    if constexpr (TEAM == 1) return v;
+    else return __shfl_sync(mask, v, src_tl, TEAM);
+}
+
+}  // namespace pdmpflux

@@ -1,0 +1,11 @@
+// Instantiations of the thinning kernel for the fecmc sampler (one translation unit per sampler so the
+// build parallelises).  See chain.cuh for the device logic and the reference lines it replaces.
+#include "chain.cuh"
+#include "launch.cuh"
+
+namespace pdmpflux {
+cudaError_t launch_skeleton_fecmc(int team, int pot, const KernelParams& p, unsigned grid, size_t smem,
+                                 cudaStream_t stream) {
+    return launch_for_sampler<PDMPFLUX_FECMC>(team, pot, p, grid, smem, stream);
+}
+}  // namespace pdmpflux

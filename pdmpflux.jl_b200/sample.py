@@ -1,0 +1,132 @@
+"""Drivers with the reference's names: sample_skeleton, sample_from_skeleton, sample (src/sample.jl:27-58,
+253-284, 475-513), plus the batched (many independent chains) forms the GPU path exists for."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from .history import PDMPHistory, PDMPHistoryBatch
+from .samplers import AbstractPDMP
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _make_tape(tape, n_chains):
+    if tape is None:
+        return None, None
+    E, U, N = (np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in tape)
+    for a in (E, U, N):
+        if a.shape[0] != n_chains:
+            raise _lib.DimensionMismatch("tape streams must have one row per chain")
+    t = _lib.Tape(_ptr(E), _ptr(U), _ptr(N), E.shape[1], U.shape[1], N.shape[1], 0)
+    return t, (E, U, N)
+
+
+def _init_arrays(sampler, xinit, vinit):
+    scalar = np.isscalar(xinit) and np.isscalar(vinit)
+    if scalar:  # src/sample.jl:289-319: scalar initial values are wrapped into 1-vectors
+        if not (math.isfinite(xinit) and math.isfinite(vinit)):
+            raise _lib.ArgumentError("Initial position and velocity must be finite numbers")
+        xinit, vinit = [float(xinit)], [float(vinit)]
+    x = np.ascontiguousarray(xinit, dtype=np.float64)
+    v = np.ascontiguousarray(vinit, dtype=np.float64)
+    batched = x.ndim == 2
+    x2, v2 = np.atleast_2d(x), np.atleast_2d(v)
+    if x2.shape[1] != sampler.dim or v2.shape[1] != sampler.dim or x2.shape != v2.shape:
+        raise _lib.DimensionMismatch(
+            f"xinit and vinit must have the same dimension as pdmp.dim ({sampler.dim}). Current dimensions: "
+            f"xinit ({x2.shape[1]}), vinit ({v2.shape[1]})")
+    return x2, v2, batched
+
+
+def sample_skeleton(sampler: AbstractPDMP, n_sk, xinit, vinit, *, seed=None, verbose=True, tape=None,
+                    chain_offset=0, batch=None, t0=None, horizon0=None, event0=0):
+    """sample_skeleton(sampler, n_sk, xinit, vinit; seed, verbose) (src/sample.jl:253-284).
+
+    xinit/vinit of shape (d,) run one chain and return a `PDMPHistory` (reference semantics); shape (C, d)
+    runs C independent chains and returns a `PDMPHistoryBatch` (chain c = Philox stream chain_offset + c).
+    `tape=(E, U, N)` injects the random draws (parity testing); otherwise draws are Philox(seed, chain, event).
+    `t0`, `horizon0` (per chain) and `event0` resume from a saved state (the last column of an earlier
+    history) instead of init_state; column 0 of the result is then that state.
+    """
+    if not isinstance(n_sk, (int, np.integer)):
+        raise TypeError("n_sk must be an integer")
+    if n_sk <= 0:
+        raise _lib.ArgumentError(f"n_sk must be positive. Current value: {n_sk}")
+    x, v, batched = _init_arrays(sampler, xinit, vinit)
+    if batch is not None:
+        batched = batch
+    n_chains = x.shape[0]
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    hb = PDMPHistoryBatch(n_chains, int(n_sk), sampler.dim)
+    view = _lib.History(_ptr(hb.X), _ptr(hb.V), _ptr(hb.t), _ptr(hb.horizon), _ptr(hb.ar), _ptr(hb.error_value_ar),
+                        _ptr(hb.errored_bound), _ptr(hb.rejected), _ptr(hb.hitting_horizon), _ptr(hb.status),
+                        _ptr(hb.tape_pos), _ptr(hb.counters), int(n_sk), 0)
+    t, keep = _make_tape(tape, n_chains)
+    t0a = None if t0 is None else np.ascontiguousarray(np.broadcast_to(t0, (n_chains,)), dtype=np.float64)
+    h0a = None if horizon0 is None else np.ascontiguousarray(np.broadcast_to(horizon0, (n_chains,)), dtype=np.float64)
+    rc = _lib.lib().pdmpflux_sample_skeleton_resume(sampler._handle, n_chains, int(n_sk), _ptr(x), _ptr(v),
+                                                    _ptr(t0a), _ptr(h0a), int(event0),
+                                                    C.c_uint64(int(seed) & (2**64 - 1)), int(chain_offset),
+                                                    C.byref(t) if t is not None else None, C.byref(view), None)
+    sampler.state = hb.status.copy()
+    _lib.check(rc, hb.status)
+    return hb if batched else hb.chain(0)
+
+
+def _as_batch_arrays(history):
+    if isinstance(history, PDMPHistoryBatch):
+        return history.X, history.V, history.t
+    # PDMPHistory: X is (d, n) like the Julia matrix -> chain-major slab (1, n, d)
+    return (np.ascontiguousarray(history.X.T)[None], np.ascontiguousarray(history.V.T)[None],
+            np.ascontiguousarray(history.t)[None])
+
+
+def sample_from_skeleton(sampler: AbstractPDMP, N, history, *, discard_vt=True):
+    """sample_from_skeleton(sampler, N, history; discard_vt) (src/sample.jl:475-513).  Returns a (d, N) array
+    (or (2d+1, N)) for a `PDMPHistory`, like the reference's Matrix; (C, N, d) for a batch."""
+    if N <= 0:
+        raise _lib.ArgumentError(f"N must be positive. Current value: {N}")
+    X, V, t = _as_batch_arrays(history)
+    n_chains, n_sk, d = X.shape
+    ld = d if discard_vt else 2 * d + 1
+    out = np.empty((n_chains, int(N), ld))
+    _lib.check(_lib.lib().pdmpflux_sample_from_skeleton(sampler.flow_kind, d, n_sk, n_chains, _ptr(X), _ptr(V), _ptr(t),
+                                                        int(N), int(bool(discard_vt)), _ptr(out), 0, None))
+    return out if isinstance(history, PDMPHistoryBatch) else out[0].T
+
+
+def sample(sampler: AbstractPDMP, N_sk, N_samples, xinit, vinit, *, seed=None, verbose=True, discard_vt=True):
+    """sample(sampler, N_sk, N_samples, xinit, vinit; seed) = sample_from_skeleton o sample_skeleton
+    (src/sample.jl:27-58)."""
+    history = sample_skeleton(sampler, N_sk, xinit, vinit, seed=seed, verbose=verbose)
+    return sample_from_skeleton(sampler, N_samples, history, discard_vt=discard_vt)
+
+
+def skeleton_moments(sampler: AbstractPDMP, history, burn_in_cols=0):
+    """Per-chain time averages of x and x^2 over the skeleton (closed-form segment integrals on the device).
+    Returns (mean[C, d], second_moment[C, d], T[C]).  No reference equivalent (ESS inputs)."""
+    X, V, t = _as_batch_arrays(history)
+    n_chains, n_sk, d = X.shape
+    m1 = np.empty((n_chains, d)); m2 = np.empty((n_chains, d)); T = np.empty(n_chains)
+    _lib.check(_lib.lib().pdmpflux_skeleton_moments(sampler.flow_kind, d, n_sk, n_chains, int(burn_in_cols), _ptr(X),
+                                                    _ptr(V), _ptr(t), _ptr(m1), _ptr(m2), _ptr(T), 0, None))
+    return m1 / T[:, None], m2 / T[:, None], T
+
+
+def ess_from_chain_means(mean, second):
+    """Cross-chain ESS per coordinate: with m_{c,i} chain c's time average of x_i and
+    Var_pi(x_i) the pooled marginal variance, ESS_i per chain = Var_pi(x_i) / Var_c(m_{c,i}); the total is C
+    times that.  Returns (ess_x[d], ess_x2[d]) totals over all chains."""
+    C_ = mean.shape[0]
+    pooled_mean = mean.mean(axis=0)
+    pooled_var = second.mean(axis=0) - pooled_mean**2
+    ess_x = C_ * pooled_var / mean.var(axis=0, ddof=1)
+    return ess_x, pooled_var

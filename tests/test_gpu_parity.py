@@ -1,0 +1,254 @@
+"""GPU parity tests: libpdmpflux_cuda.so (through the C ABI / pdmpflux_b200) against the CPU oracle.
+
+Parity tiers (DESIGN.md "Parity"):
+  * one-step (teacher-forced): every event k of every case is regenerated on the GPU from the oracle's state
+    k-1 and tape cursor; JVP/grid bounds must match to 1e-10 relative (north_star tolerance), Brent and
+    finite-difference modes to 1e-6 (they amplify last-bit summation-order differences by 1/sqrt(eps)).
+    Velocity signs, rejected / hitting_horizon / errored_bound counters and draw consumption are exact.
+  * free-running: same init + tape for the whole skeleton; held to 1e-10 over 10^4 events for the
+    non-chaotic configurations (ZigZag on Gaussians, the README config C1).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_c as oc
+from oracle_cases import CASES, case_inputs, pot_params, tier_tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+def _potential(p, kind, pp):
+    return {0: lambda: p.GaussStd(), 1: lambda: p.GaussDiag(pp), 2: lambda: p.GaussEquicorr(pp[0]),
+            3: lambda: p.Banana(), 4: lambda: p.BananaReadmeScalar()}[kind]()
+
+
+def make_sampler(p, sampler, pk, pp, d, kw):
+    kw = dict(kw)
+    ad = "ForwardDiff" if kw.pop("deriv_mode", 0) == 0 else "FiniteDiff"
+    pot = _potential(p, pk, pp)
+    if sampler == 0:
+        return p.ZigZag(d, pot, AD_backend=ad, **kw)
+    if sampler == 1:
+        if "gaussian_velocity" in kw:
+            kw["Gaussian_velocity"] = kw.pop("gaussian_velocity")
+        return p.BPS(d, pot, AD_backend=ad, **kw)
+    if sampler == 2:
+        return p.ForwardECMC(d, pot, AD_backend=ad, **kw)
+    return p.Boomerang(d, pot, AD_backend=ad, **kw)
+
+
+def relerr(a, b):
+    scale = max(np.max(np.abs(a)), np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+@pytest.fixture(scope="module")
+def p():
+    import pdmpflux_b200
+    n = __import__("ctypes").c_int(0)
+    pdmpflux_b200.lib().pdmpflux_device_count(__import__("ctypes").byref(n))
+    assert n.value > 0, "GPU tests need a CUDA device"
+    return pdmpflux_b200
+
+
+def set_team(team):
+    if team:
+        os.environ["PDMPFLUX_TEAM"] = str(team)
+    else:
+        os.environ.pop("PDMPFLUX_TEAM", None)
+
+
+@pytest.mark.parametrize("team", [1, 8, 32])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_one_step_parity(p, case, team):
+    name, sampler, pk, pp, d, kw, n_sk = case
+    if team == 1 and d > 100:
+        pytest.skip("thread-per-chain is for small d")
+    pp = pot_params(pp, d)
+    x0, v0, (E, U, N) = case_inputs(name, sampler, d, n_sk)
+    r = oc.sample_skeleton(oc.make_cfg(sampler, pk, d, pp, **kw), n_sk, x0, v0, tape=(E, U, N))
+    assert r.status[0] == oc.ST_OK
+    n = n_sk - 1
+    pos = r.tape_pos[0]                       # cursor after event k
+    use = np.diff(pos, axis=0)                # draws consumed by event k+1
+    wE, wU, wN = (int(use[:, i].max()) + 1 for i in range(3))
+    idx = lambda start, w: start[:, None] + np.arange(w)[None, :]
+    pad = lambda a, w: np.concatenate([a, np.ones(w)])
+    tE = pad(E[0], wE)[idx(pos[:-1, 0], wE)]
+    tU = pad(U[0], wU)[idx(pos[:-1, 1], wU)]
+    tN = pad(N[0], wN)[idx(pos[:-1, 2], wN)]
+    s = make_sampler(p, sampler, pk, pp, d, kw)
+    set_team(team)
+    try:
+        h = p.sample_skeleton(s, 2, r.X[0, :-1], r.V[0, :-1], tape=(tE, tU, tN), t0=r.t[0, :-1],
+                              horizon0=r.horizon[0, :-1], batch=True)
+    finally:
+        set_team(None)
+    tol = tier_tolerance(kw)
+    assert np.array_equal(h.X[:, 0], r.X[0, :-1]) and np.array_equal(h.t[:, 0], r.t[0, :-1])
+    scale_x = np.maximum(np.abs(r.X[0, 1:]).max(axis=1), 1e-300)
+    ex = (np.abs(h.X[:, 1] - r.X[0, 1:]).max(axis=1) / scale_x).max()
+    scale_v = np.abs(r.V[0, 1:]).max(axis=1)
+    ev = (np.abs(h.V[:, 1] - r.V[0, 1:]).max(axis=1) / scale_v).max()
+    dt_o = r.t[0, 1:] - r.t[0, :-1]
+    et = (np.abs((h.t[:, 1] - h.t[:, 0]) - dt_o) / dt_o).max()
+    eh = (np.abs(h.horizon[:, 1] - r.horizon[0, 1:]) / r.horizon[0, 1:]).max()
+    ea = np.abs(h.ar[:, 1] - r.ar[0, 1:]).max()
+    assert max(ex, ev, et, eh, ea) < tol, dict(x=ex, v=ev, t=et, horizon=eh, ar=ea)
+    assert np.array_equal(np.sign(h.V[:, 1]), np.sign(r.V[0, 1:]))
+    assert np.array_equal(h.rejected[:, 1], r.rejected[0, 1:])
+    assert np.array_equal(h.hitting_horizon[:, 1], r.hitting_horizon[0, 1:])
+    assert np.array_equal(h.errored_bound[:, 1], r.errored_bound[0, 1:])
+    assert np.allclose(h.error_value_ar[:, 1], r.error_value_ar[0, 1:], rtol=tol, atol=0)
+    assert np.array_equal(h.tape_pos, use)
+    assert h.counters[:, 0].sum() == r.counters[0, 0] and h.counters[:, 1].sum() == r.counters[0, 1]
+
+
+FREE_RUNNING = [
+    # name, sampler, pot, pp, d, kw, n_sk, teams
+    ("C1_zigzagAD_gauss10_1e4", 0, 0, None, 10, dict(), 10001),
+    ("zz_gauss10_unsigned", 0, 0, None, 10, dict(signed_bound=False), 3001),
+    ("zz_diag70", 0, 1, "linspace", 70, dict(), 3001),
+    ("zz_equicorr33_nonadaptive", 0, 2, [0.5], 33, dict(grid_size=5, adaptive=False, tmax=0.3), 3001),
+]
+
+
+@pytest.mark.parametrize("team", [1, 8, 32])
+@pytest.mark.parametrize("case", FREE_RUNNING, ids=[c[0] for c in FREE_RUNNING])
+def test_free_running_parity(p, case, team):
+    """north_star: with injected draws, event times / positions / velocities match the Float64 reference path to
+    1e-10 relative for the first 10^4 events, velocity signs bit-exact."""
+    name, sampler, pk, pp, d, kw, n_sk = case
+    pp = pot_params(pp, d)
+    nch = 3
+    x0, v0, (E, U, N) = case_inputs(name, sampler, d, n_sk, n_chains=nch)
+    r = oc.sample_skeleton(oc.make_cfg(sampler, pk, d, pp, **kw), n_sk, x0, v0, tape=(E, U, N))
+    assert (r.status == 0).all()
+    s = make_sampler(p, sampler, pk, pp, d, kw)
+    set_team(team)
+    try:
+        h = p.sample_skeleton(s, n_sk, x0, v0, tape=(E, U, N))
+    finally:
+        set_team(None)
+    for c in range(nch):
+        assert relerr(h.X[c], r.X[c]) < 1e-10 and relerr(h.t[c], r.t[c]) < 1e-10
+        assert relerr(h.horizon[c], r.horizon[c]) < 1e-10 and relerr(h.ar[c], r.ar[c]) < 1e-10
+        assert np.array_equal(h.V[c], r.V[c])  # ZigZag velocities are +-1: bit-exact
+    assert np.array_equal(h.rejected, r.rejected) and np.array_equal(h.hitting_horizon, r.hitting_horizon)
+    assert np.array_equal(h.errored_bound, r.errored_bound) and np.array_equal(h.tape_pos, r.tape_used)
+    assert np.array_equal(h.counters, r.counters)
+
+
+def test_philox_mode_matches_oracle_draw_spec(p):
+    """Without a tape both sides draw from Philox4x32-10(seed, chain, event): the GPU run must track the CPU
+    oracle (differences only from device libm ulps in log/sincos)."""
+    d, n_sk, nch = 10, 2001, 5
+    x0 = np.zeros((nch, d)); v0 = np.ones((nch, d))
+    r = oc.sample_skeleton(oc.make_cfg(0, 0, d), n_sk, x0, v0, seed=2024, chain_offset=7)
+    s = p.ZigZagAD(d, p.GaussStd())
+    h = p.sample_skeleton(s, n_sk, x0, v0, seed=2024, chain_offset=7)
+    assert relerr(h.X, r.X) < 1e-9 and relerr(h.t, r.t) < 1e-9 and np.array_equal(h.V, r.V)
+    # chain streams are keyed by the global chain id: shard [2:4] of the same run is reproduced exactly
+    h2 = p.sample_skeleton(s, n_sk, x0[2:4], v0[2:4], seed=2024, chain_offset=9)
+    assert np.array_equal(h2.X, h.X[2:4]) and np.array_equal(h2.t, h.t[2:4])
+    # BPS refresh (normals) and FECMC switch (2d normals) also follow the spec
+    for sampler, kw, mk in ((1, dict(tmax=1.0, refresh_rate=0.5), lambda: p.BPS(d, p.GaussStd(), refresh_rate=0.5)),
+                            (2, dict(), lambda: p.ForwardECMC(d, p.GaussStd()))):
+        v1 = v0 / np.sqrt(d)
+        r = oc.sample_skeleton(oc.make_cfg(sampler, 0, d, **kw), 60, x0, v1, seed=11)
+        h = p.sample_skeleton(mk(), 60, x0, v1, seed=11)
+        assert relerr(h.X[:, :40], r.X[:, :40]) < 1e-7 and relerr(h.t[:, :40], r.t[:, :40]) < 1e-7
+
+
+def test_resume_and_host_slicing_are_bit_identical(p):
+    d, n_sk, nch = 6, 401, 9
+    g = np.random.default_rng(3)
+    x0 = g.standard_normal((nch, d)); v0 = g.standard_normal((nch, d)); v0 /= np.linalg.norm(v0, axis=1, keepdims=True)
+    s = p.BPS(d, p.Banana(), refresh_rate=0.3)
+    h = p.sample_skeleton(s, n_sk, x0, v0, seed=5)
+    os.environ["PDMPFLUX_SLAB_BYTES"] = str(1 << 20 >> 4)  # force many small device slabs
+    try:
+        hs = p.sample_skeleton(s, n_sk, x0, v0, seed=5)
+    finally:
+        os.environ.pop("PDMPFLUX_SLAB_BYTES")
+    for f in ("X", "V", "t", "horizon", "ar", "error_value_ar", "errored_bound", "rejected", "hitting_horizon"):
+        assert np.array_equal(getattr(h, f), getattr(hs, f)), f
+    k = 150  # checkpoint = column k of the first run
+    h2 = p.sample_skeleton(s, n_sk - k, h.X[:, k], h.V[:, k], seed=5, t0=h.t[:, k], horizon0=h.horizon[:, k], event0=k)
+    assert np.array_equal(h2.X[:, 1:], h.X[:, k + 1:]) and np.array_equal(h2.t[:, 1:], h.t[:, k + 1:])
+    assert np.array_equal(h2.V[:, 1:], h.V[:, k + 1:])
+
+
+def test_sample_from_skeleton_and_moments(p):
+    d, n_sk = 5, 3000
+    for mk, fk, kw in ((lambda: p.ZigZagAD(d, p.GaussStd()), 0, dict()),
+                       (lambda: p.Boomerang(d, p.GaussDiag(np.linspace(0.5, 2, d)), refresh_rate=0.4), 1, dict())):
+        s = mk()
+        hb = p.sample_skeleton(s, n_sk, np.zeros((3, d)), np.ones((3, d)), seed=1)
+        N = 4567
+        out = p.sample_from_skeleton(s, N, hb)
+        full = p.sample_from_skeleton(s, N, hb, discard_vt=False)
+        for c in range(3):
+            ref = oc.sample_from_skeleton(fk, hb.X[c], hb.V[c], hb.t[c], N)
+            assert relerr(out[c], ref) < 1e-13
+            reff = oc.sample_from_skeleton(fk, hb.X[c], hb.V[c], hb.t[c], N, discard_vt=False)
+            assert relerr(full[c], reff) < 1e-13
+        # single-chain, reference-shaped API: (d, N) matrix
+        h1 = hb.chain(1)
+        o1 = p.sample_from_skeleton(s, N, h1)
+        assert o1.shape == (d, N) and np.array_equal(o1, out[1].T)
+        # closed-form moments agree with dense sampling of the same path
+        m1, m2, T = p.skeleton_moments(s, hb)
+        dense = p.sample_from_skeleton(s, 400000, hb)
+        assert np.allclose(m1, dense.mean(axis=1), atol=5e-3) and np.allclose(m2, (dense**2).mean(axis=1), atol=1e-2)
+        assert np.allclose(T, hb.t[:, -1])
+
+
+def test_statistical_envelopes_of_reference_tests(p):
+    """Philox-seeded runs against the envelopes the reference's own tests assert (test_property_based.jl:87-100,
+    test_samplers.jl:51-54, test_comprehensive.jl:147,172-180) and posterior moments within Monte Carlo error."""
+    s = p.ZigZagAD(1, p.GaussStd(), grid_size=0)
+    h = p.sample_skeleton(s, 5000, 0.0, 1.0, seed=42)
+    x = p.sample_from_skeleton(s, 5000, h)
+    assert x.shape == (1, 5000) and abs(x.mean()) < 0.2 and 0.8 < x.var() < 1.2
+    assert np.all(np.diff(h.t) > 0) and np.all(np.abs(h.V) == 1.0) and h.X.shape == (1, 5000)
+    # many chains: pooled moments of N(0, I) to MC accuracy, all four samplers' stationary laws for the three
+    # that target it (Boomerang's code path does not, see test_oracle_kat)
+    d, nch, n_sk = 8, 512, 600
+    for mk in (lambda: p.ZigZagAD(d, p.GaussStd()), lambda: p.BPS(d, p.GaussStd(), refresh_rate=0.5),
+               lambda: p.ForwardECMC(d, p.GaussStd())):
+        s = mk()
+        g = np.random.default_rng(0)
+        x0 = g.standard_normal((nch, d))
+        v0 = np.ones((nch, d)) if isinstance(s, p.ZigZag) else np.ones((nch, d)) / np.sqrt(d)
+        hb = p.sample_skeleton(s, n_sk, x0, v0, seed=9)
+        m1, m2, T = p.skeleton_moments(s, hb, burn_in_cols=100)
+        assert np.all(np.abs(m1.mean(axis=0)) < 0.05), m1.mean(axis=0)
+        assert np.all(np.abs(m2.mean(axis=0) - 1.0) < 0.08), m2.mean(axis=0)
+
+
+def test_error_behaviour_matches_reference(p):
+    with pytest.raises(p.ArgumentError):
+        p.ZigZag(0, p.GaussStd())
+    with pytest.raises(p.ArgumentError):
+        p.ZigZag(2, p.GaussStd(), grid_size=-1)
+    with pytest.raises(p.ArgumentError):
+        p.ForwardECMC(1, p.GaussStd())
+    with pytest.raises(p.UnsupportedError):
+        p.ZigZag(2, lambda x: x)
+    s = p.ZigZag(3, p.GaussStd())
+    with pytest.raises(p.ArgumentError):
+        p.sample_skeleton(s, 0, np.zeros(3), np.ones(3))
+    with pytest.raises(p.DimensionMismatch):
+        p.sample_skeleton(s, 10, np.zeros(2), np.ones(2))
+    h = p.sample_skeleton(s, 10, np.zeros(3), np.ones(3), seed=1)
+    with pytest.raises(p.ArgumentError):
+        p.sample_from_skeleton(s, 0, h)
+    # Categorical(p) with sum(lambda) == 0 throws upstream: x = 0, grid_size=0 never leaves the origin's zero rate?
+    # (a chain that cannot produce an event is reported, not hung)
+    with pytest.raises(p.ChainError) as ei:
+        p.sample_skeleton(p.ZigZag(2, p.GaussStd(), max_steps=50), 5, np.zeros(2), np.ones(2),
+                          tape=(np.ones((1, 2)), np.full((1, 2), 0.5), np.zeros((1, 1))))
+    assert ei.value.status[0] == 1  # tape exhausted
