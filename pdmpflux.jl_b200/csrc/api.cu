@@ -321,6 +321,9 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     ch->s = s; ch->n_chains = n_chains; ch->chain_offset = chain_offset; ch->seed = seed;
     const int d = s->dim;
     ch->team = pick_team(d, n_chains);
+    // widen the team until x and v (per-thread-owned shared-memory columns) fit next to a second block
+    while (ch->team < 32 && 2 * (size_t)((d + ch->team - 1) / ch->team) * kBlockThreads * sizeof(double) > 100 * 1024)
+        ch->team = ch->team == 1 ? 8 : 32;
     ch->n_own = (d + ch->team - 1) / ch->team;
     const int cpb = kBlockThreads / ch->team;
     ch->grid = (unsigned)((n_chains + cpb - 1) / cpb);
