@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- skeleton events/s (+ ESS/s) of the grid-based Poisson-thinning hot path on B200.
+
+Workload (BASELINE.json configs[1], "C2"): ZigZag, banana potential d=50 with the manual gradient,
+grid_size=0 (constant bound via Brent), 4096 chains per GPU, Philox draws, full PDMPHistory columns stored.
+One "step" = every chain advanced by --events accepted events (one launch of the skeleton kernel), followed
+by the closed-form moment kernel and (N > 1) one NCCL all-reduce of the moment sums.
+
+  value  events/s, whole job, state and outputs resident in HBM (CUDA events, max over ranks)
+  e2e    events/s through pdmpflux_sample_skeleton with HOST (pinned) buffers: H2D of the initial states and
+         D2H of the full history inside the timed region
+  roofline  algorithmic bytes (16 d + 76 per event: X, V, t, horizon, ar, error_value_ar, 3 int32 counters)
+         / skeleton-kernel time vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the C restatement of the reference (oracle/, OpenMP, one chain per thread) on the host cores
+`--impl reference` times that CPU restatement alone (Julia, hence the reference itself, is not installed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (description, sampler ctor, d, vinit unit-norm?, x0 value, oracle (sampler, potential, params, kwargs))
+    "c1": dict(desc="ZigZagAD std Gaussian d=10, grid_size=10 (README example)", d=10, unit_v=False, x0=0.0,
+               oracle=(0, 0, None, dict())),
+    "c2": dict(desc="ZigZag banana d=50, manual gradient, grid_size=0 (Brent constant bounds)", d=50, unit_v=False,
+               x0=1.0, oracle=(0, 3, None, dict(grid_size=0))),
+    "c3": dict(desc="BPS slanted (equicorrelated rho=0.9) Gaussian d=100, grid_size=10, refresh 0.1", d=100,
+               unit_v=True, x0=0.0, oracle=(1, 2, [0.9], dict(tmax=1.0, refresh_rate=0.1))),
+    "c5f": dict(desc="ForwardECMC std Gaussian d=1000, grid_size=10", d=1000, unit_v=True, x0=0.0,
+                oracle=(2, 0, None, dict())),
+    "c5b": dict(desc="Boomerang std Gaussian d=1000, grid_size=10, refresh 0.1", d=1000, unit_v=False, x0=0.0,
+                oracle=(3, 0, None, dict(tmax=1.0, refresh_rate=0.1, deriv_mode=1))),
+}
+DEFAULT_CHAINS = {"c1": 65536, "c2": 4096, "c3": 16384, "c5f": 8192, "c5b": 8192}
+DEFAULT_EVENTS = {"c1": 500, "c2": 1000, "c3": 300, "c5f": 40, "c5b": 40}
+
+
+def make_sampler(p, name):
+    if name == "c1":
+        return p.ZigZagAD(10, p.GaussStd())
+    if name == "c2":
+        return p.ZigZag(50, p.Banana(), grid_size=0)
+    if name == "c3":
+        return p.BPS(100, p.GaussEquicorr(0.9), refresh_rate=0.1)
+    if name == "c5f":
+        return p.ForwardECMC(1000, p.GaussStd())
+    if name == "c5b":
+        return p.Boomerang(1000, p.GaussStd())
+    raise SystemExit(f"unknown config {name}")
+
+
+def bytes_per_event(d):
+    return 16 * d + 76
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(name, target_seconds=12.0, threads=None):
+    """C restatement of the reference (oracle/) on the host cores, one chain per OpenMP thread, Philox draws:
+    a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle_c as oc
+    cfgd = CONFIGS[name]
+    sampler, pot, pp, kw = cfgd["oracle"]
+    d = cfgd["d"]
+    threads = threads or os.cpu_count() or 1
+    cfg = oc.make_cfg(sampler, pot, d, pp, **kw)
+    nch = threads * 4
+    x0 = np.full((nch, d), cfgd["x0"]); v0 = np.ones((nch, d)) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+    n_ev = 50
+    t0 = time.perf_counter()
+    oc.sample_skeleton(cfg, n_ev + 1, x0, v0, seed=2024, nthreads=threads)
+    dt = time.perf_counter() - t0
+    want = n_ev * target_seconds / max(dt, 1e-4)          # events per chain for the target time at nch chains
+    n_ev = int(max(50, min(20000, want)))                  # cap the stored history (16 d bytes per event per chain)
+    if want > n_ev:
+        nch = int(min(threads * 64, max(nch, threads * round(nch * want / n_ev / threads))))
+        x0 = np.full((nch, d), cfgd["x0"]); v0 = np.ones((nch, d)) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+    t0 = time.perf_counter()
+    r = oc.sample_skeleton(cfg, n_ev + 1, x0, v0, seed=2024, nthreads=threads)
+    dt = time.perf_counter() - t0
+    assert (r.status == 0).all()
+    return {"value": nch * n_ev / dt, "unit": "events/s", "cores": threads, "kind": "port",
+            "sample": f"{nch} chains x {n_ev} events, {dt:.1f} s, C restatement of the reference (oracle/pdmp_oracle.c) "
+                      f"with OpenMP; Julia (the reference runtime) is not installed"}, dt, nch * n_ev
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.config
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(name, target_seconds=2.0)
+    total_t, total_ev = 0.0, 0
+    for _ in range(args.steps):
+        cb, dt, ev = cpu_baseline(name, target_seconds=max(2.0, 60.0 / max(args.steps, 1)))
+        vals.append(cb); total_t += dt; total_ev += ev
+    v = total_ev / total_t
+    cb = dict(vals[-1]); cb["value"] = v
+    line = {"metric": "skeleton events/sec", "value": v, "unit": "events/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: {CONFIGS[name]['desc']}, CPU port of the reference, one chain per thread"},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the BASELINE config's)")
+    ap.add_argument("--events", type=int, default=0, help="events per chain per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pdmpflux_b200 as p
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    p.lib().pdmpflux_set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    name = args.config
+    cfgd = CONFIGS[name]
+    d = cfgd["d"]
+    nch = args.chains or DEFAULT_CHAINS[name]
+    n_ev = args.events or DEFAULT_EVENTS[name]
+    sampler = make_sampler(p, name)
+    f64 = torch.float64
+    x0 = torch.full((nch, d), cfgd["x0"], dtype=f64, device=dev)
+    v0 = torch.ones((nch, d), dtype=f64, device=dev) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+    chains = p.DeviceChains(sampler, x0, v0, seed=2024, chain_offset=rank * nch)
+    bufs = dict(X=torch.empty((nch, n_ev, d), dtype=f64, device=dev), V=torch.empty((nch, n_ev, d), dtype=f64, device=dev),
+                t=torch.empty((nch, n_ev), dtype=f64, device=dev), horizon=torch.empty((nch, n_ev), dtype=f64, device=dev),
+                ar=torch.empty((nch, n_ev), dtype=f64, device=dev),
+                error_value_ar=torch.empty((nch, n_ev, 5), dtype=f64, device=dev),
+                errored_bound=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
+                rejected=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
+                hitting_horizon=torch.empty((nch, n_ev), dtype=torch.int32, device=dev))
+    view = p.device_history_view(n_ev, **bufs)
+    m1 = torch.empty((nch, d), dtype=f64, device=dev); m2 = torch.empty((nch, d), dtype=f64, device=dev)
+    Tl = torch.empty((nch,), dtype=f64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    lib = p.lib()
+    from pdmpflux_b200 import _lib as L
+
+    kern_ms = []
+
+    def step(timed):
+        k0 = torch.cuda.Event(enable_timing=True); k1 = torch.cuda.Event(enable_timing=True)
+        k0.record()
+        chains.advance(n_ev, view, 0, stream)                       # skeleton kernel: n_ev events per chain
+        k1.record()
+        L.check(lib.pdmpflux_skeleton_moments(sampler.flow_kind, d, n_ev, nch, 0, bufs["X"].data_ptr(),
+                                              bufs["V"].data_ptr(), bufs["t"].data_ptr(), m1.data_ptr(), m2.data_ptr(),
+                                              Tl.data_ptr(), 1, stream))
+        mean = m1 / Tl[:, None]
+        sums = torch.stack([mean.sum(0), (mean * mean).sum(0), (m2 / Tl[:, None]).sum(0)])  # 3 x d moment sums
+        if world > 1:
+            dist.all_reduce(sums)                                   # the only collective: final moment reduction
+        if timed:
+            kern_ms.append((k0, k1))
+        return sums
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.pdmpflux_launch_count()
+    clocks = ClockSampler(local); clocks.start()
+    time.sleep(0.25)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        sums = step(True)
+    e1.record()
+    torch.cuda.synchronize()
+    w1 = time.time()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop(w0, w1)
+    launches = lib.pdmpflux_launch_count() - launches0
+    elapsed = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=f64, device=dev)
+    kern = torch.tensor([sum(a.elapsed_time(b) for a, b in kern_ms) * 1e-3 / len(kern_ms)], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+    elapsed = float(elapsed); kern = float(kern)
+    chains.status()  # raises if any chain stopped
+    total_chains = nch * world
+    events_per_step = total_chains * n_ev
+    value = events_per_step * args.steps / elapsed
+
+    # ESS/s from the last step's cross-chain moment sums (definition: SURVEY.md 8d / sample.ess_from_chain_means)
+    sums = sums.cpu().numpy()
+    mbar = sums[0] / total_chains
+    var_between = (sums[1] / total_chains - mbar**2) * total_chains / (total_chains - 1)
+    pooled_var = sums[2] / total_chains - mbar**2
+    ess_total = total_chains * pooled_var / var_between
+    ess_per_s = float(ess_total.min() / (elapsed / args.steps))
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = nch * n_ev * bytes_per_event(d) / kern / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "skeleton_kernel", "kernel_ms": kern * 1e3,
+                "bytes_per_event": bytes_per_event(d),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s"}
+
+    line = {"metric": "skeleton events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: {cfgd['desc']}", "chains_per_gpu": nch, "events_per_chain_per_step": n_ev,
+                       "draws": "philox4x32-10 keyed (seed=2024, chain, event)", "stored": "full PDMPHistory row",
+                       "l2": "outputs per step (%.2f GB) exceed the 126 MB L2" % (nch * n_ev * bytes_per_event(d) / 1e9)},
+            "ess_per_s": ess_per_s, "ess_definition": "min over coordinates of C * Var_pi(x_i) / Var_c(chain time-average of x_i), per step window",
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+
+    if rank == 0 and not args.no_e2e:
+        line["e2e"] = e2e(p, sampler, name, nch, n_ev, world, dev)
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(name)[0]
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e(p, sampler, name, nch, n_ev, world, dev):
+    """Same metric through the public C-ABI call with HOST buffers (pinned): every step copies the initial states
+    host->device and the full history device->host inside the timed region.  Measured on rank 0's GPU with its
+    shard (ranks are independent), scaled by the number of ranks."""
+    import ctypes as C
+    import numpy as np
+    from pdmpflux_b200 import _lib as L
+    lib = p.lib()
+    cfgd = CONFIGS[name]
+    d = cfgd["d"]
+    n_sk = n_ev + 1
+
+    def pinned(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        L.check(lib.pdmpflux_host_alloc(C.byref(ptr), n))
+        buf = (C.c_char * n).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
+
+    arrs, ptrs = {}, []
+    for f, shape, dt in (("X", (nch, n_sk, d), np.float64), ("V", (nch, n_sk, d), np.float64), ("t", (nch, n_sk), np.float64),
+                         ("horizon", (nch, n_sk), np.float64), ("ar", (nch, n_sk), np.float64),
+                         ("error_value_ar", (nch, n_sk, 5), np.float64), ("errored_bound", (nch, n_sk), np.int32),
+                         ("rejected", (nch, n_sk), np.int32), ("hitting_horizon", (nch, n_sk), np.int32),
+                         ("x0", (nch, d), np.float64), ("v0", (nch, d), np.float64)):
+        arrs[f], ptr = pinned(shape, dt)
+        ptrs.append(ptr)
+    arrs["x0"][:] = cfgd["x0"]
+    arrs["v0"][:] = 1.0 / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+    status = np.zeros(nch, dtype=np.int32)
+    view = L.History(*(arrs[f].ctypes.data for f in ("X", "V", "t", "horizon", "ar", "error_value_ar", "errored_bound",
+                                                     "rejected", "hitting_horizon")),
+                     status.ctypes.data, None, None, n_sk, 0)
+
+    def call(seed):
+        L.check(lib.pdmpflux_sample_skeleton(sampler._handle, nch, n_sk, arrs["x0"].ctypes.data, arrs["v0"].ctypes.data,
+                                             C.c_uint64(seed), 0, None, C.byref(view), None), status)
+
+    import torch
+    call(1)
+    torch.cuda.synchronize()
+    reps = 3
+    t0 = time.perf_counter()
+    for i in range(reps):
+        call(2 + i)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    ok = bool(np.isfinite(arrs["t"][:, -1]).all())
+    for ptr in ptrs:
+        lib.pdmpflux_host_free(ptr)
+    return {"value": world * nch * n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": 2 * nch * d * 8,
+            "d2h_bytes_per_step": nch * n_sk * bytes_per_event(d), "ms_per_step": dt * 1e3, "finite": ok,
+            "call": "pdmpflux_sample_skeleton (host buffers, pinned)"}
+
+
+if __name__ == "__main__":
+    main()
