@@ -68,7 +68,7 @@ struct pdmpflux_chains_s {
     pdmpflux_sampler_s* s = nullptr;
     int64_t n_chains = 0, chain_offset = 0, event0 = 0;
     uint64_t seed = 0;
-    int team = 32, n_own = 0, scratch_in_smem = 1;
+    int team = 32, n_own = 0, scratch_in_smem = 1, path = 0;
     size_t smem = 0;
     unsigned grid = 0;
     DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch;
@@ -106,6 +106,7 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     p.tmax = c.tmax; p.refresh_rate = c.refresh_rate;
     p.bound_refresh = c.signed_bound ? c.refresh_rate : 0.0;  // AbstractPDMP.jl:104-112
     p.mix_p = c.mix_p; p.speed_factor = c.speed_factor;
+    p.inv_gm1 = c.grid_size > 1 ? 1.0 / (double)(c.grid_size - 1) : 0.0;
     p.pot = s->pot->pp;
     p.n_chains = ch->n_chains; p.chain_offset = ch->chain_offset; p.seed = ch->seed;
     p.event0 = ch->event0; p.n_events = n_events;
@@ -124,10 +125,10 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     p.scratch = ch->scratch.as<double>(); p.scratch_in_smem = ch->scratch_in_smem; p.n_own = ch->n_own;
     cudaError_t e;
     switch (s->kind) {
-    case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
-    case PDMPFLUX_BPS: e = launch_skeleton_bps(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
-    case PDMPFLUX_FECMC: e = launch_skeleton_fecmc(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
-    case PDMPFLUX_BOOMERANG: e = launch_skeleton_boomerang(ch->team, s->pot->kind, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_BPS: e = launch_skeleton_bps(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_FECMC: e = launch_skeleton_fecmc(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_BOOMERANG: e = launch_skeleton_boomerang(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
     default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("skeleton kernel launch: ") + cudaGetErrorString(e));
@@ -322,15 +323,18 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     const int d = s->dim;
     ch->team = pick_team(d, n_chains);
     // widen the team until x and v (per-thread-owned shared-memory columns) fit next to a second block
-    while (ch->team < 32 && 2 * (size_t)((d + ch->team - 1) / ch->team) * kBlockThreads * sizeof(double) > 100 * 1024)
+    while (ch->team < 32 && 4 * (size_t)((d + ch->team - 1) / ch->team) * kBlockThreads * sizeof(double) > 100 * 1024)
         ch->team = ch->team == 1 ? 8 : 32;
     ch->n_own = (d + ch->team - 1) / ch->team;
     const int cpb = kBlockThreads / ch->team;
     ch->grid = (unsigned)((n_chains + cpb - 1) / cpb);
     const size_t vec_bytes = (size_t)ch->n_own * kBlockThreads * sizeof(double);
-    ch->smem = 2 * vec_bytes;
+    ch->path = select_path(s->kind, s->pot->kind, s->cfg.grid_size, s->cfg.vectorized_bound, s->cfg.deriv_mode);
+    if (const char* e = std::getenv("PDMPFLUX_FORCE_GENERIC")) { if (std::atoi(e)) ch->path = kPathGeneric; }
+    const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent) ? 4 : 2;
+    ch->smem = nvec * vec_bytes;
     if (s->kind == PDMPFLUX_FECMC) {
-        if (5 * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = 5 * vec_bytes; }
+        if ((nvec + 3) * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = (nvec + 3) * vec_bytes; }
         else {
             ch->scratch_in_smem = 0;
             CUDA_TRY(ch->scratch.alloc((size_t)ch->grid * 3 * vec_bytes));

@@ -21,26 +21,55 @@
 
 namespace pdmpflux {
 
-template <int TEAM, int SAMPLER, int POT>
+// Dynamic shared memory of the skeleton kernels.  x, v (and the ZigZag line model A, B) are addressed through
+// this symbol with per-thread element offsets so the compiler emits LDS/STS (pointers stored in the Chain object
+// degrade to generic loads).
+extern __shared__ double g_smem[];
+#define XS(j) g_smem[off_x + (j) * kBlockThreads]
+#define VS(j) g_smem[off_v + (j) * kBlockThreads]
+#define AS(j) g_smem[off_a + (j) * kBlockThreads]
+#define BS(j) g_smem[off_b + (j) * kBlockThreads]
+
+// PATH selects how the bound and the rates are evaluated:
+//   kPathGeneric   every grid node / Brent iterate makes a pass over the coordinates (any potential, any option)
+//   kPathFastBrent affine line model + Brent (grid_size = 0)
+//   kPathFastGrid  affine line model + grid bound with analytic derivatives
+// The fast paths need Pot::kAffine (constant, decoupled Hessian beyond the first kSpecial coordinates): along
+// x + t v every such coordinate rate is A_i + t B_i exactly, so
+//   * ZigZag:   rate(t) = sum_i max(0, A_i + t B_i) (+ special coordinates), and on a grid cell the reference's
+//               tangent construction max(val_l, val_r, inter, 0) collapses to max(val_l, val_r, 0) because the
+//               tangents of an affine function are the function itself (inter lies between val_l and val_r);
+//   * BPS/FECMC: <grad U(x_t), v> = a + t b with a = sum A_i, b = sum B_i: one reduction per bound instead of one
+//               per grid node;
+//   * Boomerang (kSpecial == 0): <P x_t, v_t> = sin cos (pvv - pxx) + (cos^2 - sin^2) pxv.
+// Results differ from the generic path (and the oracle) only by floating-point reassociation (~1e-16 relative).
+enum { kPathGeneric = 0, kPathFastBrent = 1, kPathFastGrid = 2 };
+
+template <int TEAM, int SAMPLER, int POT, int PATH>
 struct Chain {
     using P = Pot<POT>;
+    static constexpr bool kFast = (PATH != kPathGeneric);
+    static constexpr int NS = P::kSpecial;
     static constexpr int K = P::K;
     static constexpr int KK = K > 0 ? K : 1;
     static constexpr bool kRot = (SAMPLER == PDMPFLUX_BOOMERANG);
     static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG);
 
     const KernelParams& p;
-    double* xs;  // owned coordinate j at xs[j * stride]
-    double* vs;
+    int off_x, off_v, off_a, off_b;  // element offsets into g_smem of this thread's owned columns of x, v, A, B
     double* sc0; // scratch owned vectors (FECMC)
     double* sc1;
     double* sc2;
-    int stride, sstride;
+    int sstride;
     int tl, d, nown;
     unsigned mask;
     int64_t chain;
 
     double Lx[KK], Lv[KK];  // functionals of the current (x, v)
+    // fast-path line model of the current (x, v)
+    // (ZigZag + Brent keeps the per-owned-coordinate A_j, B_j in shared memory: AS(j), BS(j))
+    double la, lb;          // BPS/FECMC: a = sum A_i, b = sum B_i over the affine coordinates
+    double pxx, pxv, pvv;   // Boomerang: <Px,x>, <Px,v>, <Pv,v>
 
     // PDMPState scalars (Composites.jl:59-83), team-uniform
     double t, horizon, tp, ts, exp_rv, lambda_bar, ar;
@@ -50,9 +79,10 @@ struct Chain {
     int status;
     int64_t n_builds, n_rates;
 
-    // BoundBox (Composites.jl:15-20), team-uniform, thread-local storage
-    double grid[kMaxGrid], box[kMaxGrid], cum[kMaxGrid];
-    double step;
+    // BoundBox (Composites.jl:15-20), team-uniform, thread-local storage.  Grid nodes are recomputed on
+    // demand from (gc, grem, gh): node k = fma(k, gc, k * grem / (G-1)), last node = gh.
+    double box[kMaxGrid], cum[kMaxGrid];
+    double step, gc, grem, gh;
     int nb;
 
     // draws
@@ -104,8 +134,8 @@ struct Chain {
             for (int k = 0; k < 2 * KK; ++k) acc[k] = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    P::accum(p.pot, coord(j), xs[j * stride], acc);
-                    P::accum(p.pot, coord(j), vs[j * stride], acc + KK);
+                    P::accum(p.pot, coord(j), XS(j), acc);
+                    P::accum(p.pot, coord(j), VS(j), acc + KK);
                 }
             team_sum_n<TEAM, 2 * KK>(acc, mask);
 #pragma unroll
@@ -144,9 +174,9 @@ struct Chain {
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
                 double xt, vt;
-                flow_point(f, xs[j * stride], vs[j * stride], xt, vt);
-                xs[j * stride] = xt;
-                if constexpr (kRot) vs[j * stride] = vt;
+                flow_point(f, XS(j), VS(j), xt, vt);
+                XS(j) = xt;
+                if constexpr (kRot) VS(j) = vt;
             }
     }
 
@@ -154,42 +184,171 @@ struct Chain {
         return SAMPLER == PDMPFLUX_FECMC ? 0.0 : p.refresh_rate;
     }
 
+    // ================================================================================================
+    // fast-path line model (PATH != kPathGeneric; linear flow unless Boomerang)
+    // ================================================================================================
+    // signed coordinate rates of the special (non-affine) leading coordinates at time tt: y_k = g_k(x_t) v_k,
+    // dy_k = (H(x_t) v)_k v_k; these only depend on the functionals, so every lane evaluates them.
+    __device__ __forceinline__ void special_rates(double tt, double* y, double* dy) const {
+        if constexpr (NS > 0) {
+            double Lxt[KK];
+#pragma unroll
+            for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                double g, hv;
+                P::eval(p.pot, k, Lxt[k], Lv[k], Lxt, Lv, g, hv);
+                y[k] = g * Lv[k];
+                dy[k] = hv * Lv[k];
+            }
+        }
+    }
+
+    // Build the line model of the current (x, v); called once per (x, v) change, after compute_functionals().
+    __device__ void prepare_line() {
+        if constexpr (!kFast) return;
+        else if constexpr (kRot) {
+            double r3[3] = {0.0, 0.0, 0.0};
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    const double xi = XS(j), vi = VS(j);
+                    double g, hv;
+                    P::eval(p.pot, coord(j), xi, vi, Lx, Lv, g, hv);
+                    r3[0] += g * xi; r3[1] += g * vi; r3[2] += hv * vi;
+                }
+            team_sum_n<TEAM, 3>(r3, mask);
+            pxx = r3[0]; pxv = r3[1]; pvv = r3[2];
+        } else if constexpr (kZZ) {
+            if constexpr (PATH == kPathFastBrent) {
+                for (int j = 0; j < nown; ++j) {
+                    double A = 0.0, B = 0.0;  // A = B = 0 contributes max(0, 0) = 0 for unowned / special slots
+                    if (owns(j) && coord(j) >= NS) {
+                        const double vi = VS(j);
+                        double g, hv;
+                        P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
+                        A = g * vi; B = hv * vi;
+                    }
+                    AS(j) = A; BS(j) = B;
+                }
+            }
+        } else {  // BPS / FECMC
+            double r2[2] = {0.0, 0.0};
+            for (int j = 0; j < nown; ++j)
+                if (owns(j) && coord(j) >= NS) {
+                    const double vi = VS(j);
+                    double g, hv;
+                    P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
+                    r2[0] += g * vi; r2[1] += hv * vi;
+                }
+            team_sum_n<TEAM, 2>(r2, mask);
+            la = r2[0]; lb = r2[1];
+        }
+    }
+
+    // signed scalar rate <grad U(x_t), v_t> and its d/dt from the line model (BPS / FECMC / Boomerang)
+    __device__ __forceinline__ void line_scalar(double tt, double& y, double& dy) const {
+        if constexpr (kRot) {
+            double s, c;
+            sincos(tt, &s, &c);
+            const double c2 = c * c - s * s, sc = s * c;
+            y = sc * (pvv - pxx) + c2 * pxv;
+            dy = c2 * (pvv - pxx) - 4.0 * sc * pxv;  // v_t' H v_t - <grad U(x_t), x_t>
+        } else {
+            y = la + tt * lb;
+            dy = lb;
+            if constexpr (NS > 0) {
+                double ys[NS], dys[NS];
+                special_rates(tt, ys, dys);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) { y += ys[k]; dy += dys[k]; }
+            }
+        }
+    }
+
     // `sampler.rate` (always the unsigned rate): ZigZagSamplers.jl:83-86, BouncyParticleSamplers.jl:39-42,
     // ForwardEventChainMonteCarlo.jl:20-23, BoomerangSamplers.jl:38-41.  Uses Lx/Lv of the current (x, v).
     __device__ double rate_unsigned(double tt) {
-        const Flow f = flow_coef(tt);
-        double Lxt[KK], Lvt[KK];
-        flow_functionals(f, Lxt, Lvt);
-        double s = 0.0;
-        for (int j = 0; j < nown; ++j)
-            if (owns(j)) {
-                double xt, vt;
-                flow_point(f, xs[j * stride], vs[j * stride], xt, vt);
-                const double y = P::grad(p.pot, coord(j), xt, Lxt) * vt;
-                if constexpr (kZZ) s += (y > 0.0 ? y : 0.0);
-                else s += y;
+        if constexpr (kFast && !kZZ) {
+            double y, dy;
+            line_scalar(tt, y, dy);
+            return (y > 0.0 ? y : 0.0) + extra_rate();
+        } else if constexpr (kZZ && PATH == kPathFastBrent) {
+            double s0 = 0.0, s1 = 0.0;  // two accumulators: shorter dependency chain
+            int j = 0;
+            for (; j + 1 < nown; j += 2) {
+                const double y0 = fma(tt, BS(j), AS(j));
+                const double y1 = fma(tt, BS(j + 1), AS(j + 1));
+                s0 += (y0 > 0.0 ? y0 : 0.0);
+                s1 += (y1 > 0.0 ? y1 : 0.0);
             }
-        s = team_sum<TEAM>(s, mask);
-        if constexpr (kZZ) return s;
-        else return (s > 0.0 ? s : 0.0) + extra_rate();
+            if (j < nown) {
+                const double y0 = fma(tt, BS(j), AS(j));
+                s0 += (y0 > 0.0 ? y0 : 0.0);
+            }
+            double s = team_sum<TEAM>(s0 + s1, mask);
+            if constexpr (NS > 0) {
+                double ys[NS], dys[NS];
+                special_rates(tt, ys, dys);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) s += (ys[k] > 0.0 ? ys[k] : 0.0);
+            }
+            return s;
+        } else {
+            const Flow f = flow_coef(tt);
+            double Lxt[KK], Lvt[KK];
+            flow_functionals(f, Lxt, Lvt);
+            double s = 0.0;
+            for (int j = 0; j < nown; ++j)
+                if (owns(j)) {
+                    double xt, vt;
+                    flow_point(f, XS(j), VS(j), xt, vt);
+                    const double y = P::grad(p.pot, coord(j), xt, Lxt) * vt;
+                    if constexpr (kZZ) s += (y > 0.0 ? y : 0.0);
+                    else s += y;
+                }
+            s = team_sum<TEAM>(s, mask);
+            if constexpr (kZZ) return s;
+            else return (s > 0.0 ? s : 0.0) + extra_rate();
+        }
     }
 
-    // range(0, stop=h, length=G) (UpperBound.jl:94,204): ~correctly rounded k*h/(G-1); last node == h
+    // range(0, stop=h, length=G) (UpperBound.jl:94,204): Julia's TwicePrecision range gives ~correctly rounded
+    // k*h/(G-1) with the last node == h.  Here: c = h/(G-1) rounded, rem = h - c (G-1) exactly (fma), and
+    // node k = fma(k, c, k rem/(G-1)) -- one division per bound, at most 1 ulp from the exact quotient.
     __device__ void make_grid(double h, int G) {
         const double m = (double)(G - 1);
-        for (int k = 0; k < G; ++k) {
-            const double kk = (double)k;
-            const double pr = kk * h, e = fma(kk, h, -pr);
-            const double q = pr / m;
-            const double r = fma(-q, m, pr) + e;
-            grid[k] = q + r / m;
-        }
-        grid[G - 1] = h;
+        gc = h / m;
+        grem = fma(-gc, m, h) * p.inv_gm1;
+        gh = h;
+        nb = G;
+        step = grid_t(1);  // t[2] - t[1] with t[1] = 0
+    }
+    __device__ __forceinline__ double grid_t(int k) const {
+        if (k >= nb - 1) return gh;
+        const double kk = (double)k;
+        return fma(kk, gc, kk * grem);
     }
 
     __device__ static __forceinline__ double clamp_pos(double pos, double stp) {
         if (pos != pos) pos = 0.0;              // replace(NaN => 0.0)
         return fmin(fmax(pos, 0.0), stp);       // clamp.(pos, 0, step)
+    }
+    // one cell of upper_bound_grid_vect for one coordinate (UpperBound.jl:229-241)
+    // QUIRK: the tangent intersection is computed as an ABSOLUTE time, clamped to [0, step] and then used as an
+    // OFFSET from the left node.
+    __device__ __forceinline__ double vect_cell(double vl, double gl, double vr, double gr, double tl_, double tr_) const {
+        double pos = (vl - vr + gr * tr_ - gl * tl_) / (gr - gl);
+        pos = clamp_pos(pos, step);
+        const double inter = vl + gl * pos;
+        return fmax(fmax(fmax(vl, vr), inter), 0.0);
+    }
+    // one cell of upper_bound_grid (UpperBound.jl:123-131)
+    __device__ __forceinline__ double scalar_cell(double vl, double gl, double vr, double gr) const {
+        double pos = (vl - vr + gr * step) / (gr - gl);
+        pos = clamp_pos(pos, step);
+        const double inter = vl + gl * pos;
+        // QUIRK: BPS/Boomerang signed bound counts the refresh rate twice (inside the rate and via :131)
+        return fmax(fmax(fmax(vl, vr), inter), 0.0) + p.bound_refresh;
     }
 
     // ---- vectorised (ZigZag) bound: value and d/dt of (signed_)rate_vect for one owned coordinate ----
@@ -228,34 +387,65 @@ struct Chain {
     __device__ void build_bound_vect(double h) {
         const int G = p.G;
         make_grid(h, G);
-        step = grid[1] - grid[0];
-        nb = G;
         for (int k0 = 0; k0 < G - 1; k0 += kChunk) {
             const int nc = min(kChunk, G - 1 - k0);
-            double bacc[kChunk];
+            double bacc[kChunk], tn[kChunk + 1];
 #pragma unroll
             for (int u = 0; u < kChunk; ++u) bacc[u] = 0.0;
+#pragma unroll
+            for (int u = 0; u <= kChunk; ++u) tn[u] = grid_t(min(k0 + u, G - 1));
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const int i = coord(j);
-                    const double xi = xs[j * stride], vi = vs[j * stride];
-                    double vl, gl;
-                    vect_node(i, xi, vi, grid[k0], h, vl, gl);
+                    const double xi = XS(j), vi = VS(j);
+                    if constexpr (kFast) {
+                        if (i < NS) continue;  // special coordinates are added once, after the reduction
+                        // affine coordinate: max(val_l, val_r, inter, 0) == max(val_l, val_r, 0); holds for the
+                        // unsigned variant max(0, .) as well (see DESIGN.md "affine cells")
+                        double g, hv;
+                        P::eval(p.pot, i, xi, vi, Lx, Lv, g, hv);
+                        const double A = g * vi, B = hv * vi;
+                        const bool up = (B >= 0.0);
 #pragma unroll
-                    for (int u = 0; u < kChunk; ++u)
-                        if (u < nc) {
-                            double vr, gr;
-                            vect_node(i, xi, vi, grid[k0 + u + 1], h, vr, gr);
-                            // QUIRK (UpperBound.jl:229-237): the tangent intersection is computed as an ABSOLUTE
-                            // time, clamped to [0, step] and then used as an OFFSET from the left node.
-                            double pos = (vl - vr + gr * grid[k0 + u + 1] - gl * grid[k0 + u]) / (gr - gl);
-                            pos = clamp_pos(pos, step);
-                            const double inter = vl + gl * pos;
-                            bacc[u] += fmax(fmax(fmax(vl, vr), inter), 0.0);
-                            vl = vr; gl = gr;
-                        }
+                        for (int u = 0; u < kChunk; ++u)
+                            if (u < nc) {
+                                const double y = fma(up ? tn[u + 1] : tn[u], B, A);
+                                bacc[u] += (y > 0.0 ? y : 0.0);
+                            }
+                    } else {
+                        double vl, gl;
+                        vect_node(i, xi, vi, tn[0], h, vl, gl);
+#pragma unroll
+                        for (int u = 0; u < kChunk; ++u)
+                            if (u < nc) {
+                                double vr, gr;
+                                vect_node(i, xi, vi, tn[u + 1], h, vr, gr);
+                                bacc[u] += vect_cell(vl, gl, vr, gr, tn[u], tn[u + 1]);
+                                vl = vr; gl = gr;
+                            }
+                    }
                 }
             team_sum_n<TEAM, kChunk>(bacc, mask);
+            if constexpr (kFast && NS > 0) {  // special coordinates: the reference's cell formula, every lane
+                double yl[NS], dl[NS];
+                special_rates(tn[0], yl, dl);
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u)
+                    if (u < nc) {
+                        double yr[NS], dr[NS];
+                        special_rates(tn[u + 1], yr, dr);
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) {
+                            double vl = yl[k], gl = dl[k], vr = yr[k], gr = dr[k];
+                            if (!p.signed_bound) {
+                                gl = (0.0 > vl) ? 0.0 : gl; vl = (vl > 0.0 ? vl : 0.0);
+                                gr = (0.0 > vr) ? 0.0 : gr; vr = (vr > 0.0 ? vr : 0.0);
+                            }
+                            bacc[u] += vect_cell(vl, gl, vr, gr, tn[u], tn[u + 1]);
+                            yl[k] = yr[k]; dl[k] = dr[k];
+                        }
+                    }
+            }
 #pragma unroll
             for (int u = 0; u < kChunk; ++u)
                 if (u < nc) box[k0 + u] = bacc[u];
@@ -279,7 +469,7 @@ struct Chain {
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
                 const int i = coord(j);
-                const double xi = xs[j * stride], vi = vs[j * stride];
+                const double xi = XS(j), vi = VS(j);
 #pragma unroll
                 for (int u = 0; u < kChunk; ++u)
                     if (u < n) {
@@ -310,26 +500,47 @@ struct Chain {
         for (int u = 0; u < kChunk; ++u)
             if (u < n) {
                 if constexpr (kZZ) { outv[u] = av[u]; if (want_d) outd[u] = ad[u]; }
-                else if (p.signed_bound) { outv[u] = av[u] + extra_rate(); if (want_d) outd[u] = ad[u]; }
-                else {
-                    outv[u] = (av[u] > 0.0 ? av[u] : 0.0) + extra_rate();
-                    if (want_d) outd[u] = (0.0 > av[u]) ? 0.0 : ad[u];
-                }
+                else finish_scalar(av[u], ad[u], outv[u], outd[u]);
             }
     }
+    // signed / unsigned post-processing of <grad U, v> (AbstractPDMP.jl:104-112)
+    __device__ __forceinline__ void finish_scalar(double y, double dy, double& val, double& dval) const {
+        if (p.signed_bound) { val = y + extra_rate(); dval = dy; }
+        else { val = (y > 0.0 ? y : 0.0) + extra_rate(); dval = (0.0 > y) ? 0.0 : dy; }
+    }
 
-    // upper_bound_grid, UpperBound.jl:92-137 (vals/grads reuse box/cum as temporaries? no: separate arrays)
+    // upper_bound_grid, UpperBound.jl:92-137
     __device__ void build_bound_scalar(double h) {
         const int G = p.G;
-        double vals[kMaxGrid], grads[kMaxGrid];
         make_grid(h, G);
-        step = grid[1] - grid[0];
-        nb = G;
+        if constexpr (kFast && !kZZ) {  // O(1) nodes from the line model, analytic derivative
+            double vl, gl, cs = 0.0;
+            {
+                double y, dy;
+                line_scalar(0.0, y, dy);
+                finish_scalar(y, dy, vl, gl);
+            }
+            cum[0] = 0.0;
+            for (int k = 0; k < G - 1; ++k) {
+                double y, dy, vr, gr;
+                line_scalar(grid_t(k + 1), y, dy);
+                finish_scalar(y, dy, vr, gr);
+                const double b = scalar_cell(vl, gl, vr, gr);
+                box[k] = b;
+                cs += b;
+                cum[k + 1] = cs * step;
+                vl = vr; gl = gr;
+            }
+            return;
+        }
+        double vals[kMaxGrid], grads[kMaxGrid];
         const bool jvp = (p.deriv_mode == PDMPFLUX_DERIV_JVP);
         for (int k0 = 0; k0 < G; k0 += kChunk) {
             const int n = min(kChunk, G - k0);
-            double ov[kChunk], od[kChunk];
-            scalar_nodes(grid + k0, n, jvp, ov, od);
+            double tt[kChunk], ov[kChunk], od[kChunk];
+#pragma unroll
+            for (int u = 0; u < kChunk; ++u) tt[u] = grid_t(min(k0 + u, G - 1));
+            scalar_nodes(tt, n, jvp, ov, od);
 #pragma unroll
             for (int u = 0; u < kChunk; ++u)
                 if (u < n) { vals[k0 + u] = ov[u]; grads[k0 + u] = jvp ? od[u] : 0.0; }
@@ -340,7 +551,7 @@ struct Chain {
                 double tp_[kChunk], tm_[kChunk], fp[kChunk], fm[kChunk], dummy[kChunk];
 #pragma unroll
                 for (int u = 0; u < kChunk; ++u) {
-                    const double tt = (u < n) ? grid[k0 + u] : 0.0;
+                    const double tt = grid_t(min(k0 + u, G - 1));
                     const double hh_ = kSqrtEps * fmax(1.0, fabs(tt));
                     tm_[u] = fmax(0.0, tt - hh_);
                     tp_[u] = fmin(h, tt + hh_);
@@ -350,7 +561,7 @@ struct Chain {
 #pragma unroll
                 for (int u = 0; u < kChunk; ++u)
                     if (u < n) {
-                        const double tt = grid[k0 + u], fx = vals[k0 + u];
+                        const double tt = grid_t(k0 + u), fx = vals[k0 + u];
                         if (tp_[u] == tm_[u]) grads[k0 + u] = fx - fx;
                         else {
                             const double a = (tp_[u] == tt) ? fx : fp[u];
@@ -363,11 +574,7 @@ struct Chain {
         double cs = 0.0;
         cum[0] = 0.0;
         for (int k = 0; k < G - 1; ++k) {
-            double pos = (vals[k] - vals[k + 1] + grads[k + 1] * step) / (grads[k + 1] - grads[k]);
-            pos = clamp_pos(pos, step);
-            const double inter = vals[k] + grads[k] * pos;
-            double b = fmax(fmax(fmax(vals[k], vals[k + 1]), inter), 0.0);
-            b += p.bound_refresh;  // QUIRK: BPS/Boomerang signed bound counts the refresh rate twice (:131)
+            const double b = scalar_cell(vals[k], grads[k], vals[k + 1], grads[k + 1]);
             box[k] = b;
             cs += b;
             cum[k + 1] = cs * step;
@@ -376,7 +583,7 @@ struct Chain {
 
     // upper_bound_constant, UpperBound.jl:18-36: Optim.jl Brent on t -> -rate(t) over [0, h]
     __device__ void build_bound_brent(double h) {
-        const double golden = 0.5 * (3.0 - sqrt(5.0));
+        const double golden = 0.3819660112501051;  // (3 - sqrt(5)) / 2
         double lo = 0.0, hi = h;
         double x = lo + golden * (hi - lo);
         double fx = -rate_unsigned(x);
@@ -414,18 +621,22 @@ struct Chain {
                 else if (fu <= fv || vv == x || vv == w) { vv = u; fv = fu; }
             }
         }
-        grid[0] = 0.0; grid[1] = h;
         box[0] = -fx + 0.0;  // init_state passes no refresh here (AbstractPDMP.jl:122-125)
         cum[0] = 0.0; cum[1] = box[0] * (h - 0.0);
         step = h - 0.0;
-        nb = 2;
+        nb = 2; gh = h; gc = h; grem = 0.0;
     }
 
     __device__ void build_bound(double h) {
         ++n_builds;
-        if (p.G == 0) build_bound_brent(h);
-        else if (kZZ && p.vectorized) build_bound_vect(h);
-        else build_bound_scalar(h);
+        if constexpr (PATH == kPathFastBrent) build_bound_brent(h);
+        else if constexpr (PATH == kPathFastGrid) {
+            if constexpr (kZZ) build_bound_vect(h); else build_bound_scalar(h);
+        } else {
+            if (p.G == 0) build_bound_brent(h);
+            else if (kZZ && p.vectorized) build_bound_vect(h);
+            else build_bound_scalar(h);
+        }
     }
 
     // next_event, UpperBound.jl:264-273
@@ -434,7 +645,7 @@ struct Chain {
         while (idx < nb && cum[idx] < e) ++idx;  // searchsortedfirst
         if (idx >= nb) { tp_out = CUDART_INF; lb_out = box[nb - 2]; return; }
         if (idx == 0) { tp_out = CUDART_NAN; lb_out = box[0]; return; }  // e <= 0 cannot happen (randexp > 0)
-        tp_out = grid[idx - 1] + (e - cum[idx - 1]) / (cum[idx] - cum[idx - 1]) * step;
+        tp_out = grid_t(idx - 1) + (e - cum[idx - 1]) / (cum[idx] - cum[idx - 1]) * step;
         lb_out = box[idx - 1];
     }
 
@@ -445,7 +656,7 @@ struct Chain {
         double S = 0.0;
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
-                const double y = P::grad(p.pot, coord(j), xs[j * stride], Lx) * vs[j * stride];
+                const double y = P::grad(p.pot, coord(j), XS(j), Lx) * VS(j);
                 S += (y > 0.0 ? y : 0.0);
             }
         S = team_sum<TEAM>(S, mask);
@@ -453,7 +664,7 @@ struct Chain {
         double chk[2] = {0.0, 0.0};
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
-                const double y = P::grad(p.pot, coord(j), xs[j * stride], Lx) * vs[j * stride];
+                const double y = P::grad(p.pot, coord(j), XS(j), Lx) * VS(j);
                 const double pj = (y > 0.0 ? y : 0.0) / S;
                 if (!(pj >= 0.0)) chk[0] += 1.0;
                 chk[1] += pj;
@@ -470,7 +681,7 @@ struct Chain {
         for (int j = 0; j < nown; ++j) {
             double pj = 0.0;
             if (owns(j)) {
-                const double y = P::grad(p.pot, coord(j), xs[j * stride], Lx) * vs[j * stride];
+                const double y = P::grad(p.pot, coord(j), XS(j), Lx) * VS(j);
                 pj = (y > 0.0 ? y : 0.0) / S;
             }
             const double incl = team_scan_incl<TEAM>(pj, mask, tl) + carry;
@@ -485,15 +696,15 @@ struct Chain {
             if (first >= 0) { m = first + TEAM * j; break; }
             carry = team_bcast<TEAM>(incl, TEAM - 1, mask);
         }
-        if (m % TEAM == tl) { const int j = m / TEAM; vs[j * stride] = -vs[j * stride]; }
+        if (m % TEAM == tl) { const int j = m / TEAM; VS(j) = -VS(j); }
     }
 
     __device__ void jump_bps() {  // BouncyParticleSamplers.jl:50-74
         double r2[2] = {0.0, 0.0};
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
-                const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
-                r2[0] += g * vs[j * stride];
+                const double g = P::grad(p.pot, coord(j), XS(j), Lx);
+                r2[0] += g * VS(j);
                 r2[1] += g * g;
             }
         team_sum_n<TEAM, 2>(r2, mask);
@@ -506,8 +717,8 @@ struct Chain {
             const double scale = 2 * gv / gg;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
-                    vs[j * stride] = vs[j * stride] - scale * g;
+                    const double g = P::grad(p.pot, coord(j), XS(j), Lx);
+                    VS(j) = VS(j) - scale * g;
                 }
         } else {
             normals_reserve(d);
@@ -515,14 +726,14 @@ struct Chain {
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const double z = rand_normal_at(coord(j));
-                    vs[j * stride] = z;
+                    VS(j) = z;
                     nn += z * z;
                 }
             normals_advance(d);
             if (!p.gaussian_velocity) {
                 nn = sqrt(team_sum<TEAM>(nn, mask));
                 for (int j = 0; j < nown; ++j)
-                    if (owns(j)) vs[j * stride] = vs[j * stride] / nn;
+                    if (owns(j)) VS(j) = VS(j) / nn;
             }
         }
     }
@@ -532,8 +743,8 @@ struct Chain {
         double r2[2] = {0.0, 0.0};
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
-                const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx) - xs[j * stride];
-                r2[0] += g * vs[j * stride];
+                const double g = P::grad(p.pot, coord(j), XS(j), Lx) - XS(j);
+                r2[0] += g * VS(j);
                 r2[1] += g * g;
             }
         team_sum_n<TEAM, 2>(r2, mask);
@@ -546,19 +757,19 @@ struct Chain {
             double ve = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double e = (P::grad(p.pot, coord(j), xs[j * stride], Lx) - xs[j * stride]) / ng;
-                    ve += vs[j * stride] * e;
+                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) / ng;
+                    ve += VS(j) * e;
                 }
             ve = team_sum<TEAM>(ve, mask);
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double e = (P::grad(p.pot, coord(j), xs[j * stride], Lx) - xs[j * stride]) / ng;
-                    vs[j * stride] = vs[j * stride] - 2 * ve * e;
+                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) / ng;
+                    VS(j) = VS(j) - 2 * ve * e;
                 }
         } else {  // QUIRK: refresh draws from the global RNG in the reference (:65); on a tape it is the N stream
             normals_reserve(d);
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) vs[j * stride] = rand_normal_at(coord(j));
+                if (owns(j)) VS(j) = rand_normal_at(coord(j));
             normals_advance(d);
         }
     }
@@ -573,22 +784,22 @@ struct Chain {
         double r2[2] = {0.0, 0.0};
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
-                const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
+                const double g = P::grad(p.pot, coord(j), XS(j), Lx);
                 r2[0] += g * g;
             }
         const double ng = sqrt(team_sum<TEAM>(r2[0], mask));
         auto nvec = [&](int j) -> double {
-            const double g = P::grad(p.pot, coord(j), xs[j * stride], Lx);
+            const double g = P::grad(p.pot, coord(j), XS(j), Lx);
             return ng == 0 ? 0.0 : g / ng;
         };
         double vn = 0.0;
         for (int j = 0; j < nown; ++j)
-            if (owns(j)) vn += vs[j * stride] * nvec(j);
+            if (owns(j)) vn += VS(j) * nvec(j);
         vn = team_sum<TEAM>(vn, mask);
         double nvo = 0.0;
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
-                const double o = vs[j * stride] - vn * nvec(j);
+                const double o = VS(j) - vn * nvec(j);
                 vo[j * sstride] = o;
                 nvo += o * o;
             }
@@ -618,7 +829,7 @@ struct Chain {
         if (u2 >= p.mix_p) {
             const double nrm = sqrt(nvo);
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) vs[j * stride] = vo[j * sstride] / nrm * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = vo[j * sstride] / nrm * rad + rho * nvec(j);
             return;
         }
         double* prop = sc1;
@@ -694,7 +905,7 @@ struct Chain {
             if (p.positive) sgn = (r3[0] > 0) ? 1.0 : ((r3[0] < 0) ? -1.0 : r3[0]);  // sign(0)=0, sign(NaN)=NaN
             const double nrm = sqrt(r3[1] * (sgn * sgn));
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) vs[j * stride] = (prop[j * sstride] * sgn) / nrm * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = (prop[j * sstride] * sgn) / nrm * rad + rho * nvec(j);
         } else {  // _full_refresh
             normals_reserve(d);
             double nw = 0.0;
@@ -723,7 +934,7 @@ struct Chain {
                 }
             np_ = sqrt(team_sum<TEAM>(np_, mask));
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) vs[j * stride] = prop[j * sstride] / np_ * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = prop[j * sstride] / np_ * rad + rho * nvec(j);
         }
     }
 
@@ -737,72 +948,93 @@ struct Chain {
     }
 
     // ------------------------------------------------------------------------------------------------
-    // thinning state machine: SamplingLoopInplace.jl
+    // thinning state machine: SamplingLoopInplace.jl, flattened
     // ------------------------------------------------------------------------------------------------
-    __device__ void one_step_of_thinning() {  // :65-85
-        compute_functionals();
-        build_bound(horizon);
-        const double e = rand_exp();
-        next_event(e, tp, lambda_bar);
-        exp_rv = e;
-        if (tp > horizon) {  // move_to_horizon!, :87-101
-            flow_inplace(horizon);
-            ts += horizon;
-            hh += 1;
-            horizon = p.adaptive ? horizon * 1.01 : horizon;
-            return;
-        }
-        accept = false;  // moves_until_horizon!, :103-111
-        while (tp < horizon && !accept && status == 0 && !exhausted) {
+    // The reference nests three loops (events -> `while !accept` one_step_of_thinning! -> `while tp < horizon`
+    // ac_step!).  Lanes of a warp that own different chains need different trip counts (extra bound builds after
+    // horizon hits, extra proposals after rejections), and nested loops would make every chain wait for the
+    // slowest one at every loop exit.  Here the nest is flattened into one loop whose body is
+    //   [bound build + first proposal, if this chain needs one]  then  [one accept/reject step, if it has a proposal]
+    // so a chain that finished its event immediately starts the next one.  The sequence of operations per chain
+    // (and hence the draw order) is exactly the reference's.
+    __device__ void begin_event(int64_t ev) {  // get_event_state!, :28-31
+        eb = 0; rej = 0; hh = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) eva[k] = 0.0;
+        key.event = (uint32_t)(p.event0 + ev + 1);
+        sE = sU = sN = 0;
+    }
+
+    __device__ void run_events(int64_t c) {
+        int64_t ev = 0;
+        int steps = 0;
+        bool need_build = true, half = false;
+        accept = false;
+        begin_event(0);
+        while (ev < p.n_events) {
+            if (need_build) {
+                if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; break; }
+                double h = horizon;
+                if (!half) {  // one_step_of_thinning!, :65-85
+                    compute_functionals();
+                    prepare_line();
+                } else h = horizon / 2;  // erroneous_acceptance_rate!, :131-151 (same x, v: line model still valid)
+                build_bound(h);
+                const double e = rand_exp();
+                next_event(e, tp, lambda_bar);
+                exp_rv = e;
+                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
+                if (half) {
+                    // QUIRK: a non-adaptive chain keeps the full horizon although the live bound covers half of it
+                    horizon = p.adaptive ? h : horizon;
+                    eb += 1;
+                    eva[eb % 5] = ar;
+                    half = false;
+                    need_build = false;  // back in moves_until_horizon!; a proposal beyond the horizon restarts below
+                } else if (tp > horizon) {  // move_to_horizon!, :87-101
+                    flow_inplace(horizon);
+                    ts += horizon;
+                    hh += 1;
+                    horizon = p.adaptive ? horizon * 1.01 : horizon;
+                    continue;
+                } else need_build = false;
+            }
+            // moves_until_horizon!, :103-111: `while tp < horizon && !accept` -- otherwise a fresh outer step
+            if (!(tp < horizon)) { need_build = true; continue; }
             // ac_step!, :113-129
             ++n_rates;
             const double lt = rate_unsigned(tp);
             ar = lt / lambda_bar;
-            if (ar > 1.0) {  // erroneous_acceptance_rate!, :131-151
-                const double h2 = horizon / 2;
-                build_bound(h2);
-                const double e2 = rand_exp();
-                next_event(e2, tp, lambda_bar);
-                exp_rv = e2;
-                // QUIRK: a non-adaptive chain keeps the full horizon although the live bound covers half of it
-                horizon = p.adaptive ? h2 : horizon;
-                eb += 1;
-                eva[eb % 5] = ar;
-            } else {  // ac_step_with_proxy!, :153-168
-                accept = rand_uniform() < ar;
-                if (accept) {  // if_accept!, :170-186
-                    flow_inplace(tp);
-                    velocity_jump();
-                    t = t + tp + ts;
-                    ts = 0.0;
-                    tp = 0.0;
-                } else {  // if_reject!, :188-203
-                    const double e3 = exp_rv + rand_exp();
-                    next_event(e3, tp, lambda_bar);
-                    horizon = p.adaptive ? horizon / 1.04 : horizon;  // QUIRK: shrink before the horizon check
-                    exp_rv = e3;
-                    rej += 1;
-                    if (tp > horizon) {  // move_to_horizon2!, :205-217 (no horizon growth here)
-                        flow_inplace(horizon);
-                        ts += horizon;
-                        hh += 1;
-                    }
+            if (ar > 1.0) { need_build = true; half = true; continue; }
+            // ac_step_with_proxy!, :153-168
+            const bool acc = rand_uniform() < ar;
+            if (acc) {  // if_accept!, :170-186
+                flow_inplace(tp);
+                velocity_jump();
+                t = t + tp + ts;
+                ts = 0.0;
+                tp = 0.0;
+                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
+                if (status != 0) break;
+                record(c, p.col0 + ev);
+                ++ev;
+                steps = 0;
+                begin_event(ev);
+                need_build = true;
+            } else {  // if_reject!, :188-203
+                const double e3 = exp_rv + rand_exp();
+                next_event(e3, tp, lambda_bar);
+                horizon = p.adaptive ? horizon / 1.04 : horizon;  // QUIRK: shrink before the horizon check
+                exp_rv = e3;
+                rej += 1;
+                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
+                if (tp > horizon) {  // move_to_horizon2!, :205-217 (no horizon growth here)
+                    flow_inplace(horizon);
+                    ts += horizon;
+                    hh += 1;
+                    need_build = true;
                 }
             }
-        }
-    }
-
-    __device__ void get_event_state() {  // :27-39
-        eb = 0; rej = 0; hh = 0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) eva[k] = 0.0;
-        int steps = 0;
-        accept = false;
-        while (!accept) {
-            one_step_of_thinning();
-            if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; return; }
-            if (status != 0) return;
-            if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; return; }
         }
     }
 
@@ -811,10 +1043,10 @@ struct Chain {
         const int64_t o = c_local_global * p.ld_cols + col;
         if (p.X)
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) p.X[o * d + coord(j)] = xs[j * stride];
+                if (owns(j)) p.X[o * d + coord(j)] = XS(j);
         if (p.V)
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) p.V[o * d + coord(j)] = vs[j * stride];
+                if (owns(j)) p.V[o * d + coord(j)] = VS(j);
         if (tl == 0) {
             if (p.T) p.T[o] = t;
             if (p.H) p.H[o] = horizon;
@@ -832,26 +1064,33 @@ struct Chain {
 
 // One launch advances every chain by p.n_events accepted events (or just records the current state when
 // n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
-template <int TEAM, int SAMPLER, int POT>
+template <int TEAM, int SAMPLER, int POT, int PATH>
 __global__ void __launch_bounds__(kBlockThreads) skeleton_kernel(const KernelParams p) {
-    extern __shared__ double smem[];
+    double* smem = g_smem;
     constexpr int CPB = kBlockThreads / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
     const int64_t c = (int64_t)blockIdx.x * CPB + c_local;
     if (c >= p.n_chains) return;  // teams never synchronise across the block
 
-    Chain<TEAM, SAMPLER, POT> ch(p);
+    Chain<TEAM, SAMPLER, POT, PATH> ch(p);
     ch.tl = threadIdx.x % TEAM;
     ch.mask = team_mask<TEAM>();
     ch.d = p.d;
     ch.nown = p.n_own;
     ch.chain = c;
-    ch.stride = kBlockThreads;
-    ch.xs = smem + threadIdx.x;
-    ch.vs = smem + (size_t)p.n_own * kBlockThreads + threadIdx.x;
+    const size_t vec = (size_t)p.n_own * kBlockThreads;  // one owned-column vector for the whole block
+    ch.off_x = threadIdx.x;
+    ch.off_v = (int)vec + threadIdx.x;
+    size_t used = 2;
+    ch.off_a = ch.off_b = 0;
+    if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent) {
+        ch.off_a = 2 * (int)vec + threadIdx.x;
+        ch.off_b = 3 * (int)vec + threadIdx.x;
+        used = 4;
+    }
     if (p.scratch_in_smem) {
         ch.sstride = kBlockThreads;
-        double* base = smem + 2 * (size_t)p.n_own * kBlockThreads + threadIdx.x;
+        double* base = smem + used * vec + threadIdx.x;
         ch.sc0 = base;
         ch.sc1 = base + (size_t)p.n_own * kBlockThreads;
         ch.sc2 = base + 2 * (size_t)p.n_own * kBlockThreads;
@@ -865,8 +1104,8 @@ __global__ void __launch_bounds__(kBlockThreads) skeleton_kernel(const KernelPar
     // load PDMPState
     for (int j = 0; j < ch.nown; ++j)
         if (ch.owns(j)) {
-            ch.xs[j * ch.stride] = p.sx[c * p.d + ch.coord(j)];
-            ch.vs[j * ch.stride] = p.sv[c * p.d + ch.coord(j)];
+            g_smem[ch.off_x + j * kBlockThreads] = p.sx[c * p.d + ch.coord(j)];
+            g_smem[ch.off_v + j * kBlockThreads] = p.sv[c * p.d + ch.coord(j)];
         }
     ch.t = p.st[c];
     ch.horizon = p.shorizon[c];
@@ -890,20 +1129,12 @@ __global__ void __launch_bounds__(kBlockThreads) skeleton_kernel(const KernelPar
         ch.record(c, p.col0);
         return;
     }
-    if (ch.status == 0) {
-        for (int64_t ev = 0; ev < p.n_events; ++ev) {
-            ch.key.event = (uint32_t)(p.event0 + ev + 1);
-            ch.sE = ch.sU = ch.sN = 0;
-            ch.get_event_state();
-            if (ch.status != 0) break;
-            ch.record(c, p.col0 + ev);
-        }
-    }
+    if (ch.status == 0) ch.run_events(c);
     // store PDMPState
     for (int j = 0; j < ch.nown; ++j)
         if (ch.owns(j)) {
-            p.sx[c * p.d + ch.coord(j)] = ch.xs[j * ch.stride];
-            p.sv[c * p.d + ch.coord(j)] = ch.vs[j * ch.stride];
+            p.sx[c * p.d + ch.coord(j)] = g_smem[ch.off_x + j * kBlockThreads];
+            p.sv[c * p.d + ch.coord(j)] = g_smem[ch.off_v + j * kBlockThreads];
         }
     if (ch.tl == 0) {
         p.st[c] = ch.t;

@@ -29,6 +29,7 @@ struct KernelParams {
     int d, G, vectorized, signed_bound, adaptive, deriv_mode;
     int gaussian_velocity, ran_p, switch_, positive, max_steps;
     double tmax, refresh_rate, bound_refresh, mix_p, speed_factor;
+    double inv_gm1;  // 1 / (grid_size - 1)
     PotParams pot;
     // chains
     int64_t n_chains, chain_offset;

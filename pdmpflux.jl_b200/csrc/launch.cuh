@@ -4,44 +4,71 @@
 
 namespace pdmpflux {
 
-template <int TEAM, int SAMPLER, int POT>
+template <int TEAM, int SAMPLER, int POT, int PATH>
 cudaError_t launch_one(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
-    auto kern = skeleton_kernel<TEAM, SAMPLER, POT>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    // combinations without a fast path fall back to the generic kernel (same results, more passes)
+    constexpr bool ok = PATH == kPathGeneric ||
+                        (Pot<POT>::kAffine && !(SAMPLER == PDMPFLUX_BOOMERANG && Pot<POT>::kSpecial > 0));
+    if constexpr (!ok) return cudaErrorInvalidValue;
+    else {
+        auto kern = skeleton_kernel<TEAM, SAMPLER, POT, PATH>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kBlockThreads, smem, stream>>>(p);
+        return cudaGetLastError();
     }
-    kern<<<grid, kBlockThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+}
+
+template <int TEAM, int SAMPLER, int POT>
+cudaError_t launch_for_pot(int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
+    switch (path) {
+    case kPathGeneric: return launch_one<TEAM, SAMPLER, POT, kPathGeneric>(p, grid, smem, stream);
+    case kPathFastBrent: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent>(p, grid, smem, stream);
+    case kPathFastGrid: return launch_one<TEAM, SAMPLER, POT, kPathFastGrid>(p, grid, smem, stream);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 template <int TEAM, int SAMPLER>
-cudaError_t launch_for_team(int pot, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
+cudaError_t launch_for_team(int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
     switch (pot) {
-    case PDMPFLUX_GAUSS_STD: return launch_one<TEAM, SAMPLER, PDMPFLUX_GAUSS_STD>(p, grid, smem, stream);
-    case PDMPFLUX_GAUSS_DIAG: return launch_one<TEAM, SAMPLER, PDMPFLUX_GAUSS_DIAG>(p, grid, smem, stream);
-    case PDMPFLUX_GAUSS_EQUICORR: return launch_one<TEAM, SAMPLER, PDMPFLUX_GAUSS_EQUICORR>(p, grid, smem, stream);
-    case PDMPFLUX_BANANA: return launch_one<TEAM, SAMPLER, PDMPFLUX_BANANA>(p, grid, smem, stream);
+    case PDMPFLUX_GAUSS_STD: return launch_for_pot<TEAM, SAMPLER, PDMPFLUX_GAUSS_STD>(path, p, grid, smem, stream);
+    case PDMPFLUX_GAUSS_DIAG: return launch_for_pot<TEAM, SAMPLER, PDMPFLUX_GAUSS_DIAG>(path, p, grid, smem, stream);
+    case PDMPFLUX_GAUSS_EQUICORR: return launch_for_pot<TEAM, SAMPLER, PDMPFLUX_GAUSS_EQUICORR>(path, p, grid, smem, stream);
+    case PDMPFLUX_BANANA: return launch_for_pot<TEAM, SAMPLER, PDMPFLUX_BANANA>(path, p, grid, smem, stream);
     case PDMPFLUX_BANANA_README_SCALAR:
-        return launch_one<TEAM, SAMPLER, PDMPFLUX_BANANA_README_SCALAR>(p, grid, smem, stream);
+        return launch_for_pot<TEAM, SAMPLER, PDMPFLUX_BANANA_README_SCALAR>(path, p, grid, smem, stream);
     default: return cudaErrorInvalidValue;
     }
 }
 
 template <int SAMPLER>
-cudaError_t launch_for_sampler(int team, int pot, const KernelParams& p, unsigned grid, size_t smem,
+cudaError_t launch_for_sampler(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem,
                                cudaStream_t stream) {
     switch (team) {
-    case 1: return launch_for_team<1, SAMPLER>(pot, p, grid, smem, stream);
-    case 8: return launch_for_team<8, SAMPLER>(pot, p, grid, smem, stream);
-    case 32: return launch_for_team<32, SAMPLER>(pot, p, grid, smem, stream);
+    case 1: return launch_for_team<1, SAMPLER>(pot, path, p, grid, smem, stream);
+    case 8: return launch_for_team<8, SAMPLER>(pot, path, p, grid, smem, stream);
+    case 32: return launch_for_team<32, SAMPLER>(pot, path, p, grid, smem, stream);
     default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_skeleton_zigzag(int team, int pot, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_skeleton_bps(int team, int pot, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_skeleton_fecmc(int team, int pot, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_skeleton_boomerang(int team, int pot, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
+// which path a (sampler, potential, config) combination runs on; mirrors the `ok` condition of launch_one
+inline int select_path(int sampler, int pot, int grid_size, int vectorized, int deriv_mode) {
+    const bool affine = pot == PDMPFLUX_GAUSS_STD || pot == PDMPFLUX_GAUSS_DIAG || pot == PDMPFLUX_GAUSS_EQUICORR ||
+                        pot == PDMPFLUX_BANANA;
+    if (!affine || (sampler == PDMPFLUX_BOOMERANG && pot == PDMPFLUX_BANANA)) return kPathGeneric;
+    if (grid_size == 0) return kPathFastBrent;
+    if (deriv_mode != PDMPFLUX_DERIV_JVP) return kPathGeneric;
+    if (sampler == PDMPFLUX_ZIGZAG && !vectorized) return kPathGeneric;
+    return kPathFastGrid;
+}
+
+cudaError_t launch_skeleton_zigzag(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_skeleton_bps(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_skeleton_fecmc(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_skeleton_boomerang(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 
 }  // namespace pdmpflux

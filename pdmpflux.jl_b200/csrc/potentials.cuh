@@ -10,6 +10,11 @@
 //   grad (pp, i, xi, Lx)                  -> (grad U(x))_i
 //   eval (pp, i, xi, di, Lx, Ld, g, hd)   g = (grad U(x))_i, hd = (H(x) dir)_i with dir_i = di, L(dir) = Ld
 //
+// Line structure used by the fast paths (chain.cuh): for `kAffine` potentials the Hessian is constant and
+// decoupled for every coordinate i >= kSpecial, so along x + t v the signed coordinate rate is exactly
+// A_i + t B_i with A_i = g_i(x) v_i, B_i = (H v)_i v_i; the first kSpecial coordinates are functions of the
+// functionals L_0..L_{kSpecial-1} (= those coordinates themselves) and are evaluated per time by every lane.
+//
 // Formulas: SURVEY.md Appendix A (GAUSS_STD README.md:36-38; BANANA test/test_config.jl:33-36;
 // BANANA_README_SCALAR README.md:62-65; the others are not defined upstream).
 #pragma once
@@ -23,6 +28,8 @@ struct Pot;
 template <>
 struct Pot<PDMPFLUX_GAUSS_STD> {
     static constexpr int K = 0;
+    static constexpr bool kAffine = true;   // g_i(x + t v) v_i is affine in t for every i >= kSpecial
+    static constexpr int kSpecial = 0;
     __device__ static void accum(const PotParams&, int, double, double*) {}
     __device__ static double grad(const PotParams&, int, double xi, const double*) { return xi; }
     __device__ static void eval(const PotParams&, int, double xi, double di, const double*, const double*,
@@ -34,6 +41,8 @@ struct Pot<PDMPFLUX_GAUSS_STD> {
 template <>
 struct Pot<PDMPFLUX_GAUSS_DIAG> {
     static constexpr int K = 0;
+    static constexpr bool kAffine = true;
+    static constexpr int kSpecial = 0;
     __device__ static void accum(const PotParams&, int, double, double*) {}
     __device__ static double grad(const PotParams& pp, int i, double xi, const double*) {
         return __ldg(pp.vec + i) * xi;
@@ -48,6 +57,8 @@ struct Pot<PDMPFLUX_GAUSS_DIAG> {
 template <>
 struct Pot<PDMPFLUX_GAUSS_EQUICORR> {  // P = alpha I - beta 1 1^T
     static constexpr int K = 1;
+    static constexpr bool kAffine = true;
+    static constexpr int kSpecial = 0;
     __device__ static void accum(const PotParams&, int, double xi, double* acc) { acc[0] += xi; }
     __device__ static double grad(const PotParams& pp, int, double xi, const double* Lx) {
         return pp.alpha * xi - pp.beta * Lx[0];
@@ -62,6 +73,8 @@ struct Pot<PDMPFLUX_GAUSS_EQUICORR> {  // P = alpha I - beta 1 1^T
 template <>
 struct Pot<PDMPFLUX_BANANA> {  // L0 = x_1, L1 = x_2 (1-based); r = x2 - x1^2 + 1
     static constexpr int K = 2;
+    static constexpr bool kAffine = true;   // coordinates >= 2 are standard-Gaussian
+    static constexpr int kSpecial = 2;      // coordinates 0, 1 are polynomial in t and functions of (L0, L1) only
     __device__ static void accum(const PotParams&, int i, double xi, double* acc) {
         if (i == 0) acc[0] += xi;
         if (i == 1) acc[1] += xi;
@@ -88,6 +101,8 @@ struct Pot<PDMPFLUX_BANANA> {  // L0 = x_1, L1 = x_2 (1-based); r = x2 - x1^2 + 
 template <>
 struct Pot<PDMPFLUX_BANANA_README_SCALAR> {  // every coordinate = x1 + (x2 - (x1^2 - 1)) + sum_{i>=3} x_i
     static constexpr int K = 3;
+    static constexpr bool kAffine = false;
+    static constexpr int kSpecial = 0;
     __device__ static void accum(const PotParams&, int i, double xi, double* acc) {
         if (i == 0) acc[0] += xi;
         else if (i == 1) acc[1] += xi;

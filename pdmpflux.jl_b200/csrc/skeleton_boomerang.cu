@@ -4,8 +4,8 @@
 #include "launch.cuh"
 
 namespace pdmpflux {
-cudaError_t launch_skeleton_boomerang(int team, int pot, const KernelParams& p, unsigned grid, size_t smem,
+cudaError_t launch_skeleton_boomerang(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem,
                                  cudaStream_t stream) {
-    return launch_for_sampler<PDMPFLUX_BOOMERANG>(team, pot, p, grid, smem, stream);
+    return launch_for_sampler<PDMPFLUX_BOOMERANG>(team, pot, path, p, grid, smem, stream);
 }
 }  // namespace pdmpflux

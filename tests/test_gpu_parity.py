@@ -60,10 +60,15 @@ def set_team(team):
         os.environ.pop("PDMPFLUX_TEAM", None)
 
 
+@pytest.mark.parametrize("generic", [0, 1], ids=["auto", "generic"])
 @pytest.mark.parametrize("team", [1, 8, 32])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_one_step_parity(p, case, team):
+def test_one_step_parity(p, case, team, generic):
+    """`auto` runs the path the library picks (affine fast paths where they exist); `generic` forces the
+    per-node generic kernel on the same case, so both implementations are held to the oracle."""
     name, sampler, pk, pp, d, kw, n_sk = case
+    if generic and team != 8:
+        pytest.skip("generic path is exercised at one team width")
     if team == 1 and d > 100:
         pytest.skip("thread-per-chain is for small d")
     pp = pot_params(pp, d)
@@ -81,11 +86,13 @@ def test_one_step_parity(p, case, team):
     tN = pad(N[0], wN)[idx(pos[:-1, 2], wN)]
     s = make_sampler(p, sampler, pk, pp, d, kw)
     set_team(team)
+    os.environ["PDMPFLUX_FORCE_GENERIC"] = str(generic)
     try:
         h = p.sample_skeleton(s, 2, r.X[0, :-1], r.V[0, :-1], tape=(tE, tU, tN), t0=r.t[0, :-1],
                               horizon0=r.horizon[0, :-1], batch=True)
     finally:
         set_team(None)
+        os.environ.pop("PDMPFLUX_FORCE_GENERIC")
     tol = tier_tolerance(kw)
     assert np.array_equal(h.X[:, 0], r.X[0, :-1]) and np.array_equal(h.t[:, 0], r.t[0, :-1])
     scale_x = np.maximum(np.abs(r.X[0, 1:]).max(axis=1), 1e-300)
