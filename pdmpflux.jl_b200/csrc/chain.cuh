@@ -123,7 +123,10 @@ struct Chain {
     // ------------------------------------------------------------------------------------------------
     // helpers
     // ------------------------------------------------------------------------------------------------
-    __device__ __forceinline__ bool owns(int j) const { return tl + TEAM * j < d; }
+    __device__ __forceinline__ bool owns(int j) const {
+        if constexpr (TEAM == 1) return true;  // nown == d
+        else return tl + TEAM * j < d;
+    }
     __device__ __forceinline__ int coord(int j) const { return tl + TEAM * j; }
 
     // functionals of the current x and v (one fused multi-value reduction)
@@ -653,6 +656,9 @@ struct Chain {
     // velocity jumps (x already moved; functionals of x are recomputed here)
     // ------------------------------------------------------------------------------------------------
     __device__ void jump_zigzag() {  // ZigZagSamplers.jl:101-107 + Distributions.jl categorical CDF scan
+        // lambda_i = max(0, g_i v_i), p = lambda / S, m = first index with cumsum(p)_m > u (else the last index).
+        // cumsum(p)_m > u  <=>  cumsum(lambda)_m > u S, so the d divisions are not needed; isprobvec(p) (all p >= 0,
+        // sum p ~ 1, else the reference's Categorical constructor throws) holds iff S is finite and positive.
         double S = 0.0;
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
@@ -660,32 +666,18 @@ struct Chain {
                 S += (y > 0.0 ? y : 0.0);
             }
         S = team_sum<TEAM>(S, mask);
-        // isprobvec(p): all(p .>= 0) && sum(p) ~ 1, else the reference's Categorical constructor throws
-        double chk[2] = {0.0, 0.0};
-        for (int j = 0; j < nown; ++j)
-            if (owns(j)) {
-                const double y = P::grad(p.pot, coord(j), XS(j), Lx) * VS(j);
-                const double pj = (y > 0.0 ? y : 0.0) / S;
-                if (!(pj >= 0.0)) chk[0] += 1.0;
-                chk[1] += pj;
-            }
-        team_sum_n<TEAM, 2>(chk, mask);
-        if (chk[0] > 0.0 || !(fabs(chk[1] - 1.0) <= kSqrtEps * fmax(fabs(chk[1]), 1.0))) {
-            status = PDMPFLUX_CHAIN_NOT_PROBVEC;
-            return;
-        }
-        const double u = rand_uniform();
-        // first index with cumulative p > u, else the last index
+        if (!(S > 0.0) || !(S < CUDART_INF)) { status = PDMPFLUX_CHAIN_NOT_PROBVEC; return; }
+        const double uS = rand_uniform() * S;
         double carry = 0.0;
         int m = d - 1;
         for (int j = 0; j < nown; ++j) {
-            double pj = 0.0;
+            double lj = 0.0;
             if (owns(j)) {
                 const double y = P::grad(p.pot, coord(j), XS(j), Lx) * VS(j);
-                pj = (y > 0.0 ? y : 0.0) / S;
+                lj = (y > 0.0 ? y : 0.0);
             }
-            const double incl = team_scan_incl<TEAM>(pj, mask, tl) + carry;
-            const bool hit = owns(j) && (incl > u);
+            const double incl = team_scan_incl<TEAM>(lj, mask, tl) + carry;
+            const bool hit = owns(j) && (incl > uS);
             int first = -1;
             if constexpr (TEAM == 1) first = hit ? 0 : -1;
             else {
@@ -972,6 +964,8 @@ struct Chain {
         accept = false;
         begin_event(0);
         while (ev < p.n_events) {
+            // No `continue` in this loop: both blocks are plain ifs so that every lane of the warp reconverges at
+            // the end of each block (lanes that skip a block wait for the ones inside it, then all proceed).
             if (need_build) {
                 if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; break; }
                 double h = horizon;
@@ -991,48 +985,49 @@ struct Chain {
                     eva[eb % 5] = ar;
                     half = false;
                     need_build = false;  // back in moves_until_horizon!; a proposal beyond the horizon restarts below
-                } else if (tp > horizon) {  // move_to_horizon!, :87-101
+                } else if (tp > horizon) {  // move_to_horizon!, :87-101 (need_build stays set)
                     flow_inplace(horizon);
                     ts += horizon;
                     hh += 1;
                     horizon = p.adaptive ? horizon * 1.01 : horizon;
-                    continue;
                 } else need_build = false;
             }
-            // moves_until_horizon!, :103-111: `while tp < horizon && !accept` -- otherwise a fresh outer step
-            if (!(tp < horizon)) { need_build = true; continue; }
-            // ac_step!, :113-129
-            ++n_rates;
-            const double lt = rate_unsigned(tp);
-            ar = lt / lambda_bar;
-            if (ar > 1.0) { need_build = true; half = true; continue; }
-            // ac_step_with_proxy!, :153-168
-            const bool acc = rand_uniform() < ar;
-            if (acc) {  // if_accept!, :170-186
-                flow_inplace(tp);
-                velocity_jump();
-                t = t + tp + ts;
-                ts = 0.0;
-                tp = 0.0;
-                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
-                if (status != 0) break;
-                record(c, p.col0 + ev);
-                ++ev;
-                steps = 0;
-                begin_event(ev);
-                need_build = true;
-            } else {  // if_reject!, :188-203
-                const double e3 = exp_rv + rand_exp();
-                next_event(e3, tp, lambda_bar);
-                horizon = p.adaptive ? horizon / 1.04 : horizon;  // QUIRK: shrink before the horizon check
-                exp_rv = e3;
-                rej += 1;
-                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
-                if (tp > horizon) {  // move_to_horizon2!, :205-217 (no horizon growth here)
-                    flow_inplace(horizon);
-                    ts += horizon;
-                    hh += 1;
-                    need_build = true;
+            if (!need_build) {
+                // moves_until_horizon!, :103-111: `while tp < horizon && !accept` -- otherwise a fresh outer step
+                if (!(tp < horizon)) need_build = true;
+                else {
+                    // ac_step!, :113-129
+                    ++n_rates;
+                    const double lt = rate_unsigned(tp);
+                    ar = lt / lambda_bar;
+                    if (ar > 1.0) { need_build = true; half = true; }
+                    else if (rand_uniform() < ar) {  // ac_step_with_proxy!, :153-168 -> if_accept!, :170-186
+                        flow_inplace(tp);
+                        velocity_jump();
+                        t = t + tp + ts;
+                        ts = 0.0;
+                        tp = 0.0;
+                        if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
+                        if (status != 0) break;
+                        record(c, p.col0 + ev);
+                        ++ev;
+                        steps = 0;
+                        begin_event(ev);
+                        need_build = true;
+                    } else {  // if_reject!, :188-203
+                        const double e3 = exp_rv + rand_exp();
+                        next_event(e3, tp, lambda_bar);
+                        horizon = p.adaptive ? horizon / 1.04 : horizon;  // QUIRK: shrink before the horizon check
+                        exp_rv = e3;
+                        rej += 1;
+                        if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
+                        if (tp > horizon) {  // move_to_horizon2!, :205-217 (no horizon growth here)
+                            flow_inplace(horizon);
+                            ts += horizon;
+                            hh += 1;
+                            need_build = true;
+                        }
+                    }
                 }
             }
         }
