@@ -68,7 +68,7 @@ struct pdmpflux_chains_s {
     pdmpflux_sampler_s* s = nullptr;
     int64_t n_chains = 0, chain_offset = 0, event0 = 0;
     uint64_t seed = 0;
-    int team = 32, n_own = 0, scratch_in_smem = 1, path = 0;
+    int team = 32, n_own = 0, scratch_in_smem = 1, path = 0, vec_elems = 0, dpad = 0;
     size_t smem = 0;
     unsigned grid = 0;
     DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch;
@@ -123,6 +123,28 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     }
     p.col0 = col0;
     p.scratch = ch->scratch.as<double>(); p.scratch_in_smem = ch->scratch_in_smem; p.n_own = ch->n_own;
+    p.vec_elems = ch->vec_elems; p.dpad = ch->dpad;
+    if (h) {
+        auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+        p.vec32 = al(h->X, 32) && al(h->V, 32) && al(h->t, 32) && al(h->horizon, 32) && al(h->ar, 32);
+        p.bulk_rows = ch->team > 1 && (s->dim % 2 == 0) && al(h->X, 16) && al(h->V, 16);
+        if (const char* e = std::getenv("PDMPFLUX_NO_BULK")) { if (std::atoi(e)) { p.bulk_rows = 0; p.vec32 = 0; } }
+        // Diagnostic columns that are almost always zero are zero-filled here (one strided fill each) and the
+        // kernel writes only their non-zero entries.
+        p.sparse_cols = 1;
+        const int64_t ncols = n_events > 0 ? n_events : 1;
+        auto fill = [&](void* base, size_t elem) -> cudaError_t {
+            if (!base) return cudaSuccess;
+            char* q = static_cast<char*>(base) + (size_t)col0 * elem;
+            if (ncols == h->n_cols) return cudaMemsetAsync(q, 0, (size_t)ch->n_chains * ncols * elem, stream);
+            return cudaMemset2DAsync(q, (size_t)h->n_cols * elem, 0, (size_t)ncols * elem, (size_t)ch->n_chains, stream);
+        };
+        cudaError_t fe = fill(h->error_value_ar, 5 * sizeof(double));
+        if (fe == cudaSuccess) fe = fill(h->errored_bound, sizeof(int32_t));
+        if (fe == cudaSuccess) fe = fill(h->rejected, sizeof(int32_t));
+        if (fe == cudaSuccess) fe = fill(h->hitting_horizon, sizeof(int32_t));
+        if (fe != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("zero-fill of diagnostic columns: ") + cudaGetErrorString(fe));
+    }
     cudaError_t e;
     switch (s->kind) {
     case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
@@ -328,7 +350,13 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     ch->n_own = (d + ch->team - 1) / ch->team;
     const int cpb = kBlockThreads / ch->team;
     ch->grid = (unsigned)((n_chains + cpb - 1) / cpb);
-    const size_t vec_bytes = (size_t)ch->n_own * kBlockThreads * sizeof(double);
+    if (ch->team == 1) { ch->dpad = 0; ch->vec_elems = ch->n_own * kBlockThreads; }
+    else {
+        ch->dpad = ch->n_own * ch->team;
+        if (ch->team < 32) while (ch->dpad % 16 != 8) ch->dpad += 8;  // chains of a warp land on distinct bank halves
+        ch->vec_elems = cpb * ch->dpad;
+    }
+    const size_t vec_bytes = (size_t)ch->vec_elems * sizeof(double);
     ch->path = select_path(s->kind, s->pot->kind, s->cfg.grid_size, s->cfg.vectorized_bound, s->cfg.deriv_mode);
     if (const char* e = std::getenv("PDMPFLUX_FORCE_GENERIC")) { if (std::atoi(e)) ch->path = kPathGeneric; }
     const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent) ? 4 : 2;
@@ -340,6 +368,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
             CUDA_TRY(ch->scratch.alloc((size_t)ch->grid * 3 * vec_bytes));
         }
     }
+    if (ch->team == 1) ch->smem += 6 * kBlockThreads * sizeof(double);  // row carry slots (record())
     if (ch->smem > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "dimension too large for the shared-memory state layout");
     CUDA_TRY(ch->x.alloc(sizeof(double) * d * n_chains));
     CUDA_TRY(ch->v.alloc(sizeof(double) * d * n_chains));

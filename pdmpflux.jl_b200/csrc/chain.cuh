@@ -24,11 +24,16 @@ namespace pdmpflux {
 // Dynamic shared memory of the skeleton kernels.  x, v (and the ZigZag line model A, B) are addressed through
 // this symbol with per-thread element offsets so the compiler emits LDS/STS (pointers stored in the Chain object
 // degrade to generic loads).
-extern __shared__ double g_smem[];
-#define XS(j) g_smem[off_x + (j) * kBlockThreads]
-#define VS(j) g_smem[off_v + (j) * kBlockThreads]
-#define AS(j) g_smem[off_a + (j) * kBlockThreads]
-#define BS(j) g_smem[off_b + (j) * kBlockThreads]
+// Layout of one state vector (x, v, ...):
+//   TEAM == 1: element (coordinate j, thread) at j * kBlockThreads + thread            (bank-conflict free)
+//   TEAM  > 1: chain-contiguous, coordinate i of local chain c at c * dpad + i, i.e. owned coordinate j of team
+//              lane tl at c * dpad + tl + j * TEAM.  A chain's x (v) is then one contiguous run of d doubles, which
+//              is exactly a skeleton row: it is shipped to HBM by a single TMA bulk copy.
+extern __shared__ __align__(128) double g_smem[];
+#define XS(j) g_smem[off_x + (j) * kStr]
+#define VS(j) g_smem[off_v + (j) * kStr]
+#define AS(j) g_smem[off_a + (j) * kStr]
+#define BS(j) g_smem[off_b + (j) * kStr]
 
 // PATH selects how the bound and the rates are evaluated:
 //   kPathGeneric   every grid node / Brent iterate makes a pass over the coordinates (any potential, any option)
@@ -54,13 +59,13 @@ struct Chain {
     static constexpr int KK = K > 0 ? K : 1;
     static constexpr bool kRot = (SAMPLER == PDMPFLUX_BOOMERANG);
     static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG);
+    static constexpr int kStr = (TEAM == 1) ? kBlockThreads : TEAM;  // stride between a thread's owned elements
 
     const KernelParams& p;
     int off_x, off_v, off_a, off_b;  // element offsets into g_smem of this thread's owned columns of x, v, A, B
     double* sc0; // scratch owned vectors (FECMC)
     double* sc1;
     double* sc2;
-    int sstride;
     int tl, d, nown;
     unsigned mask;
     int64_t chain;
@@ -84,6 +89,13 @@ struct Chain {
     double box[kMaxGrid], cum[kMaxGrid];
     double step, gc, grem, gh;
     int nb;
+
+    // output staging (see record())
+    int off_f;               // TEAM == 1: 2 x 3 carry slots (x, v) in shared memory, slot s at off_f + s * kBlockThreads
+    int fcnt, fskip;         // row stream: elements carried over / leading phantom slots of the first 32-byte group
+    int scnt, sskip;         // scalar columns t / horizon / ar: staged events / leading phantom slots
+    double st_t[3], st_h[3], st_a[3];
+    bool bulk_pending;
 
     // draws
     DrawKey key;
@@ -173,6 +185,7 @@ struct Chain {
     }
 
     __device__ void flow_inplace(double tt) {
+        wait_row_stores();  // x / v are about to change: the TMA engine must have read the previous row
         const Flow f = flow_coef(tt);
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
@@ -276,18 +289,22 @@ struct Chain {
             line_scalar(tt, y, dy);
             return (y > 0.0 ? y : 0.0) + extra_rate();
         } else if constexpr (kZZ && PATH == kPathFastBrent) {
+            // max(0, y) = (y + |y|) / 2 exactly in binary floating point: one DADD (|.| is an operand modifier)
+            // instead of a compare and two selects; the halving is applied once to the sum.
             double s0 = 0.0, s1 = 0.0;  // two accumulators: shorter dependency chain
             int j = 0;
             for (; j + 1 < nown; j += 2) {
                 const double y0 = fma(tt, BS(j), AS(j));
                 const double y1 = fma(tt, BS(j + 1), AS(j + 1));
-                s0 += (y0 > 0.0 ? y0 : 0.0);
-                s1 += (y1 > 0.0 ? y1 : 0.0);
+                s0 += y0 + fabs(y0);
+                s1 += y1 + fabs(y1);
             }
             if (j < nown) {
                 const double y0 = fma(tt, BS(j), AS(j));
-                s0 += (y0 > 0.0 ? y0 : 0.0);
+                s0 += y0 + fabs(y0);
             }
+            s0 = 0.5 * (s0 + s1);
+            s1 = 0.0;
             double s = team_sum<TEAM>(s0 + s1, mask);
             if constexpr (NS > 0) {
                 double ys[NS], dys[NS];
@@ -392,11 +409,13 @@ struct Chain {
         make_grid(h, G);
         for (int k0 = 0; k0 < G - 1; k0 += kChunk) {
             const int nc = min(kChunk, G - 1 - k0);
-            double bacc[kChunk], tn[kChunk + 1];
+            double bacc[kChunk], tn[kChunk + 1], tm_[kChunk], th_[kChunk];
 #pragma unroll
             for (int u = 0; u < kChunk; ++u) bacc[u] = 0.0;
 #pragma unroll
             for (int u = 0; u <= kChunk; ++u) tn[u] = grid_t(min(k0 + u, G - 1));
+#pragma unroll
+            for (int u = 0; u < kChunk; ++u) { tm_[u] = 0.5 * (tn[u] + tn[u + 1]); th_[u] = 0.5 * (tn[u + 1] - tn[u]); }
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const int i = coord(j);
@@ -404,16 +423,17 @@ struct Chain {
                     if constexpr (kFast) {
                         if (i < NS) continue;  // special coordinates are added once, after the reduction
                         // affine coordinate: max(val_l, val_r, inter, 0) == max(val_l, val_r, 0); holds for the
-                        // unsigned variant max(0, .) as well (see DESIGN.md "affine cells")
+                        // unsigned variant max(0, .) as well (see DESIGN.md "affine cells").  With the cell midpoint
+                        // tm and half width th: max(val_l, val_r) = A + B tm + |B| th, and max(m, 0) = (m + |m|) / 2
+                        // -- four FP64 instructions per (coordinate, cell), no compares or selects.
                         double g, hv;
                         P::eval(p.pot, i, xi, vi, Lx, Lv, g, hv);
-                        const double A = g * vi, B = hv * vi;
-                        const bool up = (B >= 0.0);
+                        const double A = g * vi, B = hv * vi, aB = fabs(B);
 #pragma unroll
                         for (int u = 0; u < kChunk; ++u)
                             if (u < nc) {
-                                const double y = fma(up ? tn[u + 1] : tn[u], B, A);
-                                bacc[u] += (y > 0.0 ? y : 0.0);
+                                const double m = fma(aB, th_[u], fma(B, tm_[u], A));
+                                bacc[u] += m + fabs(m);
                             }
                     } else {
                         double vl, gl;
@@ -428,6 +448,10 @@ struct Chain {
                             }
                     }
                 }
+            if constexpr (kFast) {
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) bacc[u] *= 0.5;
+            }
             team_sum_n<TEAM, kChunk>(bacc, mask);
             if constexpr (kFast && NS > 0) {  // special coordinates: the reference's cell formula, every lane
                 double yl[NS], dl[NS];
@@ -516,18 +540,31 @@ struct Chain {
     __device__ void build_bound_scalar(double h) {
         const int G = p.G;
         make_grid(h, G);
-        if constexpr (kFast && !kZZ) {  // O(1) nodes from the line model, analytic derivative
-            double vl, gl, cs = 0.0;
-            {
+        if constexpr (kFast && !kZZ) {  // O(1) nodes from the line model
+            // value and d/dt of the bound function at node time tt: analytic, or the reference's
+            // finite_difference_derivative (UpperBound.jl:50-76) applied to the closed-form value
+            auto node = [&](double tt, double& val, double& dval) {
                 double y, dy;
-                line_scalar(0.0, y, dy);
-                finish_scalar(y, dy, vl, gl);
-            }
+                line_scalar(tt, y, dy);
+                finish_scalar(y, dy, val, dval);
+                if (p.deriv_mode != PDMPFLUX_DERIV_JVP) {
+                    const double hh_ = kSqrtEps * fmax(1.0, fabs(tt));
+                    const double xm = fmax(0.0, tt - hh_), xp = fmin(h, tt + hh_);
+                    if (xp == xm) dval = val - val;
+                    else {
+                        double fp = val, fm = val, dum;
+                        if (xp != tt) { line_scalar(xp, y, dy); finish_scalar(y, dy, fp, dum); }
+                        if (xm != tt) { line_scalar(xm, y, dy); finish_scalar(y, dy, fm, dum); }
+                        dval = (fp - fm) / (xp - xm);
+                    }
+                }
+            };
+            double vl, gl, cs = 0.0;
+            node(0.0, vl, gl);
             cum[0] = 0.0;
             for (int k = 0; k < G - 1; ++k) {
-                double y, dy, vr, gr;
-                line_scalar(grid_t(k + 1), y, dy);
-                finish_scalar(y, dy, vr, gr);
+                double vr, gr;
+                node(grid_t(k + 1), vr, gr);
                 const double b = scalar_cell(vl, gl, vr, gr);
                 box[k] = b;
                 cs += b;
@@ -792,7 +829,7 @@ struct Chain {
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
                 const double o = VS(j) - vn * nvec(j);
-                vo[j * sstride] = o;
+                vo[j * kStr] = o;
                 nvo += o * o;
             }
         nvo = team_sum<TEAM>(nvo, mask);
@@ -802,7 +839,7 @@ struct Chain {
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const double z = rand_normal_at(coord(j));
-                    vo[j * sstride] = z;
+                    vo[j * kStr] = z;
                     a += z * nvec(j);
                 }
             normals_advance(d);
@@ -810,8 +847,8 @@ struct Chain {
             nvo = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double o = vo[j * sstride] - a * nvec(j);
-                    vo[j * sstride] = o;
+                    const double o = vo[j * kStr] - a * nvec(j);
+                    vo[j * kStr] = o;
                     nvo += o * o;
                 }
             nvo = team_sum<TEAM>(nvo, mask);
@@ -821,7 +858,7 @@ struct Chain {
         if (u2 >= p.mix_p) {
             const double nrm = sqrt(nvo);
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) VS(j) = vo[j * sstride] / nrm * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = vo[j * kStr] / nrm * rad + rho * nvec(j);
             return;
         }
         double* prop = sc1;
@@ -834,7 +871,7 @@ struct Chain {
                 if (owns(j)) {
                     const double z1 = rand_normal_at(2 * (int64_t)coord(j));
                     const double z2 = rand_normal_at(2 * (int64_t)coord(j) + 1);
-                    e1[j * sstride] = z1; e2[j * sstride] = z2;
+                    e1[j * kStr] = z1; e2[j * kStr] = z2;
                     const double n = nvec(j);
                     a[0] += z1 * n; a[1] += z2 * n;
                 }
@@ -844,35 +881,35 @@ struct Chain {
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const double n = nvec(j);
-                    const double g1 = e1[j * sstride] - a[0] * n;
-                    e1[j * sstride] = g1;
-                    e2[j * sstride] = e2[j * sstride] - a[1] * n;
+                    const double g1 = e1[j * kStr] - a[0] * n;
+                    e1[j * kStr] = g1;
+                    e2[j * kStr] = e2[j * kStr] - a[1] * n;
                     n1 += g1 * g1;
                 }
             n1 = sqrt(team_sum<TEAM>(n1, mask));
             double b = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = e1[j * sstride] / n1;
-                    e1[j * sstride] = q;
-                    b += e2[j * sstride] * q;
+                    const double q = e1[j * kStr] / n1;
+                    e1[j * kStr] = q;
+                    b += e2[j * kStr] * q;
                 }
             b = team_sum<TEAM>(b, mask);
             double n2 = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = e2[j * sstride] - b * e1[j * sstride];
-                    e2[j * sstride] = q;
+                    const double q = e2[j * kStr] - b * e1[j * kStr];
+                    e2[j * kStr] = q;
                     n2 += q * q;
                 }
             n2 = sqrt(team_sum<TEAM>(n2, mask));
             double c[2] = {0.0, 0.0};
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = e2[j * sstride] / n2;
-                    e2[j * sstride] = q;
-                    c[0] += vo[j * sstride] * e1[j * sstride];
-                    c[1] += vo[j * sstride] * q;
+                    const double q = e2[j * kStr] / n2;
+                    e2[j * kStr] = q;
+                    c[0] += vo[j * kStr] * e1[j * kStr];
+                    c[1] += vo[j * kStr] * q;
                 }
             team_sum_n<TEAM, 2>(c, mask);
             double ct = 0.0, st = 0.0;
@@ -883,12 +920,12 @@ struct Chain {
             double r3[2] = {0.0, 0.0};  // <vo, prop>, <prop, prop>
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q1 = e1[j * sstride], q2 = e2[j * sstride], o = vo[j * sstride];
+                    const double q1 = e1[j * kStr], q2 = e2[j * kStr], o = vo[j * kStr];
                     const double vr = o - c[0] * q1 - c[1] * q2;
                     double pr;
                     if (p.ran_p) pr = vr + (ct * q1 + st * q2) * c[0] + (st * q1 - ct * q2) * c[1];
                     else pr = vr + q2 * c[0] + q1 * c[1];
-                    prop[j * sstride] = pr;  // prop aliases e1: e1[j] is dead from here on
+                    prop[j * kStr] = pr;  // prop aliases e1: e1[j] is dead from here on
                     r3[0] += o * pr;
                     r3[1] += pr * pr;
                 }
@@ -897,14 +934,14 @@ struct Chain {
             if (p.positive) sgn = (r3[0] > 0) ? 1.0 : ((r3[0] < 0) ? -1.0 : r3[0]);  // sign(0)=0, sign(NaN)=NaN
             const double nrm = sqrt(r3[1] * (sgn * sgn));
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) VS(j) = (prop[j * sstride] * sgn) / nrm * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = (prop[j * kStr] * sgn) / nrm * rad + rho * nvec(j);
         } else {  // _full_refresh
             normals_reserve(d);
             double nw = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const double z = rand_normal_at(coord(j));
-                    prop[j * sstride] = z;
+                    prop[j * kStr] = z;
                     nw += z * z;
                 }
             normals_advance(d);
@@ -912,21 +949,21 @@ struct Chain {
             double a = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = prop[j * sstride] / nw;
-                    prop[j * sstride] = q;
+                    const double q = prop[j * kStr] / nw;
+                    prop[j * kStr] = q;
                     a += q * nvec(j);
                 }
             a = team_sum<TEAM>(a, mask);
             double np_ = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = prop[j * sstride] - a * nvec(j);
-                    prop[j * sstride] = q;
+                    const double q = prop[j * kStr] - a * nvec(j);
+                    prop[j * kStr] = q;
                     np_ += q * q;
                 }
             np_ = sqrt(team_sum<TEAM>(np_, mask));
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) VS(j) = prop[j * sstride] / np_ * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = prop[j * kStr] / np_ * rad + rho * nvec(j);
         }
     }
 
@@ -957,42 +994,46 @@ struct Chain {
         sE = sU = sN = 0;
     }
 
-    __device__ void run_events(int64_t c) {
+    __device__ int64_t run_events(int64_t c, bool valid) {  // returns the number of events recorded
         int64_t ev = 0;
         int steps = 0;
         bool need_build = true, half = false;
         accept = false;
         begin_event(0);
-        while (ev < p.n_events) {
-            // No `continue` in this loop: both blocks are plain ifs so that every lane of the warp reconverges at
-            // the end of each block (lanes that skip a block wait for the ones inside it, then all proceed).
-            if (need_build) {
-                if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; break; }
-                double h = horizon;
-                if (!half) {  // one_step_of_thinning!, :65-85
-                    compute_functionals();
-                    prepare_line();
-                } else h = horizon / 2;  // erroneous_acceptance_rate!, :131-151 (same x, v: line model still valid)
-                build_bound(h);
-                const double e = rand_exp();
-                next_event(e, tp, lambda_bar);
-                exp_rv = e;
-                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
-                if (half) {
-                    // QUIRK: a non-adaptive chain keeps the full horizon although the live bound covers half of it
-                    horizon = p.adaptive ? h : horizon;
-                    eb += 1;
-                    eva[eb % 5] = ar;
-                    half = false;
-                    need_build = false;  // back in moves_until_horizon!; a proposal beyond the horizon restarts below
-                } else if (tp > horizon) {  // move_to_horizon!, :87-101 (need_build stays set)
-                    flow_inplace(horizon);
-                    ts += horizon;
-                    hh += 1;
-                    horizon = p.adaptive ? horizon * 1.01 : horizon;
-                } else need_build = false;
+        bool live = valid && status == 0 && p.n_events > 0;
+        // Every lane of the warp stays in this loop until the whole warp is done; the warp-wide vote at the loop
+        // head is the reconvergence point of each iteration, and both blocks of the body are plain ifs, so the
+        // lanes that build a bound do it together and the lanes that have a proposal test it together.
+        while (__any_sync(0xffffffffu, live)) {
+            if (live && need_build) {
+                if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; live = false; }
+                else {
+                    double h = horizon;
+                    if (!half) {  // one_step_of_thinning!, :65-85
+                        compute_functionals();
+                        prepare_line();
+                    } else h = horizon / 2;  // erroneous_acceptance_rate!, :131-151 (same x, v: line model still valid)
+                    build_bound(h);
+                    const double e = rand_exp();
+                    next_event(e, tp, lambda_bar);
+                    exp_rv = e;
+                    if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; }
+                    else if (half) {
+                        // QUIRK: a non-adaptive chain keeps the full horizon although the live bound covers half of it
+                        horizon = p.adaptive ? h : horizon;
+                        eb += 1;
+                        eva[eb % 5] = ar;
+                        half = false;
+                        need_build = false;  // back in moves_until_horizon!; a proposal beyond the horizon restarts below
+                    } else if (tp > horizon) {  // move_to_horizon!, :87-101 (need_build stays set)
+                        flow_inplace(horizon);
+                        ts += horizon;
+                        hh += 1;
+                        horizon = p.adaptive ? horizon * 1.01 : horizon;
+                    } else need_build = false;
+                }
             }
-            if (!need_build) {
+            if (live && !need_build) {
                 // moves_until_horizon!, :103-111: `while tp < horizon && !accept` -- otherwise a fresh outer step
                 if (!(tp < horizon)) need_build = true;
                 else {
@@ -1007,21 +1048,24 @@ struct Chain {
                         t = t + tp + ts;
                         ts = 0.0;
                         tp = 0.0;
-                        if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
-                        if (status != 0) break;
-                        record(c, p.col0 + ev);
-                        ++ev;
-                        steps = 0;
-                        begin_event(ev);
-                        need_build = true;
+                        if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; }
+                        else if (status != 0) live = false;
+                        else {
+                            record(c, p.col0 + ev);
+                            ++ev;
+                            steps = 0;
+                            begin_event(ev);
+                            need_build = true;
+                            live = ev < p.n_events;
+                        }
                     } else {  // if_reject!, :188-203
                         const double e3 = exp_rv + rand_exp();
                         next_event(e3, tp, lambda_bar);
                         horizon = p.adaptive ? horizon / 1.04 : horizon;  // QUIRK: shrink before the horizon check
                         exp_rv = e3;
                         rej += 1;
-                        if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
-                        if (tp > horizon) {  // move_to_horizon2!, :205-217 (no horizon growth here)
+                        if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; }
+                        else if (tp > horizon) {  // move_to_horizon2!, :205-217 (no horizon growth here)
                             flow_inplace(horizon);
                             ts += horizon;
                             hh += 1;
@@ -1031,29 +1075,171 @@ struct Chain {
                 }
             }
         }
+        return ev;
     }
 
-    // record!, Composites.jl:239-260 (chain-major slabs)
-    __device__ void record(int64_t c_local_global, int64_t col) {
-        const int64_t o = c_local_global * p.ld_cols + col;
-        if (p.X)
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) p.X[o * d + coord(j)] = XS(j);
-        if (p.V)
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) p.V[o * d + coord(j)] = VS(j);
-        if (tl == 0) {
+    // ------------------------------------------------------------------------------------------------
+    // record!, Composites.jl:239-260 (chain-major slabs) -- HBM write path
+    // ------------------------------------------------------------------------------------------------
+    // Every byte of a PDMPHistory row is written exactly once and in full 32-byte sectors wherever alignment
+    // allows (a partially written sector costs a DRAM read-modify-write):
+    //   X, V rows   TEAM > 1: one TMA bulk copy per row straight from the chain-contiguous shared-memory state
+    //               TEAM == 1: each lane streams its chain's rows as aligned groups of 4 doubles (256-bit stores);
+    //                          up to 3 doubles are carried to the next event in shared memory
+    //   t, horizon, ar   staged in registers for 4 events, one 256-bit store per column
+    //   error_value_ar, errored_bound, rejected, hitting_horizon   almost always zero: the host zero-fills the
+    //               columns (DMA fill at full bandwidth) and only non-zero entries are written here
+    __device__ __forceinline__ void wait_row_stores() {
+        if constexpr (TEAM > 1) {
+            if (bulk_pending) {
+                if (tl == 0) bulk_wait_read();
+                __syncwarp(mask);
+                bulk_pending = false;
+            }
+        }
+    }
+
+    __device__ void init_output(int64_t c) {
+        bulk_pending = false;
+        const int64_t o0 = c * p.ld_cols + p.col0;
+        scnt = sskip = (int)(o0 & 3);
+        fcnt = fskip = (int)((o0 * d) & 3);
+    }
+
+    __device__ __forceinline__ void row_group_tm1(double* G, int64_t gfirst, int q, int r, int off_src, int off_carry) {
+        // group q of the combined stream (carry[0..r) ++ row): positions 4q .. 4q+3
+        double vq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int pos = 4 * q + k;
+            vq[k] = pos < r ? g_smem[off_carry + pos * kBlockThreads] : g_smem[off_src + (pos - r) * kBlockThreads];
+        }
+        double* dst = G + gfirst + 4 * q;
+        if (q == 0 && fskip > 0) {  // first group of this launch starts mid-sector: scalar stores for the real part
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k >= fskip) dst[k] = vq[k];
+        } else st256(dst, vq[0], vq[1], vq[2], vq[3]);
+    }
+
+    __device__ void record(int64_t c, int64_t col) {
+        const int64_t o = c * p.ld_cols + col;
+        // ---- X, V rows ----
+        if constexpr (TEAM > 1) {
+            if (p.bulk_rows) {
+                fence_async_smem();   // make this lane's generic-proxy writes of x / v visible to the TMA engine
+                __syncwarp(mask);
+                if (tl == 0) {
+                    if (p.X) bulk_store(p.X + o * d, &g_smem[off_x], (uint32_t)d * 8u);
+                    if (p.V) bulk_store(p.V + o * d, &g_smem[off_v], (uint32_t)d * 8u);
+                    bulk_commit();
+                }
+                bulk_pending = true;
+            } else {
+                if (p.X)
+                    for (int j = 0; j < nown; ++j)
+                        if (owns(j)) p.X[o * d + coord(j)] = XS(j);
+                if (p.V)
+                    for (int j = 0; j < nown; ++j)
+                        if (owns(j)) p.V[o * d + coord(j)] = VS(j);
+            }
+        } else {
+            if (p.vec32) {
+                const int r = fcnt;                  // carried (or phantom) elements in front of this row
+                const int total = r + d;
+                const int ng = total >> 2;
+                const int64_t gfirst = o * d - r;    // 4-aligned element index of the combined stream's start
+                if (p.X)
+                    for (int q = 0; q < ng; ++q) row_group_tm1(p.X, gfirst, q, r, off_x, off_f);
+                if (p.V)
+                    for (int q = 0; q < ng; ++q) row_group_tm1(p.V, gfirst, q, r, off_v, off_f + 3 * kBlockThreads);
+                const int rem = total - 4 * ng;
+                if (ng > 0) {
+                    for (int k = 0; k < rem; ++k) {  // tail of the row becomes the next carry
+                        const int pos = 4 * ng + k;
+                        g_smem[off_f + k * kBlockThreads] = g_smem[off_x + (pos - r) * kBlockThreads];
+                        g_smem[off_f + (3 + k) * kBlockThreads] = g_smem[off_v + (pos - r) * kBlockThreads];
+                    }
+                    fskip = 0;
+                } else {  // d < 4 and the group is still open: append
+                    for (int k = r; k < total; ++k) {
+                        g_smem[off_f + k * kBlockThreads] = g_smem[off_x + (k - r) * kBlockThreads];
+                        g_smem[off_f + (3 + k) * kBlockThreads] = g_smem[off_v + (k - r) * kBlockThreads];
+                    }
+                }
+                fcnt = rem;
+            } else {
+                if (p.X)
+                    for (int j = 0; j < nown; ++j) p.X[o * d + j] = XS(j);
+                if (p.V)
+                    for (int j = 0; j < nown; ++j) p.V[o * d + j] = VS(j);
+            }
+        }
+        if (tl != 0) return;
+        // ---- t, horizon, ar: 4 events per 256-bit store ----
+        if (p.vec32) {
+            if (scnt < 3) {
+                if (scnt == 0) { st_t[0] = t; st_h[0] = horizon; st_a[0] = ar; }
+                else if (scnt == 1) { st_t[1] = t; st_h[1] = horizon; st_a[1] = ar; }
+                else { st_t[2] = t; st_h[2] = horizon; st_a[2] = ar; }
+                ++scnt;
+            } else {
+                if (sskip == 0) {
+                    if (p.T) st256(p.T + o - 3, st_t[0], st_t[1], st_t[2], t);
+                    if (p.H) st256(p.H + o - 3, st_h[0], st_h[1], st_h[2], horizon);
+                    if (p.AR) st256(p.AR + o - 3, st_a[0], st_a[1], st_a[2], ar);
+                } else {
+                    flush_scalars(o);  // slots [sskip, 3) are real, the current event follows
+                    if (p.T) p.T[o] = t;
+                    if (p.H) p.H[o] = horizon;
+                    if (p.AR) p.AR[o] = ar;
+                }
+                scnt = 0; sskip = 0;
+            }
+        } else {
             if (p.T) p.T[o] = t;
             if (p.H) p.H[o] = horizon;
             if (p.AR) p.AR[o] = ar;
+        }
+        // ---- sparse diagnostic columns ----
+        if (!p.sparse_cols || eb != 0) {
             if (p.EB) p.EB[o] = eb;
-            if (p.REJ) p.REJ[o] = rej;
-            if (p.HH) p.HH[o] = hh;
             if (p.EVA) {
 #pragma unroll
                 for (int k = 0; k < 5; ++k) p.EVA[o * 5 + k] = eva[k];
             }
         }
+        if ((!p.sparse_cols || rej != 0) && p.REJ) p.REJ[o] = rej;
+        if ((!p.sparse_cols || hh != 0) && p.HH) p.HH[o] = hh;
+    }
+
+    // staged scalar slots [sskip, scnt) belong to elements o_next - scnt + k
+    __device__ void flush_scalars(int64_t o_next) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k >= sskip && k < scnt) {
+                const int64_t o = o_next - scnt + k;
+                if (p.T) p.T[o] = st_t[k];
+                if (p.H) p.H[o] = st_h[k];
+                if (p.AR) p.AR[o] = st_a[k];
+            }
+    }
+
+    // end of launch: write what is still staged (scalar stores) and drain the TMA engine
+    __device__ void finish_output(int64_t c, int64_t n_recorded) {
+        const int64_t o_next = c * p.ld_cols + p.col0 + n_recorded;
+        if constexpr (TEAM == 1) {
+            if (p.vec32) {
+                for (int k = fskip; k < fcnt; ++k) {
+                    const int64_t g = o_next * d - fcnt + k;
+                    if (p.X) p.X[g] = g_smem[off_f + k * kBlockThreads];
+                    if (p.V) p.V[g] = g_smem[off_f + (3 + k) * kBlockThreads];
+                }
+            }
+        } else {
+            if (bulk_pending && tl == 0) bulk_wait_all();
+        }
+        if (tl == 0 && p.vec32) flush_scalars(o_next);
     }
 };
 
@@ -1061,11 +1247,11 @@ struct Chain {
 // n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
 template <int TEAM, int SAMPLER, int POT, int PATH>
 __global__ void __launch_bounds__(kBlockThreads) skeleton_kernel(const KernelParams p) {
-    double* smem = g_smem;
     constexpr int CPB = kBlockThreads / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
-    const int64_t c = (int64_t)blockIdx.x * CPB + c_local;
-    if (c >= p.n_chains) return;  // teams never synchronise across the block
+    const int64_t c_raw = (int64_t)blockIdx.x * CPB + c_local;
+    const bool valid = c_raw < p.n_chains;  // out-of-range lanes stay (warp-wide votes) but never touch memory
+    const int64_t c = valid ? c_raw : 0;
 
     Chain<TEAM, SAMPLER, POT, PATH> ch(p);
     ch.tl = threadIdx.x % TEAM;
@@ -1073,34 +1259,32 @@ __global__ void __launch_bounds__(kBlockThreads) skeleton_kernel(const KernelPar
     ch.d = p.d;
     ch.nown = p.n_own;
     ch.chain = c;
-    const size_t vec = (size_t)p.n_own * kBlockThreads;  // one owned-column vector for the whole block
-    ch.off_x = threadIdx.x;
-    ch.off_v = (int)vec + threadIdx.x;
-    size_t used = 2;
+    // shared-memory state vectors: [x | v | (A | B) | (scratch x3) | (row carry)]
+    const int vec = p.vec_elems;
+    const int toff = (TEAM == 1) ? (int)threadIdx.x : c_local * p.dpad + ch.tl;  // this thread's offset in a vector
+    ch.off_x = toff;
+    ch.off_v = vec + toff;
+    int used = 2;
     ch.off_a = ch.off_b = 0;
     if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent) {
-        ch.off_a = 2 * (int)vec + threadIdx.x;
-        ch.off_b = 3 * (int)vec + threadIdx.x;
+        ch.off_a = 2 * vec + toff;
+        ch.off_b = 3 * vec + toff;
         used = 4;
     }
-    if (p.scratch_in_smem) {
-        ch.sstride = kBlockThreads;
-        double* base = smem + used * vec + threadIdx.x;
+    {
+        double* base = p.scratch_in_smem ? g_smem + (size_t)used * vec + toff
+                                         : (p.scratch ? p.scratch + (size_t)blockIdx.x * 3 * vec + toff : nullptr);
         ch.sc0 = base;
-        ch.sc1 = base + (size_t)p.n_own * kBlockThreads;
-        ch.sc2 = base + 2 * (size_t)p.n_own * kBlockThreads;
-    } else {
-        ch.sstride = kBlockThreads;
-        double* base = p.scratch ? p.scratch + (size_t)blockIdx.x * 3 * p.n_own * kBlockThreads + threadIdx.x : nullptr;
-        ch.sc0 = base;
-        ch.sc1 = base + (size_t)p.n_own * kBlockThreads;
-        ch.sc2 = base + 2 * (size_t)p.n_own * kBlockThreads;
+        ch.sc1 = base + vec;
+        ch.sc2 = base + 2 * (size_t)vec;
+        if (p.scratch_in_smem && SAMPLER == PDMPFLUX_FECMC) used += 3;
     }
+    ch.off_f = used * vec + (int)threadIdx.x;  // TEAM == 1 only: 6 carry slots per thread
     // load PDMPState
     for (int j = 0; j < ch.nown; ++j)
         if (ch.owns(j)) {
-            g_smem[ch.off_x + j * kBlockThreads] = p.sx[c * p.d + ch.coord(j)];
-            g_smem[ch.off_v + j * kBlockThreads] = p.sv[c * p.d + ch.coord(j)];
+            g_smem[ch.off_x + j * ch.kStr] = p.sx[c * p.d + ch.coord(j)];
+            g_smem[ch.off_v + j * ch.kStr] = p.sv[c * p.d + ch.coord(j)];
         }
     ch.t = p.st[c];
     ch.horizon = p.shorizon[c];
@@ -1119,17 +1303,24 @@ __global__ void __launch_bounds__(kBlockThreads) skeleton_kernel(const KernelPar
     ch.key.chain_lo = (uint32_t)gchain; ch.key.chain_hi8 = (uint32_t)(gchain >> 32) << 8;
     ch.tE = p.tE + c * p.nE; ch.tU = p.tU + c * p.nU; ch.tN = p.tN + c * p.nN;
     ch.pE = p.tape_pos[3 * c]; ch.pU = p.tape_pos[3 * c + 1]; ch.pN = p.tape_pos[3 * c + 2];
+    ch.init_output(c);
+    if constexpr (TEAM > 1) __syncwarp(ch.mask);
 
     if (p.n_events == 0) {
-        ch.record(c, p.col0);
+        if (valid) {
+            ch.record(c, p.col0);
+            ch.finish_output(c, 1);
+        }
         return;
     }
-    if (ch.status == 0) ch.run_events(c);
+    const int64_t n_rec = ch.run_events(c, valid);
+    if (!valid) return;
+    ch.finish_output(c, n_rec);
     // store PDMPState
     for (int j = 0; j < ch.nown; ++j)
         if (ch.owns(j)) {
-            p.sx[c * p.d + ch.coord(j)] = g_smem[ch.off_x + j * kBlockThreads];
-            p.sv[c * p.d + ch.coord(j)] = g_smem[ch.off_v + j * kBlockThreads];
+            p.sx[c * p.d + ch.coord(j)] = g_smem[ch.off_x + j * ch.kStr];
+            p.sv[c * p.d + ch.coord(j)] = g_smem[ch.off_v + j * ch.kStr];
         }
     if (ch.tl == 0) {
         p.st[c] = ch.t;

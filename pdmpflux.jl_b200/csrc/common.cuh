@@ -56,8 +56,31 @@ struct KernelParams {
     // per-block scratch vectors in global memory (used when they do not fit in shared memory)
     double* scratch;
     int scratch_in_smem;
-    int n_own;  // ceil(d / TEAM)
+    int n_own;      // ceil(d / TEAM)
+    int vec_elems;  // doubles per shared-memory state vector of a block (x, v, A, B, scratch each take one)
+    int dpad;       // TEAM > 1: doubles reserved per chain inside a state vector (chain-contiguous layout)
+    // output path
+    int sparse_cols;  // error_value_ar / errored_bound / rejected / hitting_horizon were zero-filled by the host:
+                      // the kernel only writes their non-zero entries
+    int vec32;        // X, V, t, horizon, ar are 32-byte aligned: 256-bit (one full sector) stores are legal
+    int bulk_rows;    // TEAM > 1: X / V rows go out as TMA bulk copies straight from the shared-memory state
 };
+
+// ---- Blackwell store primitives ---------------------------------------------------------------------------
+// 256-bit store: one full 32-byte DRAM sector per lane in a single request (SASS: STG.E.ENL2.256)
+__device__ __forceinline__ void st256(double* g, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(g), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// TMA bulk copy shared -> global (SASS: UBLKCP.G.S); size and both addresses are multiples of 16 bytes
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 
 // ---- team collectives: TEAM consecutive lanes of a warp cooperate on one chain --------------------------
 template <int TEAM>

@@ -61,9 +61,12 @@ inline int select_path(int sampler, int pot, int grid_size, int vectorized, int 
                         pot == PDMPFLUX_BANANA;
     if (!affine || (sampler == PDMPFLUX_BOOMERANG && pot == PDMPFLUX_BANANA)) return kPathGeneric;
     if (grid_size == 0) return kPathFastBrent;
-    if (deriv_mode != PDMPFLUX_DERIV_JVP) return kPathGeneric;
-    if (sampler == PDMPFLUX_ZIGZAG && !vectorized) return kPathGeneric;
-    return kPathFastGrid;
+    if (sampler == PDMPFLUX_ZIGZAG) {
+        // vectorised bound with analytic derivatives only: with finite differences the reference's cell maximum
+        // depends on the O(sqrt(eps)) derivative noise, which the affine shortcut does not reproduce
+        if (!vectorized || deriv_mode != PDMPFLUX_DERIV_JVP) return kPathGeneric;
+    }
+    return kPathFastGrid;  // BPS / FECMC / Boomerang: closed-form nodes, analytic or finite-difference derivative
 }
 
 cudaError_t launch_skeleton_zigzag(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
