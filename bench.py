@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--events", type=int, default=0, help="events per chain per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -194,7 +195,8 @@ def main():
     f64 = torch.float64
     x0 = torch.full((nch, d), cfgd["x0"], dtype=f64, device=dev)
     v0 = torch.ones((nch, d), dtype=f64, device=dev) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
-    chains = p.DeviceChains(sampler, x0, v0, seed=2024, chain_offset=rank * nch)
+    chain_offset, _ = p.dist.shard(nch * world, rank, world)      # weak scaling: nch chains on every rank
+    chains = p.DeviceChains(sampler, x0, v0, seed=2024, chain_offset=chain_offset)
     bufs = dict(X=torch.empty((nch, n_ev, d), dtype=f64, device=dev), V=torch.empty((nch, n_ev, d), dtype=f64, device=dev),
                 t=torch.empty((nch, n_ev), dtype=f64, device=dev), horizon=torch.empty((nch, n_ev), dtype=f64, device=dev),
                 ar=torch.empty((nch, n_ev), dtype=f64, device=dev),
@@ -219,10 +221,8 @@ def main():
         L.check(lib.pdmpflux_skeleton_moments(sampler.flow_kind, d, n_ev, nch, 0, bufs["X"].data_ptr(),
                                               bufs["V"].data_ptr(), bufs["t"].data_ptr(), m1.data_ptr(), m2.data_ptr(),
                                               Tl.data_ptr(), 1, stream))
-        mean = m1 / Tl[:, None]
-        sums = torch.stack([mean.sum(0), (mean * mean).sum(0), (m2 / Tl[:, None]).sum(0)])  # 3 x d moment sums
-        if world > 1:
-            dist.all_reduce(sums)                                   # the only collective: final moment reduction
+        sums = p.dist.moment_sums(m1 / Tl[:, None], m2 / Tl[:, None])   # 4 x d sufficient statistics
+        p.dist.all_reduce_sums(sums)                                # the only collective: final moment reduction
         if timed:
             kern_ms.append((k0, k1))
         return sums
@@ -260,12 +260,8 @@ def main():
     value = events_per_step * args.steps / elapsed
 
     # ESS/s from the last step's cross-chain moment sums (definition: SURVEY.md 8d / sample.ess_from_chain_means)
-    sums = sums.cpu().numpy()
-    mbar = sums[0] / total_chains
-    var_between = (sums[1] / total_chains - mbar**2) * total_chains / (total_chains - 1)
-    pooled_var = sums[2] / total_chains - mbar**2
-    ess_total = total_chains * pooled_var / var_between
-    ess_per_s = float(ess_total.min() / (elapsed / args.steps))
+    stats = p.dist.ess_from_sums(sums)
+    ess_per_s = float(stats["ess"].min() / (elapsed / args.steps))
 
     peaks = {}
     try:
@@ -293,8 +289,13 @@ def main():
             "ess_per_s": ess_per_s, "ess_definition": "min over coordinates of C * Var_pi(x_i) / Var_c(chain time-average of x_i), per step window",
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
 
+    chains.close()
+    del bufs, view
+    torch.cuda.empty_cache()
     if rank == 0 and not args.no_e2e:
         line["e2e"] = e2e(p, sampler, name, nch, n_ev, world, dev)
+    if rank == 0 and world == 1 and not args.no_extra:
+        line["extra_workloads"] = extra_workloads(p, name, peak)
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -303,6 +304,46 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_workloads(p, main, peak):
+    """Short device-resident runs (kernel time by CUDA events, best of 3 after a warm-up launch) of the other
+    BASELINE.json configurations and of the headline config at 65536 chains; same byte accounting."""
+    import torch
+    out = {}
+    todo = [(n, DEFAULT_CHAINS[n], DEFAULT_EVENTS[n]) for n in ("c1", "c2", "c3", "c5f", "c5b") if n != main]
+    todo.append((main, 65536, 100))
+    dev = torch.device("cuda")
+    f64 = torch.float64
+    for name, nch, n_ev in todo:
+        cfgd = CONFIGS[name]; d = cfgd["d"]
+        s = make_sampler(p, name)
+        x0 = torch.full((nch, d), cfgd["x0"], dtype=f64, device=dev)
+        v0 = torch.ones((nch, d), dtype=f64, device=dev) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+        ch = p.DeviceChains(s, x0, v0, seed=2024)
+        bufs = dict(X=torch.empty((nch, n_ev, d), dtype=f64, device=dev), V=torch.empty((nch, n_ev, d), dtype=f64, device=dev),
+                    t=torch.empty((nch, n_ev), dtype=f64, device=dev), horizon=torch.empty((nch, n_ev), dtype=f64, device=dev),
+                    ar=torch.empty((nch, n_ev), dtype=f64, device=dev),
+                    error_value_ar=torch.empty((nch, n_ev, 5), dtype=f64, device=dev),
+                    errored_bound=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
+                    rejected=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
+                    hitting_horizon=torch.empty((nch, n_ev), dtype=torch.int32, device=dev))
+        view = p.device_history_view(n_ev, **bufs)
+        st = torch.cuda.current_stream().cuda_stream
+        ch.advance(n_ev, view, 0, st)
+        best = float("inf")
+        for _ in range(3):
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); ch.advance(n_ev, view, 0, st); b.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) * 1e-3)
+        ch.status(); ch.close()
+        gbs = nch * n_ev * bytes_per_event(d) / best / 1e9
+        out[f"{name}@{nch}"] = {"workload": cfgd["desc"], "chains": nch, "events_per_chain": n_ev,
+                                "events_per_s": nch * n_ev / best, "hbm_gbs": gbs, "hbm_frac": gbs / peak,
+                                "bytes_per_event": bytes_per_event(d), "ms": best * 1e3}
+        del bufs, view, ch
+        torch.cuda.empty_cache()
+    return out
 
 
 def e2e(p, sampler, name, nch, n_ev, world, dev):

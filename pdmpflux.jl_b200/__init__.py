@@ -8,6 +8,7 @@ the shim `pdmpflux_b200.py` at the repository root maps it).
 from ._lib import (ArgumentError, ChainError, CudaError, DimensionMismatch, UnsupportedError, LIB_PATH, build,
                    lib)
 from .device import DeviceChains, device_history_view
+from . import dist
 from .history import PDMPHistory, PDMPHistoryBatch
 from .potentials import (Banana, BananaReadmeScalar, GaussDiag, GaussEquicorr, GaussStd, LogReg, Potential)
 from .sample import (ess_from_chain_means, sample, sample_from_skeleton, sample_skeleton, skeleton_moments)
@@ -20,5 +21,5 @@ __all__ = [
     "ess_from_chain_means", "PDMPHistory", "PDMPHistoryBatch", "Potential", "GaussStd", "GaussDiag",
     "GaussEquicorr", "Banana", "BananaReadmeScalar", "LogReg", "ArgumentError", "DimensionMismatch",
     "UnsupportedError", "CudaError", "ChainError", "build", "lib", "LIB_PATH", "DeviceChains",
-    "device_history_view",
+    "device_history_view", "dist",
 ]

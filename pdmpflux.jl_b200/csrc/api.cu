@@ -86,12 +86,11 @@ int pick_team(int d, int64_t n_chains) {
         const int t = std::atoi(e);
         if (t == 1 || t == 8 || t == 32) return t;
     }
-    // Enough chains to fill the machine with one thread each and few coordinates: thread per chain.
-    const int64_t fill = 148LL * 1024;
-    if (d <= 16 && n_chains >= fill / 4) return 1;
-    if (d <= 96 && n_chains * 8 >= fill) return 8;
-    if (d < 8) return 1;
-    if (d < 32) return 8;
+    // Measured on B200 (profiles/): thread-per-chain wins for small d once there are enough chains to occupy the
+    // SMs; 8 lanes per chain win for d up to a few hundred (fewer shuffle stages than a full warp, 4 chains share a
+    // warp's instruction stream); a warp per chain beyond that (and whenever the shared-memory state would not fit).
+    if (d <= 16) return n_chains >= 8192 ? 1 : 8;
+    if (d <= 256) return 8;
     return 32;
 }
 
