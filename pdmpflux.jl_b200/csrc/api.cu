@@ -58,10 +58,29 @@ struct pdmpflux_potential_s {
     DevBuf params;
 };
 
+// Device slabs of the host-buffer pipeline, cached in the sampler handle so that repeated sample_skeleton calls do
+// not pay cudaMalloc / cudaFree (which also synchronise the device) every time.
+struct Slab {
+    DevBuf X, V, t, horizon, ar, eva, eb, rej, hh;
+    pdmpflux_history view{};
+    cudaEvent_t done = nullptr, copied = nullptr;
+    ~Slab() {
+        if (done) cudaEventDestroy(done);
+        if (copied) cudaEventDestroy(copied);
+    }
+};
+struct Workspace {
+    Slab slab[2];
+    Slab scal;  // full-length scalar columns (t, horizon, ar, error_value_ar, counters) of the host pipeline
+    cudaStream_t copy_stream = nullptr;
+    ~Workspace() { if (copy_stream) cudaStreamDestroy(copy_stream); }
+};
+
 struct pdmpflux_sampler_s {
     int kind = 0, dim = 0;
     pdmpflux_config cfg{};
     pdmpflux_potential_s* pot = nullptr;
+    Workspace ws;
 };
 
 struct pdmpflux_chains_s {
@@ -94,7 +113,12 @@ int pick_team(int d, int64_t n_chains) {
     return 32;
 }
 
-int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, int64_t col0, cudaStream_t stream) {
+// `rows`: optional separate placement of the X / V rows (host pipeline: rows go through narrow double-buffered
+// slabs while the scalar columns accumulate in full-length device buffers)
+struct RowsView { double *X, *V; int64_t ld, col0; };
+
+int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, int64_t col0, cudaStream_t stream,
+           const RowsView* rows = nullptr) {
     const pdmpflux_sampler_s* s = ch->s;
     const pdmpflux_config& c = s->cfg;
     KernelParams p{};
@@ -119,14 +143,16 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
         p.X = h->X; p.V = h->V; p.T = h->t; p.H = h->horizon; p.AR = h->ar; p.EVA = h->error_value_ar;
         p.EB = h->errored_bound; p.REJ = h->rejected; p.HH = h->hitting_horizon;
         p.ld_cols = h->n_cols;
+        p.ld_rows = h->n_cols; p.col0_rows = col0;
+        if (rows) { p.X = rows->X; p.V = rows->V; p.ld_rows = rows->ld; p.col0_rows = rows->col0; }
     }
     p.col0 = col0;
     p.scratch = ch->scratch.as<double>(); p.scratch_in_smem = ch->scratch_in_smem; p.n_own = ch->n_own;
     p.vec_elems = ch->vec_elems; p.dpad = ch->dpad;
     if (h) {
         auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
-        p.vec32 = al(h->X, 32) && al(h->V, 32) && al(h->t, 32) && al(h->horizon, 32) && al(h->ar, 32);
-        p.bulk_rows = ch->team > 1 && (s->dim % 2 == 0) && al(h->X, 16) && al(h->V, 16);
+        p.vec32 = al(p.X, 32) && al(p.V, 32) && al(h->t, 32) && al(h->horizon, 32) && al(h->ar, 32);
+        p.bulk_rows = ch->team > 1 && (s->dim % 2 == 0) && al(p.X, 16) && al(p.V, 16);
         if (const char* e = std::getenv("PDMPFLUX_NO_BULK")) { if (std::atoi(e)) { p.bulk_rows = 0; p.vec32 = 0; } }
         // Diagnostic columns that are almost always zero are zero-filled here (one strided fill each) and the
         // kernel writes only their non-zero entries.
@@ -504,44 +530,77 @@ int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int6
     const size_t per_col = (size_t)n_chains * ((hist->X ? 8 * d : 0) + (hist->V ? 8 * d : 0) + (hist->t ? 8 : 0) +
                                                (hist->horizon ? 8 : 0) + (hist->ar ? 8 : 0) + (hist->error_value_ar ? 40 : 0) +
                                                (hist->errored_bound ? 4 : 0) + (hist->rejected ? 4 : 0) + (hist->hitting_horizon ? 4 : 0));
-    size_t budget = 4ull << 30;  // bytes per device slab
-    if (const char* e = std::getenv("PDMPFLUX_SLAB_BYTES")) budget = std::max<size_t>(1 << 20, std::strtoull(e, nullptr, 10));
+    size_t budget = 1ull << 30;  // bytes per device slab
+    if (const char* e = std::getenv("PDMPFLUX_SLAB_BYTES")) budget = std::max<size_t>(1 << 16, std::strtoull(e, nullptr, 10));
     int64_t slice = per_col ? (int64_t)std::max<size_t>(1, budget / per_col) : n_sk;
     slice = std::min<int64_t>(slice, n_sk);
-    if (slice < n_sk) slice = std::min<int64_t>(slice, (n_sk + 3) / 4);  // at least a few slices so copies overlap
+    // enough slices for the copies to overlap the kernels, but slices long enough to amortise launches
+    if (n_sk >= 64) slice = std::min<int64_t>(slice, std::max<int64_t>(16, (n_sk + 11) / 12));
     slice = std::max<int64_t>(slice, 1);
+    slice = (slice + 3) & ~int64_t(3);  // keeps every slab column 32-byte aligned for the 256-bit store path
 
-    struct Slab {
-        DevBuf X, V, t, horizon, ar, eva, eb, rej, hh;
-        pdmpflux_history view{};
-        cudaEvent_t done = nullptr, copied = nullptr;
-    } slab[2];
-    cudaStream_t copy_stream = nullptr;
-    CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    struct SGuard { cudaStream_t s; Slab* sl; ~SGuard() { for (int i = 0; i < 2; ++i) { if (sl[i].done) cudaEventDestroy(sl[i].done); if (sl[i].copied) cudaEventDestroy(sl[i].copied); } cudaStreamDestroy(s); } } sguard{copy_stream, slab};
+    Workspace& ws = s->ws;
+    Slab* slab = ws.slab;
+    if (!ws.copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ws.copy_stream, cudaStreamNonBlocking));
+    cudaStream_t copy_stream = ws.copy_stream;
     const int n_slabs = slice < n_sk ? 2 : 1;
+    auto ensure = [](DevBuf& b, bool want, size_t bytes) -> cudaError_t {
+        if (!want) return cudaSuccess;
+        if (b.bytes >= bytes && b.p) return cudaSuccess;
+        return b.alloc(bytes);
+    };
+    // Scalar columns (76 of the 16d+76 bytes per event) accumulate in full-length device buffers and go to the host
+    // once at the end as wide copies; only the X / V rows are double-buffered through the narrow slabs.  (Slicing
+    // the scalar columns too would mean n_chains x n_slices x 7 strided host rows of a few hundred bytes each.)
+    const int64_t ldS = (n_sk + 3) & ~int64_t(3);
+    const bool full_scalars = (size_t)n_chains * ldS * 76 <= (8ull << 30);
+    Slab& sc = ws.scal;
+    if (full_scalars) {
+        CUDA_TRY(ensure(sc.t, hist->t, sizeof(double) * n_chains * ldS));
+        CUDA_TRY(ensure(sc.horizon, hist->horizon, sizeof(double) * n_chains * ldS));
+        CUDA_TRY(ensure(sc.ar, hist->ar, sizeof(double) * n_chains * ldS));
+        CUDA_TRY(ensure(sc.eva, hist->error_value_ar, sizeof(double) * 5 * n_chains * ldS));
+        CUDA_TRY(ensure(sc.eb, hist->errored_bound, sizeof(int32_t) * n_chains * ldS));
+        CUDA_TRY(ensure(sc.rej, hist->rejected, sizeof(int32_t) * n_chains * ldS));
+        CUDA_TRY(ensure(sc.hh, hist->hitting_horizon, sizeof(int32_t) * n_chains * ldS));
+        sc.view = pdmpflux_history{};
+        sc.view.t = hist->t ? sc.t.as<double>() : nullptr; sc.view.horizon = hist->horizon ? sc.horizon.as<double>() : nullptr;
+        sc.view.ar = hist->ar ? sc.ar.as<double>() : nullptr;
+        sc.view.error_value_ar = hist->error_value_ar ? sc.eva.as<double>() : nullptr;
+        sc.view.errored_bound = hist->errored_bound ? sc.eb.as<int32_t>() : nullptr;
+        sc.view.rejected = hist->rejected ? sc.rej.as<int32_t>() : nullptr;
+        sc.view.hitting_horizon = hist->hitting_horizon ? sc.hh.as<int32_t>() : nullptr;
+        sc.view.n_cols = ldS; sc.view.on_device = 1;
+    }
     for (int i = 0; i < n_slabs; ++i) {
         Slab& b = slab[i];
-        if (hist->X) CUDA_TRY(b.X.alloc(sizeof(double) * d * n_chains * slice));
-        if (hist->V) CUDA_TRY(b.V.alloc(sizeof(double) * d * n_chains * slice));
-        if (hist->t) CUDA_TRY(b.t.alloc(sizeof(double) * n_chains * slice));
-        if (hist->horizon) CUDA_TRY(b.horizon.alloc(sizeof(double) * n_chains * slice));
-        if (hist->ar) CUDA_TRY(b.ar.alloc(sizeof(double) * n_chains * slice));
-        if (hist->error_value_ar) CUDA_TRY(b.eva.alloc(sizeof(double) * 5 * n_chains * slice));
-        if (hist->errored_bound) CUDA_TRY(b.eb.alloc(sizeof(int32_t) * n_chains * slice));
-        if (hist->rejected) CUDA_TRY(b.rej.alloc(sizeof(int32_t) * n_chains * slice));
-        if (hist->hitting_horizon) CUDA_TRY(b.hh.alloc(sizeof(int32_t) * n_chains * slice));
-        b.view.X = b.X.as<double>(); b.view.V = b.V.as<double>(); b.view.t = b.t.as<double>();
-        b.view.horizon = b.horizon.as<double>(); b.view.ar = b.ar.as<double>(); b.view.error_value_ar = b.eva.as<double>();
-        b.view.errored_bound = b.eb.as<int32_t>(); b.view.rejected = b.rej.as<int32_t>(); b.view.hitting_horizon = b.hh.as<int32_t>();
+        CUDA_TRY(ensure(b.X, hist->X, sizeof(double) * d * n_chains * slice));
+        CUDA_TRY(ensure(b.V, hist->V, sizeof(double) * d * n_chains * slice));
+        b.view = pdmpflux_history{};
+        b.view.X = hist->X ? b.X.as<double>() : nullptr; b.view.V = hist->V ? b.V.as<double>() : nullptr;
+        if (!full_scalars) {
+            CUDA_TRY(ensure(b.t, hist->t, sizeof(double) * n_chains * slice));
+            CUDA_TRY(ensure(b.horizon, hist->horizon, sizeof(double) * n_chains * slice));
+            CUDA_TRY(ensure(b.ar, hist->ar, sizeof(double) * n_chains * slice));
+            CUDA_TRY(ensure(b.eva, hist->error_value_ar, sizeof(double) * 5 * n_chains * slice));
+            CUDA_TRY(ensure(b.eb, hist->errored_bound, sizeof(int32_t) * n_chains * slice));
+            CUDA_TRY(ensure(b.rej, hist->rejected, sizeof(int32_t) * n_chains * slice));
+            CUDA_TRY(ensure(b.hh, hist->hitting_horizon, sizeof(int32_t) * n_chains * slice));
+            b.view.t = hist->t ? b.t.as<double>() : nullptr; b.view.horizon = hist->horizon ? b.horizon.as<double>() : nullptr;
+            b.view.ar = hist->ar ? b.ar.as<double>() : nullptr;
+            b.view.error_value_ar = hist->error_value_ar ? b.eva.as<double>() : nullptr;
+            b.view.errored_bound = hist->errored_bound ? b.eb.as<int32_t>() : nullptr;
+            b.view.rejected = hist->rejected ? b.rej.as<int32_t>() : nullptr;
+            b.view.hitting_horizon = hist->hitting_horizon ? b.hh.as<int32_t>() : nullptr;
+        }
         b.view.n_cols = slice; b.view.on_device = 1;
-        CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
+        if (!b.done) CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        if (!b.copied) CUDA_TRY(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
     }
-    auto copy2d = [&](void* dst, const void* src, size_t elem, int64_t k0, int64_t n) -> cudaError_t {
-        // chain c: host dst + (c*n_cols + k0)*elem  <-  device src + c*slice*elem, n*elem bytes
+    // chain c: host dst + (c*n_cols + k0)*elem  <-  device src + c*src_ld*elem, n*elem bytes
+    auto copy2d = [&](void* dst, const void* src, size_t elem, int64_t src_ld, int64_t k0, int64_t n) -> cudaError_t {
         return cudaMemcpy2DAsync(static_cast<char*>(dst) + (size_t)k0 * elem, (size_t)hist->n_cols * elem, src,
-                                 (size_t)slice * elem, (size_t)n * elem, (size_t)n_chains, cudaMemcpyDeviceToHost, copy_stream);
+                                 (size_t)src_ld * elem, (size_t)n * elem, (size_t)n_chains, cudaMemcpyDeviceToHost, copy_stream);
     };
     int64_t k0 = 0;
     int it = 0;
@@ -549,30 +608,49 @@ int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int6
         Slab& b = slab[it % n_slabs];
         const int64_t n = std::min<int64_t>(slice, n_sk - k0);
         if (it >= n_slabs) CUDA_TRY(cudaStreamWaitEvent(stream, b.copied, 0));  // slab free again
-        int64_t col = 0, nev = n;
+        // columns [k0, k0+n): column 0 of the whole run is the initial state, the others are events
+        const pdmpflux_history* hv = full_scalars ? &sc.view : &b.view;
+        const int64_t hcol = full_scalars ? k0 : 0;
+        RowsView rows{b.view.X, b.view.V, slice, 0};
+        int64_t first = 0, nev = n;
         if (k0 == 0) {
-            rc = pdmpflux_chains_record(ch, &b.view, 0, stream);
+            rc = launch(ch, 0, hv, hcol, stream, &rows);
             if (rc != PDMPFLUX_OK) return rc;
-            col = 1; nev = n - 1;
+            first = 1; nev = n - 1;
         }
         if (nev > 0) {
-            rc = pdmpflux_chains_advance(ch, nev, &b.view, col, stream);
+            RowsView rows2{b.view.X, b.view.V, slice, first};
+            rc = launch(ch, nev, hv, hcol + first, stream, &rows2);
             if (rc != PDMPFLUX_OK) return rc;
+            ch->event0 += nev;
         }
         CUDA_TRY(cudaEventRecord(b.done, stream));
         CUDA_TRY(cudaStreamWaitEvent(copy_stream, b.done, 0));
-        if (hist->X) CUDA_TRY(copy2d(hist->X, b.view.X, sizeof(double) * d, k0, n));
-        if (hist->V) CUDA_TRY(copy2d(hist->V, b.view.V, sizeof(double) * d, k0, n));
-        if (hist->t) CUDA_TRY(copy2d(hist->t, b.view.t, sizeof(double), k0, n));
-        if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, b.view.horizon, sizeof(double), k0, n));
-        if (hist->ar) CUDA_TRY(copy2d(hist->ar, b.view.ar, sizeof(double), k0, n));
-        if (hist->error_value_ar) CUDA_TRY(copy2d(hist->error_value_ar, b.view.error_value_ar, sizeof(double) * 5, k0, n));
-        if (hist->errored_bound) CUDA_TRY(copy2d(hist->errored_bound, b.view.errored_bound, sizeof(int32_t), k0, n));
-        if (hist->rejected) CUDA_TRY(copy2d(hist->rejected, b.view.rejected, sizeof(int32_t), k0, n));
-        if (hist->hitting_horizon) CUDA_TRY(copy2d(hist->hitting_horizon, b.view.hitting_horizon, sizeof(int32_t), k0, n));
+        if (hist->X) CUDA_TRY(copy2d(hist->X, b.view.X, sizeof(double) * d, slice, k0, n));
+        if (hist->V) CUDA_TRY(copy2d(hist->V, b.view.V, sizeof(double) * d, slice, k0, n));
+        if (!full_scalars) {
+            if (hist->t) CUDA_TRY(copy2d(hist->t, b.view.t, sizeof(double), slice, k0, n));
+            if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, b.view.horizon, sizeof(double), slice, k0, n));
+            if (hist->ar) CUDA_TRY(copy2d(hist->ar, b.view.ar, sizeof(double), slice, k0, n));
+            if (hist->error_value_ar) CUDA_TRY(copy2d(hist->error_value_ar, b.view.error_value_ar, sizeof(double) * 5, slice, k0, n));
+            if (hist->errored_bound) CUDA_TRY(copy2d(hist->errored_bound, b.view.errored_bound, sizeof(int32_t), slice, k0, n));
+            if (hist->rejected) CUDA_TRY(copy2d(hist->rejected, b.view.rejected, sizeof(int32_t), slice, k0, n));
+            if (hist->hitting_horizon) CUDA_TRY(copy2d(hist->hitting_horizon, b.view.hitting_horizon, sizeof(int32_t), slice, k0, n));
+        }
         CUDA_TRY(cudaEventRecord(b.copied, copy_stream));
         k0 += n;
         ++it;
+    }
+    if (full_scalars) {  // the scalar columns: one wide copy per column array, after the last kernel
+        CUDA_TRY(cudaEventRecord(sc.done ? sc.done : slab[0].done, stream));
+        CUDA_TRY(cudaStreamWaitEvent(copy_stream, sc.done ? sc.done : slab[0].done, 0));
+        if (hist->t) CUDA_TRY(copy2d(hist->t, sc.view.t, sizeof(double), ldS, 0, n_sk));
+        if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, sc.view.horizon, sizeof(double), ldS, 0, n_sk));
+        if (hist->ar) CUDA_TRY(copy2d(hist->ar, sc.view.ar, sizeof(double), ldS, 0, n_sk));
+        if (hist->error_value_ar) CUDA_TRY(copy2d(hist->error_value_ar, sc.view.error_value_ar, sizeof(double) * 5, ldS, 0, n_sk));
+        if (hist->errored_bound) CUDA_TRY(copy2d(hist->errored_bound, sc.view.errored_bound, sizeof(int32_t), ldS, 0, n_sk));
+        if (hist->rejected) CUDA_TRY(copy2d(hist->rejected, sc.view.rejected, sizeof(int32_t), ldS, 0, n_sk));
+        if (hist->hitting_horizon) CUDA_TRY(copy2d(hist->hitting_horizon, sc.view.hitting_horizon, sizeof(int32_t), ldS, 0, n_sk));
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaStreamSynchronize(copy_stream));

@@ -403,76 +403,113 @@ struct Chain {
         }
     }
 
-    // upper_bound_grid_vect, UpperBound.jl:203-247
+    // upper_bound_grid_vect, UpperBound.jl:203-247 -- affine line model (fast path)
+    // Cells are processed in register chunks of kCellsV (= 9: the default grid_size = 10 is exactly one chunk).
+    static constexpr int kCellsV = 9;
+    template <bool FULL>
+    __device__ __forceinline__ void vect_affine_chunk(int nc, const double (&tm_)[kCellsV], const double (&th_)[kCellsV],
+                                                      double (&bacc)[kCellsV]) {
+#pragma unroll 2
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const int i = coord(j);
+                if (i < NS) continue;  // special coordinates are added once, after the reduction
+                // affine coordinate: max(val_l, val_r, inter, 0) == max(val_l, val_r, 0); holds for the unsigned
+                // variant max(0, .) as well (DESIGN.md "affine cells").  With the cell midpoint tm and half width
+                // th: max(val_l, val_r) = A + B tm + |B| th, and max(m, 0) = (m + |m|) / 2 -- four FP64 instructions
+                // per (coordinate, cell), no compares or selects.
+                const double vi = VS(j);
+                double g, hv;
+                P::eval(p.pot, i, XS(j), vi, Lx, Lv, g, hv);
+                const double A = g * vi, B = hv * vi, aB = fabs(B);
+#pragma unroll
+                for (int u = 0; u < kCellsV; ++u)
+                    if (FULL || u < nc) {
+                        const double m = fma(aB, th_[u], fma(B, tm_[u], A));
+                        bacc[u] += m + fabs(m);
+                    }
+            }
+    }
+
+    __device__ void build_bound_vect_affine(double h) {
+        const int G = p.G;
+        make_grid(h, G);
+        for (int k0 = 0; k0 < G - 1; k0 += kCellsV) {
+            const int nc = min(kCellsV, G - 1 - k0);
+            double bacc[kCellsV], tm_[kCellsV], th_[kCellsV];
+            double tl_ = grid_t(k0);
+#pragma unroll
+            for (int u = 0; u < kCellsV; ++u) {
+                const double tr_ = grid_t(min(k0 + u + 1, G - 1));
+                tm_[u] = 0.5 * (tl_ + tr_); th_[u] = 0.5 * (tr_ - tl_);
+                bacc[u] = 0.0;
+                tl_ = tr_;
+            }
+            if (nc == kCellsV) vect_affine_chunk<true>(nc, tm_, th_, bacc);
+            else vect_affine_chunk<false>(nc, tm_, th_, bacc);
+#pragma unroll
+            for (int u = 0; u < kCellsV; ++u) bacc[u] *= 0.5;
+            team_sum_n<TEAM, kCellsV>(bacc, mask);
+            if constexpr (NS > 0) {  // special coordinates: the reference's cell formula, evaluated by every lane
+                double yl[NS], dl[NS];
+                special_rates(grid_t(k0), yl, dl);
+                for (int u = 0; u < nc; ++u) {
+                    double yr[NS], dr[NS];
+                    special_rates(grid_t(k0 + u + 1), yr, dr);
+                    double add = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        double vl = yl[k], gl = dl[k], vr = yr[k], gr = dr[k];
+                        if (!p.signed_bound) {
+                            gl = (0.0 > vl) ? 0.0 : gl; vl = (vl > 0.0 ? vl : 0.0);
+                            gr = (0.0 > vr) ? 0.0 : gr; vr = (vr > 0.0 ? vr : 0.0);
+                        }
+                        add += vect_cell(vl, gl, vr, gr, grid_t(k0 + u), grid_t(k0 + u + 1));
+                        yl[k] = yr[k]; dl[k] = dr[k];
+                    }
+                    box[k0 + u] = add;  // stash; merged below
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kCellsV; ++u)
+                if (u < nc) {
+                    if constexpr (NS > 0) box[k0 + u] += bacc[u];
+                    else box[k0 + u] = bacc[u];
+                }
+        }
+        double cs = 0.0;
+        cum[0] = 0.0;
+        for (int k = 0; k < G - 1; ++k) { cs += box[k]; cum[k + 1] = cs * step; }
+    }
+
+    // upper_bound_grid_vect, UpperBound.jl:203-247 -- generic path
     __device__ void build_bound_vect(double h) {
+        if constexpr (kFast) { build_bound_vect_affine(h); return; }
         const int G = p.G;
         make_grid(h, G);
         for (int k0 = 0; k0 < G - 1; k0 += kChunk) {
             const int nc = min(kChunk, G - 1 - k0);
-            double bacc[kChunk], tn[kChunk + 1], tm_[kChunk], th_[kChunk];
+            double bacc[kChunk], tn[kChunk + 1];
 #pragma unroll
             for (int u = 0; u < kChunk; ++u) bacc[u] = 0.0;
 #pragma unroll
             for (int u = 0; u <= kChunk; ++u) tn[u] = grid_t(min(k0 + u, G - 1));
-#pragma unroll
-            for (int u = 0; u < kChunk; ++u) { tm_[u] = 0.5 * (tn[u] + tn[u + 1]); th_[u] = 0.5 * (tn[u + 1] - tn[u]); }
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const int i = coord(j);
                     const double xi = XS(j), vi = VS(j);
-                    if constexpr (kFast) {
-                        if (i < NS) continue;  // special coordinates are added once, after the reduction
-                        // affine coordinate: max(val_l, val_r, inter, 0) == max(val_l, val_r, 0); holds for the
-                        // unsigned variant max(0, .) as well (see DESIGN.md "affine cells").  With the cell midpoint
-                        // tm and half width th: max(val_l, val_r) = A + B tm + |B| th, and max(m, 0) = (m + |m|) / 2
-                        // -- four FP64 instructions per (coordinate, cell), no compares or selects.
-                        double g, hv;
-                        P::eval(p.pot, i, xi, vi, Lx, Lv, g, hv);
-                        const double A = g * vi, B = hv * vi, aB = fabs(B);
+                    double vl, gl;
+                    vect_node(i, xi, vi, tn[0], h, vl, gl);
 #pragma unroll
-                        for (int u = 0; u < kChunk; ++u)
-                            if (u < nc) {
-                                const double m = fma(aB, th_[u], fma(B, tm_[u], A));
-                                bacc[u] += m + fabs(m);
-                            }
-                    } else {
-                        double vl, gl;
-                        vect_node(i, xi, vi, tn[0], h, vl, gl);
-#pragma unroll
-                        for (int u = 0; u < kChunk; ++u)
-                            if (u < nc) {
-                                double vr, gr;
-                                vect_node(i, xi, vi, tn[u + 1], h, vr, gr);
-                                bacc[u] += vect_cell(vl, gl, vr, gr, tn[u], tn[u + 1]);
-                                vl = vr; gl = gr;
-                            }
-                    }
-                }
-            if constexpr (kFast) {
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u) bacc[u] *= 0.5;
-            }
-            team_sum_n<TEAM, kChunk>(bacc, mask);
-            if constexpr (kFast && NS > 0) {  // special coordinates: the reference's cell formula, every lane
-                double yl[NS], dl[NS];
-                special_rates(tn[0], yl, dl);
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u)
-                    if (u < nc) {
-                        double yr[NS], dr[NS];
-                        special_rates(tn[u + 1], yr, dr);
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) {
-                            double vl = yl[k], gl = dl[k], vr = yr[k], gr = dr[k];
-                            if (!p.signed_bound) {
-                                gl = (0.0 > vl) ? 0.0 : gl; vl = (vl > 0.0 ? vl : 0.0);
-                                gr = (0.0 > vr) ? 0.0 : gr; vr = (vr > 0.0 ? vr : 0.0);
-                            }
+                    for (int u = 0; u < kChunk; ++u)
+                        if (u < nc) {
+                            double vr, gr;
+                            vect_node(i, xi, vi, tn[u + 1], h, vr, gr);
                             bacc[u] += vect_cell(vl, gl, vr, gr, tn[u], tn[u + 1]);
-                            yl[k] = yr[k]; dl[k] = dr[k];
+                            vl = vr; gl = gr;
                         }
-                    }
-            }
+                }
+            team_sum_n<TEAM, kChunk>(bacc, mask);
 #pragma unroll
             for (int u = 0; u < kChunk; ++u)
                 if (u < nc) box[k0 + u] = bacc[u];
@@ -1102,8 +1139,9 @@ struct Chain {
     __device__ void init_output(int64_t c) {
         bulk_pending = false;
         const int64_t o0 = c * p.ld_cols + p.col0;
+        const int64_t r0 = c * p.ld_rows + p.col0_rows;
         scnt = sskip = (int)(o0 & 3);
-        fcnt = fskip = (int)((o0 * d) & 3);
+        fcnt = fskip = (int)((r0 * d) & 3);
     }
 
     __device__ __forceinline__ void row_group_tm1(double* G, int64_t gfirst, int q, int r, int off_src, int off_carry) {
@@ -1123,32 +1161,33 @@ struct Chain {
     }
 
     __device__ void record(int64_t c, int64_t col) {
-        const int64_t o = c * p.ld_cols + col;
+        const int64_t o = c * p.ld_cols + col;                                // scalar columns
+        const int64_t orow = c * p.ld_rows + (col - p.col0) + p.col0_rows;    // X / V rows
         // ---- X, V rows ----
         if constexpr (TEAM > 1) {
             if (p.bulk_rows) {
                 fence_async_smem();   // make this lane's generic-proxy writes of x / v visible to the TMA engine
                 __syncwarp(mask);
                 if (tl == 0) {
-                    if (p.X) bulk_store(p.X + o * d, &g_smem[off_x], (uint32_t)d * 8u);
-                    if (p.V) bulk_store(p.V + o * d, &g_smem[off_v], (uint32_t)d * 8u);
+                    if (p.X) bulk_store(p.X + orow * d, &g_smem[off_x], (uint32_t)d * 8u);
+                    if (p.V) bulk_store(p.V + orow * d, &g_smem[off_v], (uint32_t)d * 8u);
                     bulk_commit();
                 }
                 bulk_pending = true;
             } else {
                 if (p.X)
                     for (int j = 0; j < nown; ++j)
-                        if (owns(j)) p.X[o * d + coord(j)] = XS(j);
+                        if (owns(j)) p.X[orow * d + coord(j)] = XS(j);
                 if (p.V)
                     for (int j = 0; j < nown; ++j)
-                        if (owns(j)) p.V[o * d + coord(j)] = VS(j);
+                        if (owns(j)) p.V[orow * d + coord(j)] = VS(j);
             }
         } else {
             if (p.vec32) {
                 const int r = fcnt;                  // carried (or phantom) elements in front of this row
                 const int total = r + d;
                 const int ng = total >> 2;
-                const int64_t gfirst = o * d - r;    // 4-aligned element index of the combined stream's start
+                const int64_t gfirst = orow * d - r;    // 4-aligned element index of the combined stream's start
                 if (p.X)
                     for (int q = 0; q < ng; ++q) row_group_tm1(p.X, gfirst, q, r, off_x, off_f);
                 if (p.V)
@@ -1170,9 +1209,9 @@ struct Chain {
                 fcnt = rem;
             } else {
                 if (p.X)
-                    for (int j = 0; j < nown; ++j) p.X[o * d + j] = XS(j);
+                    for (int j = 0; j < nown; ++j) p.X[orow * d + j] = XS(j);
                 if (p.V)
-                    for (int j = 0; j < nown; ++j) p.V[o * d + j] = VS(j);
+                    for (int j = 0; j < nown; ++j) p.V[orow * d + j] = VS(j);
             }
         }
         if (tl != 0) return;
@@ -1228,10 +1267,11 @@ struct Chain {
     // end of launch: write what is still staged (scalar stores) and drain the TMA engine
     __device__ void finish_output(int64_t c, int64_t n_recorded) {
         const int64_t o_next = c * p.ld_cols + p.col0 + n_recorded;
+        const int64_t r_next = c * p.ld_rows + p.col0_rows + n_recorded;
         if constexpr (TEAM == 1) {
             if (p.vec32) {
                 for (int k = fskip; k < fcnt; ++k) {
-                    const int64_t g = o_next * d - fcnt + k;
+                    const int64_t g = r_next * d - fcnt + k;
                     if (p.X) p.X[g] = g_smem[off_f + k * kBlockThreads];
                     if (p.V) p.V[g] = g_smem[off_f + (3 + k) * kBlockThreads];
                 }

@@ -52,7 +52,8 @@ struct KernelParams {
     // outputs (any may be null)
     double *X, *V, *T, *H, *AR, *EVA;
     int32_t *EB, *REJ, *HH;
-    int64_t ld_cols, col0;
+    int64_t ld_cols, col0;        // scalar columns: leading dimension / first column of this launch
+    int64_t ld_rows, col0_rows;   // X, V rows (may live in a narrower slab than the scalar columns)
     // per-block scratch vectors in global memory (used when they do not fit in shared memory)
     double* scratch;
     int scratch_in_smem;
