@@ -103,7 +103,7 @@ namespace {
 int pick_team(int d, int64_t n_chains) {
     if (const char* e = std::getenv("PDMPFLUX_TEAM")) {
         const int t = std::atoi(e);
-        if (t == 1 || t == 8 || t == 32) return t;
+        if (t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32) return t;
     }
     // Measured on B200 (profiles/): thread-per-chain wins for small d once there are enough chains to occupy the
     // SMs; 8 lanes per chain win for d up to a few hundred (fewer shuffle stages than a full warp, 4 chains share a
@@ -371,14 +371,14 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     ch->team = pick_team(d, n_chains);
     // widen the team until x and v (per-thread-owned shared-memory columns) fit next to a second block
     while (ch->team < 32 && 4 * (size_t)((d + ch->team - 1) / ch->team) * kBlockThreads * sizeof(double) > 100 * 1024)
-        ch->team = ch->team == 1 ? 8 : 32;
+        ch->team = ch->team < 8 ? 8 : 32;
     ch->n_own = (d + ch->team - 1) / ch->team;
     const int cpb = kBlockThreads / ch->team;
     ch->grid = (unsigned)((n_chains + cpb - 1) / cpb);
     if (ch->team == 1) { ch->dpad = 0; ch->vec_elems = ch->n_own * kBlockThreads; }
     else {
-        ch->dpad = ch->n_own * ch->team;
-        if (ch->team < 32) while (ch->dpad % 16 != 8) ch->dpad += 8;  // chains of a warp land on distinct bank halves
+        ch->dpad = (ch->n_own * ch->team + 7) / 8 * 8;                  // 64-byte aligned chain slots (TMA source)
+        if (ch->team < 32 && ch->dpad % 16 != 8) ch->dpad += 8;         // chains of a warp land on distinct bank halves
         ch->vec_elems = cpb * ch->dpad;
     }
     const size_t vec_bytes = (size_t)ch->vec_elems * sizeof(double);

@@ -124,6 +124,56 @@ struct Chain {
         if (p.draw_mode) return draw_normal(key, sN + (uint32_t)off);
         return exhausted ? 1.0 : __ldg(tN + pN + off);
     }
+    // Normals number 2*i and 2*i+1 of the current block (FECMC orthogonal switch: g1[i], g2[i]) -- one Box-Muller.
+    __device__ __forceinline__ void rand_normal_two_at(int64_t i, double& z1, double& z2) {
+        if (p.draw_mode && !(sN & 1u)) draw_normal_pair(key, (sN >> 1) + (uint32_t)i, z1, z2);
+        else { z1 = rand_normal_at(2 * i); z2 = rand_normal_at(2 * i + 1); }
+    }
+    // Normals for the owned coordinates j0 and j0+1 (slot = coordinate index) of a block of d normals.  In Philox
+    // mode neighbouring lanes (tl, tl^1) own the two halves of the same Box-Muller pair at every j, so the even lane
+    // evaluates the pair of row j0, the odd lane the pair of row j0+1, and they swap halves with one shuffle:
+    // one Box-Muller per lane per two coordinates instead of two.
+    __device__ __forceinline__ void rand_normal_rows(int j0, double& z0, double& z1) {
+        if constexpr (TEAM >= 2) {
+            if (p.draw_mode && !(sN & 1u)) {
+                const int odd = tl & 1;
+                const int ie = (tl & ~1) + TEAM * (j0 + odd);  // even coordinate of the pair this lane evaluates
+                double ne, no;
+                draw_normal_pair(key, (sN >> 1) + (uint32_t)(ie >> 1), ne, no);
+                const double recv = __shfl_xor_sync(mask, odd ? ne : no, 1);
+                z0 = odd ? recv : ne;
+                z1 = odd ? no : recv;
+                return;
+            }
+        }
+        if constexpr (TEAM == 1) {
+            if (p.draw_mode && !((sN + (uint32_t)j0) & 1u)) {  // rows j0, j0+1 are the two halves of one pair
+                draw_normal_pair(key, (sN + (uint32_t)j0) >> 1, z0, z1);
+                return;
+            }
+        }
+        z0 = rand_normal_at(coord(j0));
+        z1 = rand_normal_at(coord(j0 + 1));
+    }
+    // v_j <- N(0,1) for every owned coordinate (BPS / Boomerang refresh); returns the lane's partial sum of squares
+    __device__ double refresh_velocity_normals() {
+        normals_reserve(d);
+        double nn = 0.0;
+        int j = 0;
+        for (; j + 1 < nown; j += 2) {  // every lane takes part in the shuffle, ownership only gates the store
+            double z0, z1;
+            rand_normal_rows(j, z0, z1);
+            if (owns(j)) { VS(j) = z0; nn += z0 * z0; }
+            if (owns(j + 1)) { VS(j + 1) = z1; nn += z1 * z1; }
+        }
+        if (j < nown && owns(j)) {
+            const double z = rand_normal_at(coord(j));
+            VS(j) = z; nn += z * z;
+        }
+        normals_advance(d);
+        return nn;
+    }
+
     __device__ void normals_reserve(int64_t count) {
         if (!p.draw_mode && pN + count > p.nN) exhausted = true;
     }
@@ -787,15 +837,7 @@ struct Chain {
                     VS(j) = VS(j) - scale * g;
                 }
         } else {
-            normals_reserve(d);
-            double nn = 0.0;
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) {
-                    const double z = rand_normal_at(coord(j));
-                    VS(j) = z;
-                    nn += z * z;
-                }
-            normals_advance(d);
+            double nn = refresh_velocity_normals();
             if (!p.gaussian_velocity) {
                 nn = sqrt(team_sum<TEAM>(nn, mask));
                 for (int j = 0; j < nown; ++j)
@@ -833,10 +875,7 @@ struct Chain {
                     VS(j) = VS(j) - 2 * ve * e;
                 }
         } else {  // QUIRK: refresh draws from the global RNG in the reference (:65); on a tape it is the N stream
-            normals_reserve(d);
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) VS(j) = rand_normal_at(coord(j));
-            normals_advance(d);
+            refresh_velocity_normals();
         }
     }
 
@@ -845,7 +884,7 @@ struct Chain {
         const double u = rand_uniform();
         double rho = -sqrt(1 - pow(u, 2.0 / (d - 1)));
         if (sf != 1.0) rho = sf * rho;
-        double* vo = sc0;
+        double* __restrict__ vo = sc0;
         // n = grad U(x) / |grad U(x)| (zero vector if the norm is 0)
         double r2[2] = {0.0, 0.0};
         for (int j = 0; j < nown; ++j)
@@ -898,16 +937,16 @@ struct Chain {
                 if (owns(j)) VS(j) = vo[j * kStr] / nrm * rad + rho * nvec(j);
             return;
         }
-        double* prop = sc1;
+        double* __restrict__ prop = sc1;
         if (p.switch_) {  // _orthogonal_switch; randn(key, 2, dim) is column-major: g1[i] = N[2i], g2[i] = N[2i+1]
             double* e1 = sc1;
-            double* e2 = sc2;
+            double* __restrict__ e2 = sc2;
             normals_reserve(2 * (int64_t)d);
             double a[2] = {0.0, 0.0};
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double z1 = rand_normal_at(2 * (int64_t)coord(j));
-                    const double z2 = rand_normal_at(2 * (int64_t)coord(j) + 1);
+                    double z1, z2;
+                    rand_normal_two_at(coord(j), z1, z2);
                     e1[j * kStr] = z1; e2[j * kStr] = z2;
                     const double n = nvec(j);
                     a[0] += z1 * n; a[1] += z2 * n;

@@ -49,6 +49,9 @@ cudaError_t launch_for_sampler(int team, int pot, int path, const KernelParams& 
                                cudaStream_t stream) {
     switch (team) {
     case 1: return launch_for_team<1, SAMPLER>(pot, path, p, grid, smem, stream);
+#ifdef PDMPFLUX_EXTRA_TEAM
+    case PDMPFLUX_EXTRA_TEAM: return launch_for_team<PDMPFLUX_EXTRA_TEAM, SAMPLER>(pot, path, p, grid, smem, stream);
+#endif
     case 8: return launch_for_team<8, SAMPLER>(pot, path, p, grid, smem, stream);
     case 32: return launch_for_team<32, SAMPLER>(pot, path, p, grid, smem, stream);
     default: return cudaErrorInvalidValue;

@@ -55,13 +55,21 @@ __device__ __forceinline__ double draw_uniform(const DrawKey& k, uint32_t slot) 
     draw_call(k, 1u, slot, r);
     return u53(r[0], r[1]);
 }
-__device__ __forceinline__ double draw_normal(const DrawKey& k, uint32_t slot) {
+// Both normals of Box-Muller pair `pair` (slots 2*pair and 2*pair+1): one Philox call, one log, one sincospi.
+// cos/sin(2 pi u) are evaluated as sincospi(2u): no range reduction, and exact at the quadrant boundaries.
+__device__ __forceinline__ void draw_normal_pair(const DrawKey& k, uint32_t pair, double& n_even, double& n_odd) {
     uint32_t r[4];
-    draw_call(k, 2u, slot >> 1, r);
+    draw_call(k, 2u, pair, r);
     const double rad = sqrt(-2.0 * log(u52_open(r[0], r[1])));
     double s, c;
-    sincos(6.283185307179586476925286766559 * u53(r[2], r[3]), &s, &c);
-    return rad * ((slot & 1u) ? s : c);
+    sincospi(2.0 * u53(r[2], r[3]), &s, &c);
+    n_even = rad * c;
+    n_odd = rad * s;
+}
+__device__ __forceinline__ double draw_normal(const DrawKey& k, uint32_t slot) {
+    double a, b;
+    draw_normal_pair(k, slot >> 1, a, b);
+    return (slot & 1u) ? b : a;
 }
 
 }  // namespace pdmpflux
