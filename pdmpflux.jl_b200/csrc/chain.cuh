@@ -647,8 +647,28 @@ struct Chain {
                 }
             };
             double vl, gl, cs = 0.0;
-            node(0.0, vl, gl);
             cum[0] = 0.0;
+            if constexpr (!kRot && NS == 0) {
+                if (p.deriv_mode == PDMPFLUX_DERIV_JVP) {
+                    // <grad U(x + t v), v> = a + t b is affine: both tangents of a cell are the function itself, so the
+                    // reference's max(val_l, val_r, inter, 0) is max(val_l, val_r, 0) (same for the unsigned variant) --
+                    // no division, no clamping.
+                    double d0;
+                    finish_scalar(la, lb, vl, d0);
+                    for (int k = 0; k < G - 1; ++k) {
+                        double vr;
+                        finish_scalar(fma(grid_t(k + 1), lb, la), lb, vr, d0);
+                        const double m = fmax(vl, vr);
+                        const double b = 0.5 * (m + fabs(m)) + p.bound_refresh;
+                        box[k] = b;
+                        cs += b;
+                        cum[k + 1] = cs * step;
+                        vl = vr;
+                    }
+                    return;
+                }
+            }
+            node(0.0, vl, gl);
             for (int k = 0; k < G - 1; ++k) {
                 double vr, gr;
                 node(grid_t(k + 1), vr, gr);
@@ -839,9 +859,9 @@ struct Chain {
         } else {
             double nn = refresh_velocity_normals();
             if (!p.gaussian_velocity) {
-                nn = sqrt(team_sum<TEAM>(nn, mask));
+                nn = 1.0 / sqrt(team_sum<TEAM>(nn, mask));
                 for (int j = 0; j < nown; ++j)
-                    if (owns(j)) VS(j) = VS(j) / nn;
+                    if (owns(j)) VS(j) = VS(j) * nn;
             }
         }
     }
@@ -861,17 +881,17 @@ struct Chain {
         const double prob = bounce / (bounce + p.refresh_rate);
         const double u = rand_uniform();
         if (u < prob) {
-            const double ng = sqrt(r2[1]);
+            const double ing = 1.0 / sqrt(r2[1]);
             double ve = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) / ng;
+                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) * ing;
                     ve += VS(j) * e;
                 }
             ve = team_sum<TEAM>(ve, mask);
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) / ng;
+                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) * ing;
                     VS(j) = VS(j) - 2 * ve * e;
                 }
         } else {  // QUIRK: refresh draws from the global RNG in the reference (:65); on a tape it is the N stream
@@ -893,10 +913,9 @@ struct Chain {
                 r2[0] += g * g;
             }
         const double ng = sqrt(team_sum<TEAM>(r2[0], mask));
-        auto nvec = [&](int j) -> double {
-            const double g = P::grad(p.pot, coord(j), XS(j), Lx);
-            return ng == 0 ? 0.0 : g / ng;
-        };
+        // n_i = g_i / |g|: multiplied by the reciprocal (1 ulp from the reference's division, 25x cheaper)
+        const double inv_ng = ng == 0 ? 0.0 : 1.0 / ng;
+        auto nvec = [&](int j) -> double { return P::grad(p.pot, coord(j), XS(j), Lx) * inv_ng; };
         double vn = 0.0;
         for (int j = 0; j < nown; ++j)
             if (owns(j)) vn += VS(j) * nvec(j);
@@ -932,9 +951,9 @@ struct Chain {
         const double u2 = rand_uniform();
         const double rad = (sf != 1.0) ? sqrt(sf * sf - rho * rho) : sqrt(1 - rho * rho);
         if (u2 >= p.mix_p) {
-            const double nrm = sqrt(nvo);
+            const double sc_ = rad / sqrt(nvo);
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) VS(j) = vo[j * kStr] / nrm * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = vo[j * kStr] * sc_ + rho * nvec(j);
             return;
         }
         double* __restrict__ prop = sc1;
@@ -962,11 +981,11 @@ struct Chain {
                     e2[j * kStr] = e2[j * kStr] - a[1] * n;
                     n1 += g1 * g1;
                 }
-            n1 = sqrt(team_sum<TEAM>(n1, mask));
+            n1 = 1.0 / sqrt(team_sum<TEAM>(n1, mask));
             double b = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = e1[j * kStr] / n1;
+                    const double q = e1[j * kStr] * n1;
                     e1[j * kStr] = q;
                     b += e2[j * kStr] * q;
                 }
@@ -978,11 +997,11 @@ struct Chain {
                     e2[j * kStr] = q;
                     n2 += q * q;
                 }
-            n2 = sqrt(team_sum<TEAM>(n2, mask));
+            n2 = 1.0 / sqrt(team_sum<TEAM>(n2, mask));
             double c[2] = {0.0, 0.0};
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = e2[j * kStr] / n2;
+                    const double q = e2[j * kStr] * n2;
                     e2[j * kStr] = q;
                     c[0] += vo[j * kStr] * e1[j * kStr];
                     c[1] += vo[j * kStr] * q;
@@ -1008,9 +1027,9 @@ struct Chain {
             team_sum_n<TEAM, 2>(r3, mask);
             double sgn = 1.0;
             if (p.positive) sgn = (r3[0] > 0) ? 1.0 : ((r3[0] < 0) ? -1.0 : r3[0]);  // sign(0)=0, sign(NaN)=NaN
-            const double nrm = sqrt(r3[1] * (sgn * sgn));
+            const double sc_ = sgn * rad / sqrt(r3[1] * (sgn * sgn));  // sign(0) = 0 -> 0/0 = NaN as in the reference
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) VS(j) = (prop[j * kStr] * sgn) / nrm * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = prop[j * kStr] * sc_ + rho * nvec(j);
         } else {  // _full_refresh
             normals_reserve(d);
             double nw = 0.0;
@@ -1021,11 +1040,11 @@ struct Chain {
                     nw += z * z;
                 }
             normals_advance(d);
-            nw = sqrt(team_sum<TEAM>(nw, mask));
+            nw = 1.0 / sqrt(team_sum<TEAM>(nw, mask));
             double a = 0.0;
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
-                    const double q = prop[j * kStr] / nw;
+                    const double q = prop[j * kStr] * nw;
                     prop[j * kStr] = q;
                     a += q * nvec(j);
                 }
@@ -1037,10 +1056,49 @@ struct Chain {
                     prop[j * kStr] = q;
                     np_ += q * q;
                 }
-            np_ = sqrt(team_sum<TEAM>(np_, mask));
+            np_ = rad / sqrt(team_sum<TEAM>(np_, mask));
             for (int j = 0; j < nown; ++j)
-                if (owns(j)) VS(j) = prop[j * kStr] / np_ * rad + rho * nvec(j);
+                if (owns(j)) VS(j) = prop[j * kStr] * np_ + rho * nvec(j);
         }
+    }
+
+    // if_accept! for ZigZag with a linear flow, fused into one pass over the coordinates:
+    //   x <- x + tp v (flow), lambda_i = max(0, g_i(x) v_i) at the new x, categorical draw, flip.
+    // `S` = sum lambda_i is exactly the rate just evaluated at tp for the accept test (same point, same formula), and
+    // the functionals of the new x follow from linearity (L(x + tp v) = L(x) + tp L(v)), so the reference's separate
+    // passes (flow, grad, sum, cdf scan: ZigZagSamplers.jl:80, :101-107) collapse into this loop.  S > 0 is implied
+    // by the acceptance (u < S / lambda_bar), hence Categorical's isprobvec check cannot fail here.
+    __device__ void accept_zigzag(double tt, double S) {
+        wait_row_stores();
+        double Lxn[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) Lxn[k] = Lx[k] + Lv[k] * tt;
+        const double uS = rand_uniform() * S;
+        double carry = 0.0;
+        int m = d - 1;
+        bool found = false;
+        for (int j = 0; j < nown; ++j) {
+            double lj = 0.0;
+            if (owns(j)) {
+                const double vi = VS(j);
+                const double xn = XS(j) + vi * tt;
+                XS(j) = xn;
+                const double y = P::grad(p.pot, coord(j), xn, Lxn) * vi;
+                lj = (y > 0.0 ? y : 0.0);
+            }
+            const double incl = team_scan_incl<TEAM>(lj, mask, tl) + carry;
+            const bool hit = !found && owns(j) && (incl > uS);
+            int first = -1;
+            if constexpr (TEAM == 1) first = hit ? 0 : -1;
+            else {
+                unsigned b = __ballot_sync(mask, hit) & mask;
+                b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
+                first = b ? (__ffs(b) - 1) : -1;
+            }
+            if (first >= 0) { m = first + TEAM * j; found = true; }
+            carry = team_bcast<TEAM>(incl, TEAM - 1, mask);
+        }
+        if (m % TEAM == tl) { const int j = m / TEAM; VS(j) = -VS(j); }
     }
 
     __device__ void velocity_jump() {
@@ -1119,8 +1177,11 @@ struct Chain {
                     ar = lt / lambda_bar;
                     if (ar > 1.0) { need_build = true; half = true; }
                     else if (rand_uniform() < ar) {  // ac_step_with_proxy!, :153-168 -> if_accept!, :170-186
-                        flow_inplace(tp);
-                        velocity_jump();
+                        if constexpr (kZZ) accept_zigzag(tp, lt);
+                        else {
+                            flow_inplace(tp);
+                            velocity_jump();
+                        }
                         t = t + tp + ts;
                         ts = 0.0;
                         tp = 0.0;
