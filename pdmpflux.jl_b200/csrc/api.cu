@@ -394,6 +394,10 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
         }
     }
     if (ch->team == 1) ch->smem += 6 * kBlockThreads * sizeof(double);  // row carry slots (record())
+    {
+        const size_t gb = s->cfg.grid_size > 2 ? s->cfg.grid_size : 2;      // box_max / cum_sum, one copy per chain
+        ch->smem += (ch->team == 1 ? (size_t)kBlockThreads : (size_t)cpb) * 2 * gb * sizeof(double);
+    }
     if (ch->smem > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "dimension too large for the shared-memory state layout");
     CUDA_TRY(ch->x.alloc(sizeof(double) * d * n_chains));
     CUDA_TRY(ch->v.alloc(sizeof(double) * d * n_chains));

@@ -34,6 +34,8 @@ extern __shared__ __align__(128) double g_smem[];
 #define VS(j) g_smem[off_v + (j) * kStr]
 #define AS(j) g_smem[off_a + (j) * kStr]
 #define BS(j) g_smem[off_b + (j) * kStr]
+#define BOX(k) g_smem[off_box + (k) * kBStr]
+#define CUM(k) g_smem[off_cum + (k) * kBStr]
 
 // PATH selects how the bound and the rates are evaluated:
 //   kPathGeneric   every grid node / Brent iterate makes a pass over the coordinates (any potential, any option)
@@ -60,6 +62,7 @@ struct Chain {
     static constexpr bool kRot = (SAMPLER == PDMPFLUX_BOOMERANG);
     static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG);
     static constexpr int kStr = (TEAM == 1) ? kBlockThreads : TEAM;  // stride between a thread's owned elements
+    static constexpr int kBStr = (TEAM == 1) ? kBlockThreads : 1;    // stride between a chain's box / cum entries
 
     const KernelParams& p;
     int off_x, off_v, off_a, off_b;  // element offsets into g_smem of this thread's owned columns of x, v, A, B
@@ -86,7 +89,9 @@ struct Chain {
 
     // BoundBox (Composites.jl:15-20), team-uniform, thread-local storage.  Grid nodes are recomputed on
     // demand from (gc, grem, gh): node k = fma(k, gc, k * grem / (G-1)), last node = gh.
-    double box[kMaxGrid], cum[kMaxGrid];
+    // box_max / cum_sum live in shared memory, one copy per chain (every lane of a team writes the same values;
+    // thread-local arrays would be replicated TEAM times in local memory and spill to DRAM behind the row traffic)
+    int off_box, off_cum;
     double step, gc, grem, gh;
     int nb;
 
@@ -517,19 +522,19 @@ struct Chain {
                         add += vect_cell(vl, gl, vr, gr, grid_t(k0 + u), grid_t(k0 + u + 1));
                         yl[k] = yr[k]; dl[k] = dr[k];
                     }
-                    box[k0 + u] = add;  // stash; merged below
+                    BOX(k0 + u) = add;  // stash; merged below
                 }
             }
 #pragma unroll
             for (int u = 0; u < kCellsV; ++u)
                 if (u < nc) {
-                    if constexpr (NS > 0) box[k0 + u] += bacc[u];
-                    else box[k0 + u] = bacc[u];
+                    if constexpr (NS > 0) BOX(k0 + u) += bacc[u];
+                    else BOX(k0 + u) = bacc[u];
                 }
         }
         double cs = 0.0;
-        cum[0] = 0.0;
-        for (int k = 0; k < G - 1; ++k) { cs += box[k]; cum[k + 1] = cs * step; }
+        CUM(0) = 0.0;
+        for (int k = 0; k < G - 1; ++k) { cs += BOX(k); CUM(k + 1) = cs * step; }
     }
 
     // upper_bound_grid_vect, UpperBound.jl:203-247 -- generic path
@@ -562,12 +567,12 @@ struct Chain {
             team_sum_n<TEAM, kChunk>(bacc, mask);
 #pragma unroll
             for (int u = 0; u < kChunk; ++u)
-                if (u < nc) box[k0 + u] = bacc[u];
+                if (u < nc) BOX(k0 + u) = bacc[u];
         }
-        // sum_i cumsum_k(box[i,k]) * step  ==  cumsum_k(sum_i box[i,k]) * step   (UpperBound.jl:243-246)
+        // sum_i cumsum_k(BOX(i,k)) * step  ==  cumsum_k(sum_i BOX(i,k)) * step   (UpperBound.jl:243-246)
         double cs = 0.0;
-        cum[0] = 0.0;
-        for (int k = 0; k < G - 1; ++k) { cs += box[k]; cum[k + 1] = cs * step; }
+        CUM(0) = 0.0;
+        for (int k = 0; k < G - 1; ++k) { cs += BOX(k); CUM(k + 1) = cs * step; }
     }
 
     // ---- scalar bound function: `signed_rate` / `rate` (AbstractPDMP.jl:104-112) at n <= kChunk times ----
@@ -647,7 +652,7 @@ struct Chain {
                 }
             };
             double vl, gl, cs = 0.0;
-            cum[0] = 0.0;
+            CUM(0) = 0.0;
             if constexpr (!kRot && NS == 0) {
                 if (p.deriv_mode == PDMPFLUX_DERIV_JVP) {
                     // <grad U(x + t v), v> = a + t b is affine: both tangents of a cell are the function itself, so the
@@ -660,9 +665,9 @@ struct Chain {
                         finish_scalar(fma(grid_t(k + 1), lb, la), lb, vr, d0);
                         const double m = fmax(vl, vr);
                         const double b = 0.5 * (m + fabs(m)) + p.bound_refresh;
-                        box[k] = b;
+                        BOX(k) = b;
                         cs += b;
-                        cum[k + 1] = cs * step;
+                        CUM(k + 1) = cs * step;
                         vl = vr;
                     }
                     return;
@@ -673,9 +678,9 @@ struct Chain {
                 double vr, gr;
                 node(grid_t(k + 1), vr, gr);
                 const double b = scalar_cell(vl, gl, vr, gr);
-                box[k] = b;
+                BOX(k) = b;
                 cs += b;
-                cum[k + 1] = cs * step;
+                CUM(k + 1) = cs * step;
                 vl = vr; gl = gr;
             }
             return;
@@ -719,12 +724,12 @@ struct Chain {
             }
         }
         double cs = 0.0;
-        cum[0] = 0.0;
+        CUM(0) = 0.0;
         for (int k = 0; k < G - 1; ++k) {
             const double b = scalar_cell(vals[k], grads[k], vals[k + 1], grads[k + 1]);
-            box[k] = b;
+            BOX(k) = b;
             cs += b;
-            cum[k + 1] = cs * step;
+            CUM(k + 1) = cs * step;
         }
     }
 
@@ -768,8 +773,8 @@ struct Chain {
                 else if (fu <= fv || vv == x || vv == w) { vv = u; fv = fu; }
             }
         }
-        box[0] = -fx + 0.0;  // init_state passes no refresh here (AbstractPDMP.jl:122-125)
-        cum[0] = 0.0; cum[1] = box[0] * (h - 0.0);
+        BOX(0) = -fx + 0.0;  // init_state passes no refresh here (AbstractPDMP.jl:122-125)
+        CUM(0) = 0.0; CUM(1) = BOX(0) * (h - 0.0);
         step = h - 0.0;
         nb = 2; gh = h; gc = h; grem = 0.0;
     }
@@ -789,11 +794,11 @@ struct Chain {
     // next_event, UpperBound.jl:264-273
     __device__ void next_event(double e, double& tp_out, double& lb_out) const {
         int idx = 0;
-        while (idx < nb && cum[idx] < e) ++idx;  // searchsortedfirst
-        if (idx >= nb) { tp_out = CUDART_INF; lb_out = box[nb - 2]; return; }
-        if (idx == 0) { tp_out = CUDART_NAN; lb_out = box[0]; return; }  // e <= 0 cannot happen (randexp > 0)
-        tp_out = grid_t(idx - 1) + (e - cum[idx - 1]) / (cum[idx] - cum[idx - 1]) * step;
-        lb_out = box[idx - 1];
+        while (idx < nb && CUM(idx) < e) ++idx;  // searchsortedfirst
+        if (idx >= nb) { tp_out = CUDART_INF; lb_out = BOX(nb - 2); return; }
+        if (idx == 0) { tp_out = CUDART_NAN; lb_out = BOX(0); return; }  // e <= 0 cannot happen (randexp > 0)
+        tp_out = grid_t(idx - 1) + (e - CUM(idx - 1)) / (CUM(idx) - CUM(idx - 1)) * step;
+        lb_out = BOX(idx - 1);
     }
 
     // ------------------------------------------------------------------------------------------------
@@ -1386,7 +1391,7 @@ struct Chain {
 // One launch advances every chain by p.n_events accepted events (or just records the current state when
 // n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
 template <int TEAM, int SAMPLER, int POT, int PATH>
-__global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : 4) skeleton_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : 4) skeleton_kernel(const __grid_constant__ KernelParams p) {
     constexpr int CPB = kBlockThreads / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
     const int64_t c_raw = (int64_t)blockIdx.x * CPB + c_local;
@@ -1420,6 +1425,17 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : 4) s
         if (p.scratch_in_smem && SAMPLER == PDMPFLUX_FECMC) used += 3;
     }
     ch.off_f = used * vec + (int)threadIdx.x;  // TEAM == 1 only: 6 carry slots per thread
+    {
+        const int gb = p.G > 2 ? p.G : 2;      // entries per array (Brent uses 1 + 2)
+        const int base = used * vec + (TEAM == 1 ? 6 * kBlockThreads : 0);
+        if constexpr (TEAM == 1) {
+            ch.off_box = base + (int)threadIdx.x;
+            ch.off_cum = base + gb * kBlockThreads + (int)threadIdx.x;
+        } else {
+            ch.off_box = base + c_local * 2 * gb;
+            ch.off_cum = ch.off_box + gb;
+        }
+    }
     // load PDMPState
     for (int j = 0; j < ch.nown; ++j)
         if (ch.owns(j)) {
