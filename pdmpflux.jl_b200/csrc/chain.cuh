@@ -1161,7 +1161,12 @@ struct Chain {
                         // QUIRK: a non-adaptive chain keeps the full horizon although the live bound covers half of it
                         horizon = p.adaptive ? h : horizon;
                         eb += 1;
-                        eva[eb % 5] = ar;
+                        {   // error_value_ar[errored_bound % 5 + 1] = ar, without dynamic indexing (keeps the state in registers)
+                            const int slot = eb % 5;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k)
+                                if (k == slot) eva[k] = ar;
+                        }
                         half = false;
                         need_build = false;  // back in moves_until_horizon!; a proposal beyond the horizon restarts below
                     } else if (tp > horizon) {  // move_to_horizon!, :87-101 (need_build stays set)
