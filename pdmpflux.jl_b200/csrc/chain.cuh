@@ -1396,7 +1396,7 @@ struct Chain {
 // One launch advances every chain by p.n_events accepted events (or just records the current state when
 // n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
 template <int TEAM, int SAMPLER, int POT, int PATH>
-__global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : 4) skeleton_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PATH == kPathFastBrent ? 2 : 4)) skeleton_kernel(const __grid_constant__ KernelParams p) {
     constexpr int CPB = kBlockThreads / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
     const int64_t c_raw = (int64_t)blockIdx.x * CPB + c_local;
