@@ -171,6 +171,10 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
         if (fe != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("zero-fill of diagnostic columns: ") + cudaGetErrorString(fe));
     }
     cudaError_t e;
+    if (s->pot->kind == PDMPFLUX_LOGREG) {
+        p.vec32 = 0; p.bulk_rows = 0;
+        e = launch_logreg_zigzag(p, ch->grid, ch->smem, stream);
+    } else
     switch (s->kind) {
     case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
     case PDMPFLUX_BPS: e = launch_skeleton_bps(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
@@ -315,7 +319,22 @@ int pdmpflux_potential_create(int kind, int dim, const double* params, int64_t n
         pot->pp.alpha = 1.0 / (1.0 - rho);
         pot->pp.beta = rho / ((1.0 - rho) * (1.0 - rho + dim * rho));
     } break;
-    case PDMPFLUX_LOGREG:
+    case PDMPFLUX_LOGREG: {
+        if (!need(2)) { rc = fail(PDMPFLUX_ERR_ARGUMENT, "LOGREG needs n, sigma0, X[n*d], y[n]"); break; }
+        const int64_t n = (int64_t)params[0];
+        const double s0 = params[1];
+        if (n <= 0 || !(s0 > 0.0) || !need(2 + n * dim + n)) { rc = fail(PDMPFLUX_ERR_ARGUMENT, "LOGREG: bad n / sigma0 / parameter length"); break; }
+        if (dim > 128) { rc = fail(PDMPFLUX_ERR_UNSUPPORTED, "LOGREG supports dim <= 128 on the device path"); break; }
+        if (pot->params.alloc(sizeof(double) * (size_t)(n * dim + n)) != cudaSuccess ||
+            cudaMemcpy(pot->params.p, params + 2, sizeof(double) * (size_t)(n * dim + n), cudaMemcpyHostToDevice) != cudaSuccess) {
+            rc = fail(PDMPFLUX_ERR_CUDA, "LOGREG design-matrix upload failed (is a CUDA device present?)");
+            break;
+        }
+        pot->pp.vec = pot->params.as<double>();
+        pot->pp.vec2 = pot->pp.vec + n * dim;
+        pot->pp.n = n;
+        pot->pp.inv_s2 = 1.0 / (s0 * s0);
+    } break;
     case PDMPFLUX_GAUSS_DENSE:
         rc = fail(PDMPFLUX_ERR_UNSUPPORTED, "potential kind not available on the device path yet (no CPU fallback)");
         break;
@@ -344,6 +363,15 @@ int pdmpflux_sampler_create(int kind, int dim, pdmpflux_potential_t pot, const p
     auto s = new pdmpflux_sampler_s();
     s->kind = kind; s->dim = dim; s->cfg = *cfg; s->pot = pot;
     normalise_config(kind, dim, s->cfg);
+    if (pot->kind == PDMPFLUX_LOGREG) {
+        const pdmpflux_config& c = s->cfg;
+        if (kind != PDMPFLUX_ZIGZAG || !c.vectorized_bound || c.grid_size < 2 || c.grid_size > 12 ||
+            c.deriv_mode != PDMPFLUX_DERIV_JVP) {
+            delete s;
+            return fail(PDMPFLUX_ERR_UNSUPPORTED, "LOGREG runs on the device with ZigZag, vectorized_bound=true, 2 <= grid_size <= 12 "
+                                                  "and an exact AD_backend (no CPU fallback)");
+        }
+    }
     *out = s;
     return PDMPFLUX_OK;
 }
@@ -368,6 +396,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     struct Guard { pdmpflux_chains_s* c; ~Guard() { delete c; } } guard{ch};
     ch->s = s; ch->n_chains = n_chains; ch->chain_offset = chain_offset; ch->seed = seed;
     const int d = s->dim;
+    const bool logreg = s->pot->kind == PDMPFLUX_LOGREG;
     ch->team = pick_team(d, n_chains);
     // widen the team until x and v (per-thread-owned shared-memory columns) fit next to a second block
     while (ch->team < 32 && 4 * (size_t)((d + ch->team - 1) / ch->team) * kBlockThreads * sizeof(double) > 100 * 1024)
@@ -397,6 +426,10 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     {
         const size_t gb = s->cfg.grid_size > 2 ? s->cfg.grid_size : 2;      // box_max / cum_sum, one copy per chain
         ch->smem += (ch->team == 1 ? (size_t)kBlockThreads : (size_t)cpb) * 2 * gb * sizeof(double);
+    }
+    if (logreg) {  // one CTA per chain
+        ch->grid = (unsigned)n_chains;
+        ch->smem = logreg_smem_bytes(d, s->cfg.grid_size);
     }
     if (ch->smem > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "dimension too large for the shared-memory state layout");
     CUDA_TRY(ch->x.alloc(sizeof(double) * d * n_chains));

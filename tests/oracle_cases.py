@@ -32,12 +32,28 @@ CASES = [
     ("boom_banana_jvp", BOOMERANG, BANANA, None, 4, dict(tmax=1.0, refresh_rate=0.1), 1000),
     ("boom_diag_brent", BOOMERANG, GAUSS_DIAG, "linspace", 6, dict(tmax=1.0, refresh_rate=0.1, grid_size=0), 500),
     ("boom_equi64", BOOMERANG, GAUSS_EQUICORR, [0.3], 64, dict(tmax=1.0, refresh_rate=0.3), 500),
+    # Bayesian logistic regression (BASELINE.json config 4 in miniature): n rows, prior N(0, 10^2 I)
+    ("zz_logreg5_n40", ZIGZAG, LOGREG, "logreg:40", 5, dict(grid_size=6), 300),
+    ("zz_logreg100_n300", ZIGZAG, LOGREG, "logreg:300", 100, dict(grid_size=10), 120),
+    ("zz_logreg13_unsigned", ZIGZAG, LOGREG, "logreg:70", 13, dict(grid_size=4, signed_bound=False, adaptive=False, tmax=0.05), 200),
 ]
+
+
+def logreg_data(n, d, seed=2024, sigma0=10.0):
+    """Synthetic design of SURVEY.md 8d (C4): rows ~ N(0, I/d), theta* ~ N(0, I), y ~ Bernoulli(sigma(x.theta*))."""
+    g = np.random.default_rng([seed, n, d])
+    X = g.standard_normal((n, d)) / np.sqrt(d)
+    theta = g.standard_normal(d)
+    y = (g.random(n) < 1.0 / (1.0 + np.exp(-X @ theta))).astype(np.float64)
+    return X, y, sigma0
 
 
 def pot_params(pp, d):
     if isinstance(pp, str) and pp == "linspace":
         return np.linspace(0.5, 2.0, d)
+    if isinstance(pp, str) and pp.startswith("logreg:"):
+        X, y, s0 = logreg_data(int(pp.split(":")[1]), d)
+        return np.concatenate([[float(X.shape[0]), s0], X.ravel(), y])
     return None if pp is None else np.asarray(pp, dtype=np.float64)
 
 

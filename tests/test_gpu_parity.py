@@ -20,8 +20,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _potential(p, kind, pp):
+    def logreg():
+        n = int(pp[0])
+        d = (len(pp) - 2 - n) // n
+        return p.LogReg(pp[2:2 + n * d].reshape(n, d), pp[2 + n * d:], pp[1])
     return {0: lambda: p.GaussStd(), 1: lambda: p.GaussDiag(pp), 2: lambda: p.GaussEquicorr(pp[0]),
-            3: lambda: p.Banana(), 4: lambda: p.BananaReadmeScalar()}[kind]()
+            3: lambda: p.Banana(), 4: lambda: p.BananaReadmeScalar(), 5: logreg}[kind]()
 
 
 def make_sampler(p, sampler, pk, pp, d, kw):
@@ -71,6 +75,8 @@ def test_one_step_parity(p, case, team, generic):
         pytest.skip("generic path is exercised at one team width")
     if team == 1 and d > 100:
         pytest.skip("thread-per-chain is for small d")
+    if pk == 5 and (team != 8 or generic):
+        pytest.skip("logistic regression has its own CTA-per-chain kernel (team width does not apply)")
     pp = pot_params(pp, d)
     x0, v0, (E, U, N) = case_inputs(name, sampler, d, n_sk)
     r = oc.sample_skeleton(oc.make_cfg(sampler, pk, d, pp, **kw), n_sk, x0, v0, tape=(E, U, N))
@@ -282,3 +288,42 @@ def test_vector_and_bulk_store_paths_match_scalar_stores(p, d, team, n_sk, nch):
     for f in ("X", "V", "t", "horizon", "ar", "error_value_ar", "errored_bound", "rejected", "hitting_horizon"):
         assert np.array_equal(getattr(a, f), getattr(b, f)), f
     assert np.isfinite(a.X).all() and np.isfinite(a.t).all()
+
+
+def test_logreg_free_running_and_posterior(p):
+    """Config C4 in miniature: Zig-Zag on a logistic-regression posterior (CTA-per-chain DMMA kernel).  Free-running
+    parity with injected draws, Philox determinism across sharding, and a posterior sanity check against a Laplace
+    approximation."""
+    from oracle_cases import logreg_data
+    n, d, n_sk, nch = 200, 8, 400, 6
+    X, y, s0 = logreg_data(n, d)
+    pp = np.concatenate([[float(n), s0], X.ravel(), y])
+    x0, v0, (E, U, N) = case_inputs("logreg_free", 0, d, n_sk, n_chains=nch)
+    r = oc.sample_skeleton(oc.make_cfg(0, 5, d, pp, grid_size=8), n_sk, x0, v0, tape=(E, U, N))
+    assert (r.status == 0).all()
+    s = p.ZigZagAD(d, p.LogReg(X, y, s0), grid_size=8)
+    h = p.sample_skeleton(s, n_sk, x0, v0, tape=(E, U, N))
+    assert relerr(h.X, r.X) < 1e-9 and relerr(h.t, r.t) < 1e-9 and np.array_equal(h.V, r.V)
+    assert np.array_equal(h.rejected, r.rejected) and np.array_equal(h.hitting_horizon, r.hitting_horizon)
+    assert np.array_equal(h.tape_pos[:, :2], r.tape_used[:, :2])
+    # Philox mode: shards reproduce the big run
+    hp = p.sample_skeleton(s, 60, x0, v0, seed=3)
+    hp2 = p.sample_skeleton(s, 60, x0[2:5], v0[2:5], seed=3, chain_offset=2)
+    assert np.array_equal(hp.X[2:5], hp2.X) and np.array_equal(hp.t[2:5], hp2.t)
+    # posterior mean ~ MAP (Laplace) within a few posterior standard deviations, pooled over chains
+    nch2 = 64
+    hb = p.sample_skeleton(s, 1500, np.zeros((nch2, d)), np.where(np.arange(nch2 * d).reshape(nch2, d) % 2, 1.0, -1.0), seed=11)
+    m1, m2, T = p.skeleton_moments(s, hb, burn_in_cols=300)
+    theta = np.zeros(d)
+    for _ in range(50):  # Newton iterations for the MAP
+        sg = 1 / (1 + np.exp(-X @ theta))
+        g = X.T @ (sg - y) + theta / s0**2
+        Hm = X.T @ (X * (sg * (1 - sg))[:, None]) + np.eye(d) / s0**2
+        theta -= np.linalg.solve(Hm, g)
+    sd = np.sqrt(np.diag(np.linalg.inv(Hm)))
+    assert np.all(np.abs(m1.mean(axis=0) - theta) < 0.5 * sd), (m1.mean(axis=0), theta, sd)
+    # unsupported combinations fail loudly instead of falling back
+    with pytest.raises(p.UnsupportedError):
+        p.BPS(d, p.LogReg(X, y, s0))
+    with pytest.raises(p.UnsupportedError):
+        p.ZigZag(d, p.LogReg(X, y, s0), grid_size=0)

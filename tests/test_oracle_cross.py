@@ -19,7 +19,8 @@ from oracle_cases import CASES, case_inputs, pot_params, tier_tolerance
 
 def np_potential(kind, pp, d):
     return {0: lambda: onp.GaussStd(), 1: lambda: onp.GaussDiag(pp), 2: lambda: onp.GaussEquicorr(d, pp[0]),
-            3: lambda: onp.Banana(), 4: lambda: onp.BananaReadmeScalar()}[kind]()
+            3: lambda: onp.Banana(), 4: lambda: onp.BananaReadmeScalar(),
+            5: lambda: onp.LogReg(pp[2:2 + int(pp[0]) * d].reshape(int(pp[0]), d), pp[2 + int(pp[0]) * d:], pp[1])}[kind]()
 
 
 def relerr(a, b):
