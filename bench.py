@@ -33,13 +33,25 @@ CONFIGS = {
                x0=1.0, oracle=(0, 3, None, dict(grid_size=0))),
     "c3": dict(desc="BPS slanted (equicorrelated rho=0.9) Gaussian d=100, grid_size=10, refresh 0.1", d=100,
                unit_v=True, x0=0.0, oracle=(1, 2, [0.9], dict(tmax=1.0, refresh_rate=0.1))),
+    "c4": dict(desc="ZigZag Bayesian logistic regression d=100, n=1e5 synthetic rows, grid_size=10 (FP64 DMMA gradient)",
+               d=100, unit_v=False, x0=0.0, oracle=(0, 5, "logreg:100000", dict())),
     "c5f": dict(desc="ForwardECMC std Gaussian d=1000, grid_size=10", d=1000, unit_v=True, x0=0.0,
                 oracle=(2, 0, None, dict())),
     "c5b": dict(desc="Boomerang std Gaussian d=1000, grid_size=10, refresh 0.1", d=1000, unit_v=False, x0=0.0,
                 oracle=(3, 0, None, dict(tmax=1.0, refresh_rate=0.1, deriv_mode=1))),
 }
-DEFAULT_CHAINS = {"c1": 65536, "c2": 4096, "c3": 16384, "c5f": 8192, "c5b": 8192}
-DEFAULT_EVENTS = {"c1": 500, "c2": 1000, "c3": 300, "c5f": 40, "c5b": 40}
+DEFAULT_CHAINS = {"c1": 65536, "c2": 4096, "c3": 16384, "c4": 4096, "c5f": 8192, "c5b": 8192}
+DEFAULT_EVENTS = {"c1": 500, "c2": 1000, "c3": 300, "c4": 2, "c5f": 40, "c5b": 40}
+
+
+def logreg_data(n, d, seed=2024, sigma0=10.0):
+    """Synthetic design of SURVEY.md 8d (C4): rows ~ N(0, I/d), theta* ~ N(0, I), y ~ Bernoulli(sigma(x.theta*))."""
+    import numpy as np
+    g = np.random.default_rng([seed, n, d])
+    X = g.standard_normal((n, d)) / np.sqrt(d)
+    theta = g.standard_normal(d)
+    y = (g.random(n) < 1.0 / (1.0 + np.exp(-X @ theta))).astype(np.float64)
+    return X, y, sigma0
 
 
 def make_sampler(p, name):
@@ -49,6 +61,9 @@ def make_sampler(p, name):
         return p.ZigZag(50, p.Banana(), grid_size=0)
     if name == "c3":
         return p.BPS(100, p.GaussEquicorr(0.9), refresh_rate=0.1)
+    if name == "c4":
+        X, y, s0 = logreg_data(100000, 100)
+        return p.ZigZagAD(100, p.LogReg(X, y, s0))
     if name == "c5f":
         return p.ForwardECMC(1000, p.GaussStd())
     if name == "c5b":
@@ -111,15 +126,22 @@ def cpu_baseline(name, target_seconds=12.0, threads=None):
     sampler, pot, pp, kw = cfgd["oracle"]
     d = cfgd["d"]
     threads = threads or os.cpu_count() or 1
+    if isinstance(pp, str) and pp.startswith("logreg:"):
+        import numpy as np
+        X, y, s0 = logreg_data(int(pp.split(":")[1]), d)
+        pp = np.concatenate([[float(X.shape[0]), s0], X.ravel(), y])
     cfg = oc.make_cfg(sampler, pot, d, pp, **kw)
     nch = threads * 4
     x0 = np.full((nch, d), cfgd["x0"]); v0 = np.ones((nch, d)) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
-    n_ev = 50
+    n_ev = 50 if name != "c4" else 1
+    if name == "c4":
+        nch = threads
+        x0, v0 = x0[:nch], v0[:nch]
     t0 = time.perf_counter()
     oc.sample_skeleton(cfg, n_ev + 1, x0, v0, seed=2024, nthreads=threads)
     dt = time.perf_counter() - t0
     want = n_ev * target_seconds / max(dt, 1e-4)          # events per chain for the target time at nch chains
-    n_ev = int(max(50, min(20000, want)))                  # cap the stored history (16 d bytes per event per chain)
+    n_ev = int(max(50 if name != "c4" else 1, min(20000, want)))   # cap the stored history (16 d bytes per event per chain)
     if want > n_ev:
         nch = int(min(threads * 64, max(nch, threads * round(nch * want / n_ev / threads))))
         x0 = np.full((nch, d), cfgd["x0"]); v0 = np.ones((nch, d)) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
@@ -311,7 +333,7 @@ def extra_workloads(p, main, peak):
     BASELINE.json configurations and of the headline config at 65536 chains; same byte accounting."""
     import torch
     out = {}
-    todo = [(n, DEFAULT_CHAINS[n], DEFAULT_EVENTS[n]) for n in ("c1", "c2", "c3", "c5f", "c5b") if n != main]
+    todo = [(n, DEFAULT_CHAINS[n], DEFAULT_EVENTS[n]) for n in ("c1", "c2", "c3", "c4", "c5f", "c5b") if n != main]
     todo.append((main, 65536, 100))
     dev = torch.device("cuda")
     f64 = torch.float64

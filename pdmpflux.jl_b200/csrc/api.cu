@@ -325,13 +325,15 @@ int pdmpflux_potential_create(int kind, int dim, const double* params, int64_t n
         const double s0 = params[1];
         if (n <= 0 || !(s0 > 0.0) || !need(2 + n * dim + n)) { rc = fail(PDMPFLUX_ERR_ARGUMENT, "LOGREG: bad n / sigma0 / parameter length"); break; }
         if (dim > 128) { rc = fail(PDMPFLUX_ERR_UNSUPPORTED, "LOGREG supports dim <= 128 on the device path"); break; }
-        if (pot->params.alloc(sizeof(double) * (size_t)(n * dim + n)) != cudaSuccess ||
-            cudaMemcpy(pot->params.p, params + 2, sizeof(double) * (size_t)(n * dim + n), cudaMemcpyHostToDevice) != cudaSuccess) {
+        const size_t yoff = ((size_t)n * dim + 1) & ~size_t(1);  // y starts 16-byte aligned (TMA bulk source)
+        if (pot->params.alloc(sizeof(double) * (yoff + n)) != cudaSuccess ||
+            cudaMemcpy(pot->params.p, params + 2, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(pot->params.as<double>() + yoff, params + 2 + (size_t)n * dim, sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
             rc = fail(PDMPFLUX_ERR_CUDA, "LOGREG design-matrix upload failed (is a CUDA device present?)");
             break;
         }
         pot->pp.vec = pot->params.as<double>();
-        pot->pp.vec2 = pot->pp.vec + n * dim;
+        pot->pp.vec2 = pot->pp.vec + yoff;
         pot->pp.n = n;
         pot->pp.inv_s2 = 1.0 / (s0 * s0);
     } break;

@@ -21,9 +21,8 @@
 namespace pdmpflux {
 
 constexpr int kLrThreads = 128;
-constexpr int kLrRows = 64;    // rows of X per tile
+constexpr int kLrRows = 32;    // rows of X per tile (two tiles in flight per CTA, three CTAs per SM at d = 100)
 constexpr int kLrMaxG = 12;    // 2G <= 24 residual columns = 3 n-tiles
-constexpr int kLrNc = 24;      // residual-column stride in shared memory (== 4 mod 16 would be conflict free; 24 is close)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -31,76 +30,132 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+// ---- TMA bulk load global -> shared with an mbarrier (SASS: UBLKCP.S.G + SYNCS) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 struct LrShared {  // offsets (in doubles) into dynamic shared memory
-    int x, v, xv, Xt, rs, acc, z, w, y, lam, box, cum, red, total;
+    int bar, x, v, xv, Xt, ybuf, rs, acc, z, w, lam, box, cum, red, ncs, tile, total;
 };
 __host__ __device__ inline LrShared lr_layout(int d, int G) {
     LrShared L;
     const int dp = (d + 7) / 8 * 8;
     const int dm = dp + 8;  // accumulator rows (m-tiles of 8, +1 spare)
+    // residual-column stride: >= 2G and == 4 (mod 16) so the B fragments (4 rows x 8 columns) hit 32 distinct banks
+    int ncs = 4;
+    while (ncs < 2 * G) ncs += 16;
+    L.ncs = ncs;
+    L.tile = kLrRows * d + 32;                 // one X tile, rows contiguous (+ slack for fragment over-reads)
     int o = 0;
+    L.bar = o; o += 2;                          // two mbarriers (8 bytes each)
+    L.Xt = o; o += 2 * L.tile;                  // double-buffered X tiles (16-byte aligned: tile is even)
+    L.ybuf = o; o += 2 * kLrRows;
     L.x = o; o += dp;
     L.v = o; o += dp;
-    L.xv = o; o += (dp + 4) * 8;          // [k][8]: (x_k, v_k, 0...) B operand of the z/w product
-    L.Xt = o; o += kLrRows * d + 64;      // X tile, rows contiguous (+ slack for fragment over-reads)
-    L.rs = o; o += kLrRows * kLrNc + 32;  // residual columns
-    L.acc = o; o += dm * kLrNc;           // X^T R accumulators
+    L.xv = o; o += (dp + 4) * 8;                // [k][8]: (x_k, v_k, 0...) B operand of the z/w product
+    L.rs = o; o += kLrRows * ncs + 32;          // residual columns
+    L.acc = o; o += dm * 24;                    // X^T R accumulators [i][24]
     L.z = o; o += kLrRows;
     L.w = o; o += kLrRows;
-    L.y = o; o += kLrRows;
     L.lam = o; o += dp;
     L.box = o; o += kLrMaxG + 4;
     L.cum = o; o += kLrMaxG + 4;
     L.red = o; o += 64;
     L.total = o;
-    (void)G;
     return L;
 }
 size_t logreg_smem_bytes(int d, int G) { return sizeof(double) * (size_t)lr_layout(d, G).total; }
 
 // One pass over all rows of X: acc[i][c] = sum_r X[r][i] * R[r][c] for nt times tt[0..nt) (c = k: sigma - y,
-// c = nt + k: sigma' * w when want_h).  All threads of the CTA participate.
-__device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, const double* tt, int nt, bool want_h) {
+// c = nt + k: sigma' * w when want_h).  All threads of the CTA participate.  X tiles and y arrive by TMA bulk copies
+// into a two-deep ring; `phase` carries the mbarrier parities across calls.
+__device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, const double* tt, int nt, bool want_h,
+                        uint32_t (&phase)[2]) {
     const int d = p.d, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int64_t n = p.pot.n;
+    const int ncs = L.ncs;
     const int ncols = want_h ? 2 * nt : nt;
     const int n_nt = (ncols + 7) / 8;                // n-tiles of the main product
     const int n_mt = (d + 7) / 8;                    // m-tiles (coordinates)
     const int kz = (d + 3) / 4;                      // k-steps of the z/w product
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
     double acc[4][3][2];                             // up to 4 m-tiles per warp x 3 n-tiles
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    for (int64_t r0 = 0; r0 < n; r0 += kLrRows) {
+    const int64_t ntiles = (n + kLrRows - 1) / kLrRows;
+    auto issue = [&](int64_t tile) {  // thread 0: TMA the tile's rows of X and y into ring slot tile & 1
+        const int slot = (int)(tile & 1);
+        const int64_t r0 = tile * kLrRows;
         const int rows = (int)min((int64_t)kLrRows, n - r0);
-        __syncthreads();  // previous tile fully consumed
-        // ---- stage the X tile (contiguous rows) and y ----
-        const double* src = p.pot.vec + r0 * d;
-        for (int e = tid; e < kLrRows * d; e += kLrThreads) sm[L.Xt + e] = (e < rows * d) ? __ldg(src + e) : 0.0;
-        if (tid < kLrRows) sm[L.y + tid] = (tid < rows) ? __ldg(p.pot.vec2 + r0 + tid) : 0.0;
-        __syncthreads();
-        // ---- z = X x, w = X v for the tile: DMMA with B = [x v 0 ...] (k x 8) ----
-        for (int mt = warp; mt < kLrRows / 8; mt += kLrThreads / 32) {
-            double c0 = 0.0, c1 = 0.0;
-            const double* arow = sm + L.Xt + (mt * 8 + gid) * d + tig;
+        const uint32_t xb = ((uint32_t)rows * d * 8u) & ~15u, yb = ((uint32_t)rows * 8u) & ~15u;
+        mbar_expect_tx(&bar[slot], xb + yb);
+        if (xb) bulk_load(sm + L.Xt + slot * L.tile, p.pot.vec + r0 * d, xb, &bar[slot]);
+        if (yb) bulk_load(sm + L.ybuf + slot * kLrRows, p.pot.vec2 + r0, yb, &bar[slot]);
+    };
+    __syncthreads();  // the ring is free (previous pass fully consumed)
+    if (tid == 0) issue(0);
+    for (int64_t tile = 0; tile < ntiles; ++tile) {
+        const int slot = (int)(tile & 1);
+        const int64_t r0 = tile * kLrRows;
+        const int rows = (int)min((int64_t)kLrRows, n - r0);
+        if (tid == 0 && tile + 1 < ntiles) issue(tile + 1);  // slot (tile+1)&1 was released by the barrier below
+        mbar_wait(&bar[slot], phase[slot]);
+        phase[slot] ^= 1u;
+        double* Xs = sm + L.Xt + slot * L.tile;
+        double* ys = sm + L.ybuf + slot * kLrRows;
+        if (tid == 0) {  // odd tails that a 16-byte granular bulk copy cannot carry
+            if ((rows * d) & 1) Xs[rows * d - 1] = __ldg(p.pot.vec + r0 * d + rows * d - 1);
+            if (rows & 1) ys[rows - 1] = __ldg(p.pot.vec2 + r0 + rows - 1);
+        }
+        if ((rows & 1) || ((rows * d) & 1)) __syncthreads();
+        // ---- z = X x, w = X v for the tile: DMMA with B = [x v 0 ...] (k x 8); one m-tile (8 rows) per warp ----
+        {
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: halves the dependent MMA chain
+            const double* arow = Xs + (warp * 8 + gid) * d + tig;
             const double* bcol = sm + L.xv + tig * 8 + gid;
-            for (int ks = 0; ks < kz; ++ks) dmma(c0, c1, arow[4 * ks], bcol[32 * ks]);
-            if (tig == 0) { sm[L.z + mt * 8 + gid] = c0; sm[L.w + mt * 8 + gid] = c1; }
+            int ks = 0;
+            for (; ks + 1 < kz; ks += 2) {
+                dmma(c0, c1, arow[4 * ks], bcol[32 * ks]);
+                dmma(e0, e1, arow[4 * ks + 4], bcol[32 * ks + 32]);
+            }
+            if (ks < kz) dmma(c0, c1, arow[4 * ks], bcol[32 * ks]);
+            if (tig == 0) { sm[L.z + warp * 8 + gid] = c0 + e0; sm[L.w + warp * 8 + gid] = c1 + e1; }
         }
         __syncthreads();
-        // ---- residual columns: thread -> (row, half of the times) ----
+        // ---- residual columns: thread -> (row, quarter of the times) ----
         {
-            const int row = tid & (kLrRows - 1), part = tid / kLrRows;  // 2 parts
-            const double z = sm[L.z + row], w = sm[L.w + row], yy = sm[L.y + row];
+            const int row = tid & (kLrRows - 1), part = tid / kLrRows;  // 4 parts
+            const double z = sm[L.z + row], w = sm[L.w + row], yy = ys[row];
             const bool live = row < rows;
             for (int k = part; k < nt; k += kLrThreads / kLrRows) {
                 const double eta = z + tt[k] * w;
                 const double sg = 1.0 / (1.0 + exp(-eta));
-                sm[L.rs + row * kLrNc + k] = live ? sg - yy : 0.0;
-                if (want_h) sm[L.rs + row * kLrNc + nt + k] = live ? sg * (1.0 - sg) * w : 0.0;
+                sm[L.rs + row * ncs + k] = live ? sg - yy : 0.0;
+                if (want_h) sm[L.rs + row * ncs + nt + k] = live ? sg * (1.0 - sg) * w : 0.0;
             }
         }
         __syncthreads();
@@ -109,18 +164,19 @@ __device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, co
         for (int a = 0; a < 4; ++a) {
             const int mt = warp + 4 * a;
             if (mt < n_mt) {
-                const double* ap = sm + L.Xt + tig * d + mt * 8 + gid;
-                const double* bp = sm + L.rs + tig * kLrNc + gid;
+                const double* ap = Xs + tig * d + mt * 8 + gid;
+                const double* bp = sm + L.rs + tig * ncs + gid;
+#pragma unroll
                 for (int ks = 0; ks < kLrRows / 4; ++ks) {
                     const double av = ap[4 * ks * d];
 #pragma unroll
                     for (int b = 0; b < 3; ++b)
-                        if (b < n_nt) dmma(acc[a][b][0], acc[a][b][1], av, bp[4 * ks * kLrNc + 8 * b]);
+                        if (b < n_nt) dmma(acc[a][b][0], acc[a][b][1], av, bp[4 * ks * ncs + 8 * b]);
                 }
             }
         }
+        __syncthreads();  // tile consumed: its ring slot may be refilled, z / w / rs may be overwritten
     }
-    __syncthreads();
     // ---- accumulator fragments -> shared memory acc[i][c] ----
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -130,8 +186,8 @@ __device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, co
             for (int b = 0; b < 3; ++b)
                 if (b < n_nt) {
                     const int i = mt * 8 + gid, c = 8 * b + 2 * tig;
-                    sm[L.acc + i * kLrNc + c] = acc[a][b][0];
-                    sm[L.acc + i * kLrNc + c + 1] = acc[a][b][1];
+                    sm[L.acc + i * 24 + c] = acc[a][b][0];
+                    sm[L.acc + i * 24 + c + 1] = acc[a][b][1];
                 }
         }
     }
@@ -151,7 +207,7 @@ __device__ __forceinline__ double lr_block_sum(double v, double* red) {  // all 
 }
 
 __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_constant__ KernelParams p) {
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double sm[];
     const int d = p.d, G = p.G, tid = threadIdx.x;
     const int64_t c = blockIdx.x;
     const LrShared L = lr_layout(d, G);
@@ -162,8 +218,17 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         sm[L.x + i] = i < d ? p.sx[c * d + i] : 0.0;
         sm[L.v + i] = i < d ? p.sv[c * d + i] : 0.0;
     }
-    for (int e = tid; e < 64; e += kLrThreads) sm[L.Xt + kLrRows * d + e] = 0.0;      // slack read by fragment over-reads
-    for (int e = tid; e < kLrRows * kLrNc + 32; e += kLrThreads) sm[L.rs + e] = 0.0;
+    for (int e = tid; e < 2 * L.tile; e += kLrThreads) sm[L.Xt + e] = 0.0;            // incl. the slack fragment over-reads touch
+    for (int e = tid; e < kLrRows * L.ncs + 32; e += kLrThreads) sm[L.rs + e] = 0.0;
+    fence_async_smem();  // order these generic-proxy writes before the TMA (async-proxy) writes into the same buffers
+    uint32_t phase[2] = {0u, 0u};
+    if (tid == 0) {
+        uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
     double t = p.st[c], horizon = p.shorizon[c], ar = p.sar[c];
     int status = p.status[c];
     int64_t n_builds = p.counters[2 * c], n_rates = p.counters[2 * c + 1];
@@ -235,7 +300,7 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         double tt[kLrMaxG];
 #pragma unroll
         for (int k = 0; k < kLrMaxG; ++k) tt[k] = grid_t(min(k, G - 1));
-        lr_pass(p, sm, L, tt, G, true);
+        lr_pass(p, sm, L, tt, G, true, phase);
         // per-coordinate cells (thread i = coordinate i), QUIRK-preserving tangent formula (UpperBound.jl:229-241)
         double bpart[kLrMaxG];
 #pragma unroll
@@ -246,8 +311,8 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
 #pragma unroll
             for (int k = 0; k < kLrMaxG; ++k)
                 if (k < G) {
-                    const double g = sm[L.acc + i * kLrNc + k] + (xi + tt[k] * vi) * inv_s2;
-                    const double hv = sm[L.acc + i * kLrNc + G + k] + vi * inv_s2;
+                    const double g = sm[L.acc + i * 24 + k] + (xi + tt[k] * vi) * inv_s2;
+                    const double hv = sm[L.acc + i * 24 + G + k] + vi * inv_s2;
                     double val = g * vi, dval = hv * vi;
                     if (!p.signed_bound) { dval = (0.0 > val) ? 0.0 : dval; val = (val > 0.0 ? val : 0.0); }
                     if (k > 0) {
@@ -281,11 +346,11 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
     // Uses the xv operand staged by the last build_bound (x, v unchanged since).
     auto rate_at = [&](double tp) -> double {
         double tt1[1] = {tp};
-        lr_pass(p, sm, L, tt1, 1, false);
+        lr_pass(p, sm, L, tt1, 1, false, phase);
         double part = 0.0;
         for (int i = tid; i < d; i += kLrThreads) {
             const double vi = sm[L.v + i];
-            const double g = sm[L.acc + i * kLrNc] + (sm[L.x + i] + tp * vi) * inv_s2;
+            const double g = sm[L.acc + i * 24] + (sm[L.x + i] + tp * vi) * inv_s2;
             const double y = g * vi;
             const double lam = (y > 0.0 ? y : 0.0);
             sm[L.lam + i] = lam;
