@@ -71,6 +71,9 @@ def make_sampler(p, name):
     raise SystemExit(f"unknown config {name}")
 
 
+FP64_PEAK_TFLOPS = 33.4  # measured DFMA throughput (scratch/fp64_peak.cu); datasheet FP64 / FP64-tensor: 37-40
+
+
 def bytes_per_event(d):
     return 16 * d + 76
 
@@ -358,11 +361,20 @@ def extra_workloads(p, main, peak):
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
             a.record(); ch.advance(n_ev, view, 0, st); b.record(); torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b) * 1e-3)
-        ch.status(); ch.close()
+        _, _, cnt = ch.status(); ch.close()
         gbs = nch * n_ev * bytes_per_event(d) / best / 1e9
         out[f"{name}@{nch}"] = {"workload": cfgd["desc"], "chains": nch, "events_per_chain": n_ev,
                                 "events_per_s": nch * n_ev / best, "hbm_gbs": gbs, "hbm_frac": gbs / peak,
                                 "bytes_per_event": bytes_per_event(d), "ms": best * 1e3}
+        if name == "c4":
+            # governing roofline is FP64 (north_star: DMMA): 2nd(2+2G) flop per bound build (z, w and the d x 2G product),
+            # 2nd(2+1) per rate evaluation; counts come from the kernel's own counters (4 launches of n_ev events)
+            n_rows, G = 100000, 10
+            builds, rates = cnt[:, 0].sum() / 4.0, cnt[:, 1].sum() / 4.0
+            flop = 2.0 * n_rows * d * ((2 + 2 * G) * builds + 3 * rates)
+            out[f"{name}@{nch}"].update({"fp64_tflops": flop / best / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
+                                         "fp64_frac": flop / best / 1e12 / FP64_PEAK_TFLOPS,
+                                         "fp64_peak_source": "scratch/fp64_peak.cu DFMA microbenchmark on this pool's B200 (MEASURED_PEAKS.json has no FP64 entry)"})
         del bufs, view, ch
         torch.cuda.empty_cache()
     return out

@@ -193,12 +193,12 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
 __global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64_t n_sk, int64_t N, int discard_vt,
                                                      const double* __restrict__ X, const double* __restrict__ V,
                                                      const double* __restrict__ T, double* __restrict__ out) {
-    const int64_t c = blockIdx.y;
+    const int64_t c = blockIdx.x;  // chains on grid.x (up to 2^31 - 1), output elements grid-strided over grid.y
     const double* t = T + c * n_sk;
     const double dt = t[n_sk - 1] / (double)N;
     const int ld = discard_vt ? d : 2 * d + 1;
     const int64_t total = N * (int64_t)ld;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.y * blockDim.x) {
         const int64_t j = e / ld;
         const int a = (int)(e - j * ld);
         const double tm = (double)(j + 1) * dt;
@@ -719,8 +719,7 @@ int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t 
         pX = dX.as<double>(); pV = dV.as<double>(); pt = dt.as<double>(); po = dout.as<double>();
     }
     const int64_t total = N * (int64_t)ld;
-    dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, 65535), (unsigned)n_chains);
-    if (n_chains > 65535) return fail(PDMPFLUX_ERR_UNSUPPORTED, "sample_from_skeleton: more than 65535 chains per call");
+    dim3 grid((unsigned)n_chains, (unsigned)std::min<int64_t>((total + 255) / 256, 65535));
     interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, N, discard_vt, pX, pV, pt, po);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);

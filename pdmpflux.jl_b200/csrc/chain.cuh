@@ -793,8 +793,11 @@ struct Chain {
 
     // next_event, UpperBound.jl:264-273
     __device__ void next_event(double e, double& tp_out, double& lb_out) const {
+        // searchsortedfirst(cum_sum, e): cum_sum is non-decreasing (box_max >= 0), so the first index with
+        // cum_sum[idx] >= e is the number of entries below e -- counted without a data-dependent loop exit, which
+        // would make the lanes of a warp (different chains) leave one by one.
         int idx = 0;
-        while (idx < nb && CUM(idx) < e) ++idx;  // searchsortedfirst
+        for (int k = 0; k < nb; ++k) idx += (CUM(k) < e) ? 1 : 0;
         if (idx >= nb) { tp_out = CUDART_INF; lb_out = BOX(nb - 2); return; }
         if (idx == 0) { tp_out = CUDART_NAN; lb_out = BOX(0); return; }  // e <= 0 cannot happen (randexp > 0)
         tp_out = grid_t(idx - 1) + (e - CUM(idx - 1)) / (CUM(idx) - CUM(idx - 1)) * step;
