@@ -23,6 +23,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+ALL_CPUS = os.sched_getaffinity(0)
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
@@ -72,6 +73,28 @@ def make_sampler(p, name):
 
 
 FP64_PEAK_TFLOPS = 33.4  # measured DFMA throughput (scratch/fp64_peak.cu); datasheet FP64 / FP64-tensor: 37-40
+
+
+def pin_to_gpu_numa_node(index):
+    """Run (and allocate pinned host memory) on the CPUs local to the GPU's PCIe root: host buffers on the remote
+    NUMA node make the D2H leg of the end-to-end number vary by 2-3x from run to run."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        cpus = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return None
 
 
 def bytes_per_event(d):
@@ -205,6 +228,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    numa_cpus = pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     p.lib().pdmpflux_set_device(local)
     if world > 1:
@@ -312,7 +336,7 @@ def main():
                        "draws": "philox4x32-10 keyed (seed=2024, chain, event)", "stored": "full PDMPHistory row",
                        "l2": "outputs per step (%.2f GB) exceed the 126 MB L2" % (nch * n_ev * bytes_per_event(d) / 1e9)},
             "ess_per_s": ess_per_s, "ess_definition": "min over coordinates of C * Var_pi(x_i) / Var_c(chain time-average of x_i), per step window",
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "host_cpus": numa_cpus}
 
     chains.close()
     del bufs, view
@@ -324,6 +348,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, ALL_CPUS)  # the CPU baseline uses every host core
         line["cpu_baseline"] = cpu_baseline(name)[0]
     if rank == 0:
         print(json.dumps(line))
@@ -419,7 +444,8 @@ def e2e(p, sampler, name, nch, n_ev, world, dev):
                                              C.c_uint64(seed), 0, None, C.byref(view), None), status)
 
     import torch
-    call(1)
+    for w in range(4):  # warm-up calls: slab allocation, lazy module loading, PCIe / copy-engine ramp
+        call(100 + w)
     torch.cuda.synchronize()
     reps = 3
     t0 = time.perf_counter()
