@@ -33,7 +33,8 @@ typedef enum pdmpflux_error {
     PDMPFLUX_ERR_DIMENSION_MISMATCH = -2, /* Julia DimensionMismatch (AbstractPDMP.jl:96-98) */
     PDMPFLUX_ERR_UNSUPPORTED = -3,        /* sampler/potential/option outside the device path (no fallback) */
     PDMPFLUX_ERR_CUDA = -4,               /* CUDA runtime error, or no device */
-    PDMPFLUX_ERR_CHAIN = -5               /* at least one chain stopped; see per-chain status */
+    PDMPFLUX_ERR_CHAIN = -5,              /* at least one chain stopped; see per-chain status */
+    PDMPFLUX_ERR_CAPACITY = -6            /* time-horizon variant: some chain needs more than `capacity` columns */
 } pdmpflux_error;
 
 /* src/Samplers/{ZigZagSamplers,BouncyParticleSamplers,ForwardEventChainMonteCarlo,BoomerangSamplers}.jl */
@@ -64,7 +65,8 @@ typedef enum pdmpflux_chain_status {
     PDMPFLUX_CHAIN_OK = 0,
     PDMPFLUX_CHAIN_TAPE_EXHAUSTED = 1, /* injected draw tape ran out */
     PDMPFLUX_CHAIN_NOT_PROBVEC = 2,    /* ZigZag jump with sum(lambda)==0/NaN: the reference's Categorical throws */
-    PDMPFLUX_CHAIN_STEP_LIMIT = 3      /* more than max_steps thinning steps inside one event */
+    PDMPFLUX_CHAIN_STEP_LIMIT = 3,     /* more than max_steps thinning steps inside one event */
+    PDMPFLUX_CHAIN_DONE = 4            /* time-horizon variant: the chain reached t = T (not an error) */
 } pdmpflux_chain_status;
 
 /* Keyword arguments of the reference constructors (ZigZagSamplers.jl:58-60, BouncyParticleSamplers.jl:21-24,
@@ -158,6 +160,17 @@ int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int6
                                     uint64_t seed, int64_t chain_offset, const pdmpflux_tape* tape_or_null,
                                     const pdmpflux_history* hist, void* cuda_stream);
 
+/* replaces sample_skeleton(sampler, T::Float64, xinit, vinit; seed, init_capacity) (src/sample.jl:323-439): every
+ * chain advances until time T; events with t <= T are recorded and the skeleton ends with the point at exactly
+ * t = T reached by the deterministic flow (zeroed event statistics), so t[end] == T.  hist->n_cols >= capacity;
+ * n_cols_out[c] = columns written for chain c (ragged).  Returns PDMPFLUX_ERR_CAPACITY when some chain has not
+ * reached T within `capacity` columns (the first `capacity` columns of every chain are valid: grow and call again;
+ * the reference grows its PDMPHistory by doubling, Composites.jl:172-191). */
+int pdmpflux_sample_skeleton_until(pdmpflux_sampler_t s, int64_t n_chains, double T, int64_t capacity,
+                                   const double* xinit, const double* vinit, uint64_t seed, int64_t chain_offset,
+                                   const pdmpflux_tape* tape_or_null, const pdmpflux_history* hist,
+                                   int64_t* n_cols_out, void* cuda_stream);
+
 /* Streaming form of the same loop: device-resident PDMPState array (the analogue of `sampler.state`,
  * src/sample.jl:281) that can be advanced in slices; lets skeletons larger than HBM stream to the host. */
 int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double* xinit, const double* vinit,
@@ -168,6 +181,10 @@ int pdmpflux_chains_set_state(pdmpflux_chains_t ch, const double* t, const doubl
                               int32_t on_device);
 int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double* t, double* horizon,
                               int32_t on_device);
+/* time-horizon mode for chains_advance: chains stop (status PDMPFLUX_CHAIN_DONE) at exactly t = T; NaN disables */
+int pdmpflux_chains_set_stop_time(pdmpflux_chains_t ch, double T);
+/* columns recorded so far per chain (host pointer, [C]) */
+int pdmpflux_chains_get_ncols(pdmpflux_chains_t ch, int64_t* ncols);
 /* generate n_events more events per chain; column j of this call goes to hist column col0 + j (device view) */
 int pdmpflux_chains_advance(pdmpflux_chains_t ch, int64_t n_events, const pdmpflux_history* device_hist,
                             int64_t col0, void* cuda_stream);

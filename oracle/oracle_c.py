@@ -124,6 +124,37 @@ def sample_skeleton(cfg: Cfg, n_sk, xinit, vinit, *, tape=None, seed=0, chain_of
     return r
 
 
+def sample_skeleton_until(cfg: Cfg, T, cap, xinit, vinit, *, tape=None, seed=0, chain_offset=0, nthreads=1):
+    """Time-horizon variant (src/sample.jl:323-439).  Returns (result arrays with `cap` columns, ncols[C])."""
+    x = np.ascontiguousarray(np.atleast_2d(xinit), dtype=np.float64)
+    v = np.ascontiguousarray(np.atleast_2d(vinit), dtype=np.float64)
+    nch, d = x.shape
+    r = SkeletonResult()
+    r.X = np.full((nch, cap, d), np.nan); r.V = np.full((nch, cap, d), np.nan)
+    r.error_value_ar = np.zeros((nch, cap, 5))
+    r.t = np.full((nch, cap), np.nan); r.horizon = np.full((nch, cap), np.nan); r.ar = np.full((nch, cap), np.nan)
+    r.errored_bound = np.zeros((nch, cap), dtype=np.int32); r.rejected = np.zeros((nch, cap), dtype=np.int32)
+    r.hitting_horizon = np.zeros((nch, cap), dtype=np.int32)
+    r.status = np.zeros(nch, dtype=np.int32)
+    r.ncols = np.zeros(nch, dtype=np.int64)
+    h = Hist(r.X.ctypes.data, r.V.ctypes.data, r.t.ctypes.data, r.horizon.ctypes.data, r.ar.ctypes.data,
+             r.error_value_ar.ctypes.data, r.errored_bound.ctypes.data, r.rejected.ctypes.data,
+             r.hitting_horizon.ctypes.data, None)
+    if tape is not None:
+        E, U, N = (np.ascontiguousarray(np.atleast_2d(a), dtype=np.float64) for a in tape)
+        mode = 0
+    else:
+        E = U = N = np.zeros((nch, 1)); mode = 1
+    rc = lib().pdmp_oracle_sample_skeleton_until(
+        C.byref(cfg), C.c_int64(nch), C.c_int64(cap), C.c_double(T), _dp(x), _dp(v), C.c_int(mode), C.c_uint64(seed),
+        C.c_int64(chain_offset), _dp(E), C.c_int64(E.shape[1]), _dp(U), C.c_int64(U.shape[1]), _dp(N),
+        C.c_int64(N.shape[1]), C.byref(h), r.status.ctypes.data_as(C.c_void_p), r.ncols.ctypes.data_as(C.c_void_p),
+        C.c_int(nthreads))
+    if rc != 0:
+        raise ValueError("pdmp_oracle_sample_skeleton_until: invalid arguments")
+    return r
+
+
 def bound(cfg: Cfg, x, v, horizon):
     G = max(cfg.grid_size, 2)
     x = np.ascontiguousarray(x, dtype=np.float64)

@@ -756,6 +756,82 @@ int pdmp_oracle_sample_skeleton(const pdmp_oracle_cfg* cfg_in, int64_t n_chains,
     return 0;
 }
 
+/*
+ * sample_skeleton(sampler, T::Float64, ...) (src/sample.jl:323-439) for n_chains chains: events with t <= T are
+ * recorded; the first event beyond T is replaced by the point at t = T obtained by flowing the PREVIOUS state
+ * (x_prev, v_prev, t_prev) for T - t_prev, with zeroed statistics (:385-420).  `cap` columns per chain;
+ * ncols[c] = columns used, or -1 when cap was too small.
+ */
+int pdmp_oracle_sample_skeleton_until(const pdmp_oracle_cfg* cfg_in, int64_t n_chains, int64_t cap, double T,
+                                      const double* xinit, const double* vinit, int draw_mode, uint64_t seed,
+                                      int64_t chain_offset, const double* tapeE, int64_t nE, const double* tapeU,
+                                      int64_t nU, const double* tapeN, int64_t nN, const pdmp_oracle_hist* hist,
+                                      int32_t* status, int64_t* ncols, int nthreads) {
+    pdmp_oracle_cfg cfg = *cfg_in;
+    normalise_cfg(&cfg);
+    if (cap <= 0 || cfg.dim <= 0 || cfg.grid_size < 0 || cfg.grid_size == 1 || !(T >= 0) || isinf(T)) return -1;
+    int d = cfg.dim, G = cfg.grid_size > 2 ? cfg.grid_size : 2;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t c = 0; c < n_chains; ++c) {
+        chain_t ch; memset(&ch, 0, sizeof(ch));
+        ch.c = &cfg; ch.d = d; ch.G = cfg.grid_size;
+        pot_init(&ch.pot, &cfg);
+        double* buf = (double*)calloc((size_t)d * 12 + (size_t)2 * d * G + 3 * (size_t)G + 8, sizeof(double));
+        double* p = buf;
+        ch.x = p; p += d; ch.v = p; p += d; ch.xt = p; p += d; ch.vt = p; p += d; ch.g = p; p += d; ch.h = p; p += d;
+        ch.w1 = p; p += d; ch.w2 = p; p += d; ch.w3 = p; p += d; ch.w4 = p; p += d;
+        double* x_prev = p; p += d; double* v_prev = p; p += d;
+        ch.vals = p; p += (size_t)d * G; ch.grads = p; p += (size_t)d * G;
+        ch.grid = p; p += G; ch.box_max = p; p += G; ch.cum_sum = p; p += G;
+        ch.signed_bound = cfg.signed_bound;
+        ch.bound_refresh = cfg.signed_bound ? cfg.refresh_rate : 0.0;
+        memcpy(ch.x, xinit + (size_t)c * d, sizeof(double) * d);
+        memcpy(ch.v, vinit + (size_t)c * d, sizeof(double) * d);
+        ch.t = 0.0; ch.horizon = cfg.tmax; ch.adaptive = cfg.adaptive;
+        ch.dr.mode = draw_mode; ch.dr.seed = seed; ch.dr.chain = (uint64_t)(chain_offset + c);
+        if (!draw_mode) {
+            ch.dr.E = tapeE + (size_t)c * nE; ch.dr.nE = nE;
+            ch.dr.U = tapeU + (size_t)c * nU; ch.dr.nU = nU;
+            ch.dr.N = tapeN + (size_t)c * nN; ch.dr.nN = nN;
+        }
+        int64_t k = 0;
+        record(hist, c, cap, 0, &ch);
+        k = 1;
+        int overflow = 0;
+        uint64_t ev = 0;
+        while (ch.t < T) {
+            memcpy(x_prev, ch.x, sizeof(double) * d);
+            memcpy(v_prev, ch.v, sizeof(double) * d);
+            double t_prev = ch.t;
+            ch.dr.event = ++ev; ch.dr.sE = ch.dr.sU = ch.dr.sN = 0;
+            get_event_state(&ch, 1000000);
+            if (ch.status != ST_OK) break;
+            if (k >= cap) { overflow = 1; break; }
+            if (ch.t <= T) {
+                record(hist, c, cap, k, &ch);
+                ++k;
+            } else { /* overshoot: the t = T point by flow from the previous state */
+                double tau = T - t_prev;
+                flow(&ch, x_prev, v_prev, tau, ch.x, ch.v);
+                ch.t = T;
+                ch.ar = 0.0; ch.errored_bound = 0; ch.rejected = 0; ch.hitting_horizon = 0;
+                for (int j = 0; j < 5; ++j) ch.error_value_ar[j] = 0.0;
+                record(hist, c, cap, k, &ch);
+                ++k;
+                break;
+            }
+        }
+        if (status) status[c] = ch.status;
+        if (ncols) ncols[c] = overflow ? -1 : k;
+        pot_free(&ch.pot);
+        free(buf);
+    }
+    return 0;
+}
+
 /* One bound build + inversion, exposed for known-answer tests: fills grid/box_max/cum_sum (G entries,
  * or 2 for grid_size 0) and returns step_size. */
 double pdmp_oracle_bound(const pdmp_oracle_cfg* cfg_in, const double* x, const double* v, double horizon,

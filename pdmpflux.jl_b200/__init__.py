@@ -5,19 +5,20 @@ sample_from_skeleton, sample, PDMPHistory.  Everything computes on the GPU throu
 fallback.  Import name: `pdmpflux_b200` (the directory name `pdmpflux.jl_b200` is not a Python identifier;
 the shim `pdmpflux_b200.py` at the repository root maps it).
 """
-from ._lib import (ArgumentError, ChainError, CudaError, DimensionMismatch, UnsupportedError, LIB_PATH, build,
+from ._lib import (ArgumentError, CapacityError, ChainError, CudaError, DimensionMismatch, UnsupportedError, LIB_PATH, build,
                    lib)
 from .device import DeviceChains, device_history_view
 from . import dist
 from .history import PDMPHistory, PDMPHistoryBatch
 from .potentials import (Banana, BananaReadmeScalar, GaussDiag, GaussEquicorr, GaussStd, LogReg, Potential)
-from .sample import (ess_from_chain_means, sample, sample_from_skeleton, sample_skeleton, skeleton_moments)
+from .sample import (ess_from_chain_means, sample, sample_from_skeleton, sample_skeleton, sample_skeleton_until,
+                     skeleton_moments)
 from .samplers import (BPS, BPSAD, AbstractPDMP, Boomerang, BoomerangAD, ForwardECMC, ForwardECMCAD, ZigZag,
                        ZigZagAD)
 
 __all__ = [
     "ZigZag", "ZigZagAD", "BPS", "BPSAD", "ForwardECMC", "ForwardECMCAD", "Boomerang", "BoomerangAD",
-    "AbstractPDMP", "sample", "sample_skeleton", "sample_from_skeleton", "skeleton_moments",
+    "AbstractPDMP", "sample", "sample_skeleton", "sample_skeleton_until", "CapacityError", "sample_from_skeleton", "skeleton_moments",
     "ess_from_chain_means", "PDMPHistory", "PDMPHistoryBatch", "Potential", "GaussStd", "GaussDiag",
     "GaussEquicorr", "Banana", "BananaReadmeScalar", "LogReg", "ArgumentError", "DimensionMismatch",
     "UnsupportedError", "CudaError", "ChainError", "build", "lib", "LIB_PATH", "DeviceChains",

@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpdmpflux_cuda.so")
 
-OK, ERR_ARGUMENT, ERR_DIMENSION_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR_CHAIN = 0, -1, -2, -3, -4, -5
+OK, ERR_ARGUMENT, ERR_DIMENSION_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR_CHAIN, ERR_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 
 
 class ArgumentError(ValueError):
@@ -30,6 +30,10 @@ class UnsupportedError(NotImplementedError):
 
 class CudaError(RuntimeError):
     pass
+
+
+class CapacityError(RuntimeError):
+    """Time-horizon variant: a chain needs more history columns than the capacity it was given."""
 
 
 class ChainError(RuntimeError):
@@ -78,6 +82,11 @@ SIGNATURES = {
     "pdmpflux_sample_skeleton_resume": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64,
                                                   C.POINTER(Tape), C.POINTER(History), C.c_void_p]),
+    "pdmpflux_sample_skeleton_until": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
+                                                 C.c_uint64, C.c_int64, C.POINTER(Tape), C.POINTER(History), C.c_void_p,
+                                                 C.c_void_p]),
+    "pdmpflux_chains_set_stop_time": (C.c_int, [C.c_void_p, C.c_double]),
+    "pdmpflux_chains_get_ncols": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pdmpflux_chains_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
     "pdmpflux_chains_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "pdmpflux_chains_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64,
@@ -135,4 +144,6 @@ def check(rc, status=None):
         raise UnsupportedError(msg)
     if rc == ERR_CHAIN:
         raise ChainError(msg, status)
+    if rc == ERR_CAPACITY:
+        raise CapacityError(msg)
     raise CudaError(msg)

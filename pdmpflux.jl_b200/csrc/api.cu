@@ -90,7 +90,9 @@ struct pdmpflux_chains_s {
     int team = 32, n_own = 0, scratch_in_smem = 1, path = 0, vec_elems = 0, dpad = 0;
     size_t smem = 0;
     unsigned grid = 0;
-    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch;
+    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols;
+    double t_stop = 0.0;
+    int use_t_stop = 0;
     // draws
     int draw_mode = 1;
     DevBuf tE, tU, tN;  // owned device copies when the tape was given on the host
@@ -137,6 +139,8 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     p.shorizon = ch->horizon.as<double>(); p.sar = ch->ar.as<double>();
     p.tape_pos = ch->tape_pos.as<int64_t>(); p.status = ch->status.as<int32_t>();
     p.counters = ch->counters.as<int64_t>();
+    p.ncols = ch->ncols.as<int64_t>();
+    p.use_t_stop = ch->use_t_stop; p.t_stop = ch->t_stop;
     p.draw_mode = ch->draw_mode; p.tE = ch->dE; p.tU = ch->dU; p.tN = ch->dN;
     p.nE = ch->nE; p.nU = ch->nU; p.nN = ch->nN;
     if (h) {
@@ -442,6 +446,8 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     CUDA_TRY(ch->tape_pos.alloc(sizeof(int64_t) * 3 * n_chains));
     CUDA_TRY(ch->status.alloc(sizeof(int32_t) * n_chains));
     CUDA_TRY(ch->counters.alloc(sizeof(int64_t) * 2 * n_chains));
+    CUDA_TRY(ch->ncols.alloc(sizeof(int64_t) * n_chains));
+    CUDA_TRY(cudaMemset(ch->ncols.p, 0, sizeof(int64_t) * n_chains));
     const cudaMemcpyKind k = init_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CUDA_TRY(cudaMemcpy(ch->x.p, xinit, sizeof(double) * d * n_chains, k));
     CUDA_TRY(cudaMemcpy(ch->v.p, vinit, sizeof(double) * d * n_chains, k));
@@ -496,6 +502,20 @@ int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double
     return PDMPFLUX_OK;
 }
 
+int pdmpflux_chains_set_stop_time(pdmpflux_chains_t ch, double T) {
+    if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
+    if (T != T) { ch->use_t_stop = 0; return PDMPFLUX_OK; }
+    if (!std::isfinite(T) || T < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "T must be finite and non-negative. Current value: " + std::to_string(T));
+    ch->use_t_stop = 1; ch->t_stop = T;
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_get_ncols(pdmpflux_chains_t ch, int64_t* ncols) {
+    if (!ch || !ncols) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
+    CUDA_TRY(cudaMemcpy(ncols, ch->ncols.p, sizeof(int64_t) * ch->n_chains, cudaMemcpyDeviceToHost));
+    return PDMPFLUX_OK;
+}
+
 int pdmpflux_chains_advance(pdmpflux_chains_t ch, int64_t n_events, const pdmpflux_history* h, int64_t col0, void* stream) {
     if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
     if (n_events <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "n_events must be positive");
@@ -521,7 +541,7 @@ int pdmpflux_chains_status(pdmpflux_chains_t ch, int32_t* status, int64_t* tape_
     if (counters) CUDA_TRY(cudaMemcpy(counters, ch->counters.p, sizeof(int64_t) * 2 * ch->n_chains, cudaMemcpyDeviceToHost));
     int64_t bad = 0, first = -1;
     for (int64_t c = 0; c < ch->n_chains; ++c)
-        if (st[c] != 0) { if (first < 0) first = c; ++bad; }
+        if (st[c] != 0 && st[c] != PDMPFLUX_CHAIN_DONE) { if (first < 0) first = c; ++bad; }
     if (bad) return fail(PDMPFLUX_ERR_CHAIN, std::to_string(bad) + " chain(s) stopped; first: chain " + std::to_string(first) + " status " + std::to_string(st[first]));
     return PDMPFLUX_OK;
 }
@@ -535,10 +555,33 @@ int pdmpflux_sample_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_s
                                            tape, hist, stream_);
 }
 
+static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, const double* xinit, const double* vinit,
+                        const double* t0, const double* horizon0, int64_t event0, uint64_t seed, int64_t chain_offset,
+                        const pdmpflux_tape* tape, const pdmpflux_history* hist, void* stream_, const double* t_stop,
+                        int64_t* n_cols_out);
+
 int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, const double* xinit,
                                     const double* vinit, const double* t0, const double* horizon0, int64_t event0,
                                     uint64_t seed, int64_t chain_offset, const pdmpflux_tape* tape,
                                     const pdmpflux_history* hist, void* stream_) {
+    return run_skeleton(s, n_chains, n_sk, xinit, vinit, t0, horizon0, event0, seed, chain_offset, tape, hist, stream_,
+                        nullptr, nullptr);
+}
+
+int pdmpflux_sample_skeleton_until(pdmpflux_sampler_t s, int64_t n_chains, double T, int64_t capacity,
+                                   const double* xinit, const double* vinit, uint64_t seed, int64_t chain_offset,
+                                   const pdmpflux_tape* tape, const pdmpflux_history* hist, int64_t* n_cols_out,
+                                   void* stream_) {
+    if (!std::isfinite(T) || T < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "T must be finite and non-negative. Current value: " + std::to_string(T));
+    if (capacity <= 0 || !n_cols_out) return fail(PDMPFLUX_ERR_ARGUMENT, "capacity must be positive and n_cols_out non-NULL");
+    return run_skeleton(s, n_chains, capacity, xinit, vinit, nullptr, nullptr, 0, seed, chain_offset, tape, hist, stream_,
+                        &T, n_cols_out);
+}
+
+static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, const double* xinit, const double* vinit,
+                        const double* t0, const double* horizon0, int64_t event0, uint64_t seed, int64_t chain_offset,
+                        const pdmpflux_tape* tape, const pdmpflux_history* hist, void* stream_, const double* t_stop,
+                        int64_t* n_cols_out) {
     if (!s || !hist) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
     if (n_sk <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "n_sk must be positive. Current value: " + std::to_string(n_sk));
     if (hist->n_cols < n_sk) return fail(PDMPFLUX_ERR_ARGUMENT, "history n_cols < n_sk");
@@ -552,6 +595,28 @@ int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int6
         rc = pdmpflux_chains_set_state(ch, t0, horizon0, event0, hist->on_device);
         if (rc != PDMPFLUX_OK) return rc;
     }
+    if (t_stop) {
+        rc = pdmpflux_chains_set_stop_time(ch, *t_stop);
+        if (rc != PDMPFLUX_OK) return rc;
+    }
+    // time-horizon variant: report ragged column counts; a chain that used the whole capacity without reaching T
+    // makes the call return PDMPFLUX_ERR_CAPACITY (after the outputs have been delivered)
+    auto finish = [&](int rc_status) -> int {
+        if (!t_stop || (rc_status != PDMPFLUX_OK)) return rc_status;
+        std::vector<int64_t> nc((size_t)n_chains);
+        std::vector<int32_t> st((size_t)n_chains);
+        if (cudaMemcpy(nc.data(), ch->ncols.p, sizeof(int64_t) * n_chains, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(st.data(), ch->status.p, sizeof(int32_t) * n_chains, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(PDMPFLUX_ERR_CUDA, "reading back column counts failed");
+        int64_t unfinished = 0;
+        for (int64_t c = 0; c < n_chains; ++c) {
+            if (hist->on_device) { /* counts are always returned on the host */ }
+            n_cols_out[c] = nc[c];
+            if (st[c] != PDMPFLUX_CHAIN_DONE) ++unfinished;
+        }
+        if (unfinished) return fail(PDMPFLUX_ERR_CAPACITY, std::to_string(unfinished) + " chain(s) need more than " + std::to_string(n_sk) + " columns to reach T");
+        return PDMPFLUX_OK;
+    };
 
     if (hist->on_device) {
         pdmpflux_history h = *hist;
@@ -562,7 +627,7 @@ int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int6
         if (hist->status) CUDA_TRY(cudaMemcpy(hist->status, ch->status.p, sizeof(int32_t) * n_chains, cudaMemcpyDeviceToDevice));
         if (hist->tape_pos) CUDA_TRY(cudaMemcpy(hist->tape_pos, ch->tape_pos.p, sizeof(int64_t) * 3 * n_chains, cudaMemcpyDeviceToDevice));
         if (hist->counters) CUDA_TRY(cudaMemcpy(hist->counters, ch->counters.p, sizeof(int64_t) * 2 * n_chains, cudaMemcpyDeviceToDevice));
-        return pdmpflux_chains_status(ch, nullptr, nullptr, nullptr);
+        return finish(pdmpflux_chains_status(ch, nullptr, nullptr, nullptr));
     }
 
     // ---- host-buffer path: slices of columns, two device slabs, D2H of slice i overlaps the kernel of slice i+1
@@ -693,7 +758,7 @@ int pdmpflux_sample_skeleton_resume(pdmpflux_sampler_t s, int64_t n_chains, int6
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaStreamSynchronize(copy_stream));
-    return pdmpflux_chains_status(ch, hist->status, hist->tape_pos, hist->counters);
+    return finish(pdmpflux_chains_status(ch, hist->status, hist->tape_pos, hist->counters));
 }
 
 int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, const double* X,

@@ -1142,6 +1142,8 @@ struct Chain {
         bool need_build = true, half = false;
         accept = false;
         begin_event(0);
+        // time-horizon variant: `while state.t < T` (src/sample.jl:360)
+        if (p.use_t_stop && status == 0 && !(t < p.t_stop)) status = PDMPFLUX_CHAIN_DONE;
         bool live = valid && status == 0 && p.n_events > 0;
         // Every lane of the warp stays in this loop until the whole warp is done; the warp-wide vote at the loop
         // head is the reconvergence point of each iteration, and both blocks of the body are plain ifs, so the
@@ -1190,6 +1192,22 @@ struct Chain {
                     ar = lt / lambda_bar;
                     if (ar > 1.0) { need_build = true; half = true; }
                     else if (rand_uniform() < ar) {  // ac_step_with_proxy!, :153-168 -> if_accept!, :170-186
+                        if (p.use_t_stop && t + tp + ts > p.t_stop) {
+                            // The event falls beyond T: the skeleton ends with the point at exactly t = T reached by
+                            // the deterministic flow, with zeroed event statistics (src/sample.jl:385-420).  The
+                            // state is at time t + ts here, so the remaining flow time may be negative when horizon
+                            // moves already carried it past T (the flows are groups: same point as flowing the
+                            // pre-event state by T - t).
+                            flow_inplace(p.t_stop - (t + ts));
+                            t = p.t_stop;
+                            ar = 0.0; eb = 0; rej = 0; hh = 0;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) eva[k] = 0.0;
+                            record(c, p.col0 + ev);
+                            ++ev;
+                            status = PDMPFLUX_CHAIN_DONE;
+                            live = false;
+                        } else {
                         if constexpr (kZZ) accept_zigzag(tp, lt);
                         else {
                             flow_inplace(tp);
@@ -1207,6 +1225,8 @@ struct Chain {
                             begin_event(ev);
                             need_build = true;
                             live = ev < p.n_events;
+                            if (p.use_t_stop && !(t < p.t_stop)) { status = PDMPFLUX_CHAIN_DONE; live = false; }
+                        }
                         }
                     } else {  // if_reject!, :188-203
                         const double e3 = exp_rv + rand_exp();
@@ -1474,6 +1494,7 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
         if (valid) {
             ch.record(c, p.col0);
             ch.finish_output(c, 1);
+            if (ch.tl == 0) p.ncols[c] += 1;
         }
         return;
     }
@@ -1494,6 +1515,7 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
         p.counters[2 * c] = ch.n_builds;
         p.counters[2 * c + 1] = ch.n_rates;
         p.tape_pos[3 * c] = ch.pE; p.tape_pos[3 * c + 1] = ch.pU; p.tape_pos[3 * c + 2] = ch.pN;
+        p.ncols[c] += n_rec;
     }
 }
 

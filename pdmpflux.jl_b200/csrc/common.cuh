@@ -45,6 +45,10 @@ struct KernelParams {
     int64_t* tape_pos; // [C][3]
     int32_t* status;   // [C]
     int64_t* counters; // [C][2]
+    int64_t* ncols;    // [C] history columns recorded so far (time-horizon variant)
+    // time-horizon variant (src/sample.jl:323-439): stop each chain at exactly t_stop
+    int use_t_stop;
+    double t_stop;
     // draws
     int draw_mode;  // 0 tape, 1 philox
     const double *tE, *tU, *tN;

@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
     if (p.n_events == 0) {
         const double zero5[5] = {0, 0, 0, 0, 0};
         record(p.col0, 0, 0, 0, zero5);
+        if (tid == 0) p.ncols[c] += 1;
         return;
     }
 
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
     };
 
     int64_t n_rec = 0;
+    if (p.use_t_stop && status == 0 && !(t < p.t_stop)) status = PDMPFLUX_CHAIN_DONE;
     if (status == 0) {
         for (int64_t ev = 0; ev < p.n_events; ++ev) {
             key.event = (uint32_t)(p.event0 + ev + 1);
@@ -399,6 +401,15 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
                         eb += 1;
                         eva[eb % 5] = ar;
                     } else if (rand_uniform() < ar) {  // if_accept!, :170-186
+                        if (p.use_t_stop && t + tp + ts > p.t_stop) {  // time-horizon variant, src/sample.jl:385-420
+                            flow(p.t_stop - (t + ts));
+                            t = p.t_stop;
+                            ar = 0.0; eb = 0; rej = 0; hh = 0;
+                            for (int k = 0; k < 5; ++k) eva[k] = 0.0;
+                            status = PDMPFLUX_CHAIN_DONE;
+                            accept = true;
+                            break;
+                        }
                         const double uS = rand_uniform() * lt;  // categorical draw against the rates just computed
                         flow(tp);
                         if (tid == 0) {                          // first index with cumulative lambda > u S
@@ -422,9 +433,11 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
                     if (exhausted) status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED;
                 }
             }
-            if (status != 0) break;
+            if (status != 0 && status != PDMPFLUX_CHAIN_DONE) break;
             record(p.col0 + ev, eb, rej, hh, eva);
             ++n_rec;
+            if (status == PDMPFLUX_CHAIN_DONE) break;
+            if (p.use_t_stop && !(t < p.t_stop)) { status = PDMPFLUX_CHAIN_DONE; break; }
         }
     }
     __syncthreads();
@@ -436,6 +449,7 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         p.st[c] = t; p.shorizon[c] = horizon; p.sar[c] = ar; p.status[c] = status;
         p.counters[2 * c] = n_builds; p.counters[2 * c + 1] = n_rates;
         p.tape_pos[3 * c] = pE; p.tape_pos[3 * c + 1] = pU;
+        p.ncols[c] += n_rec;
     }
 }
 

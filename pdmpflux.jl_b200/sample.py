@@ -55,8 +55,11 @@ def sample_skeleton(sampler: AbstractPDMP, n_sk, xinit, vinit, *, seed=None, ver
     `t0`, `horizon0` (per chain) and `event0` resume from a saved state (the last column of an earlier
     history) instead of init_state; column 0 of the result is then that state.
     """
+    if isinstance(n_sk, (float, np.floating)):  # Julia dispatches on Float64: the time-horizon method
+        return sample_skeleton_until(sampler, float(n_sk), xinit, vinit, seed=seed, verbose=verbose, tape=tape,
+                                     chain_offset=chain_offset, batch=batch)
     if not isinstance(n_sk, (int, np.integer)):
-        raise TypeError("n_sk must be an integer")
+        raise TypeError("n_sk must be an integer (number of skeleton points) or a float (time horizon T)")
     if n_sk <= 0:
         raise _lib.ArgumentError(f"n_sk must be positive. Current value: {n_sk}")
     x, v, batched = _init_arrays(sampler, xinit, vinit)
@@ -79,6 +82,49 @@ def sample_skeleton(sampler: AbstractPDMP, n_sk, xinit, vinit, *, seed=None, ver
     sampler.state = hb.status.copy()
     _lib.check(rc, hb.status)
     return hb if batched else hb.chain(0)
+
+
+def sample_skeleton_until(sampler: AbstractPDMP, T, xinit, vinit, *, seed=None, verbose=True, tape=None, chain_offset=0,
+                          batch=None, init_capacity=1024):
+    """sample_skeleton(sampler, T::Float64, xinit, vinit; seed, init_capacity) (src/sample.jl:323-439): advance every
+    chain to time T; the skeleton ends with the point at exactly t = T (t[end] == T).  The number of events is not
+    known a priori: like the reference the history capacity doubles until every chain fits (the run is
+    deterministic, so it is simply repeated with the larger capacity).  Returns a `PDMPHistory` for a (d,) init, a
+    list of ragged `PDMPHistory` (one per chain) for a (C, d) init."""
+    T = float(T)
+    if not math.isfinite(T) or T < 0:
+        raise _lib.ArgumentError(f"T must be finite and non-negative. Current value: {T}")
+    x, v, batched = _init_arrays(sampler, xinit, vinit)
+    if batch is not None:
+        batched = batch
+    n_chains = x.shape[0]
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    cap = max(1, int(init_capacity))
+    t, keep = _make_tape(tape, n_chains)
+    while True:
+        hb = PDMPHistoryBatch(n_chains, cap, sampler.dim)
+        ncols = np.zeros(n_chains, dtype=np.int64)
+        view = _lib.History(_ptr(hb.X), _ptr(hb.V), _ptr(hb.t), _ptr(hb.horizon), _ptr(hb.ar), _ptr(hb.error_value_ar),
+                            _ptr(hb.errored_bound), _ptr(hb.rejected), _ptr(hb.hitting_horizon), _ptr(hb.status),
+                            _ptr(hb.tape_pos), _ptr(hb.counters), cap, 0)
+        rc = _lib.lib().pdmpflux_sample_skeleton_until(sampler._handle, n_chains, T, cap, _ptr(x), _ptr(v),
+                                                       C.c_uint64(int(seed) & (2**64 - 1)), int(chain_offset),
+                                                       C.byref(t) if t is not None else None, C.byref(view), _ptr(ncols),
+                                                       None)
+        if rc == _lib.ERR_CAPACITY:
+            cap *= 2
+            continue
+        sampler.state = hb.status.copy()
+        _lib.check(rc, hb.status)
+        break
+    out = []
+    for c in range(n_chains):
+        n = int(ncols[c])
+        out.append(PDMPHistory(hb.X[c, :n].T, hb.V[c, :n].T, hb.t[c, :n], hb.horizon[c, :n], hb.ar[c, :n],
+                               hb.errored_bound[c, :n], hb.error_value_ar[c, :n].T, hb.rejected[c, :n],
+                               hb.hitting_horizon[c, :n]))
+    return out if batched else out[0]
 
 
 def _as_batch_arrays(history):

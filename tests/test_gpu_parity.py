@@ -327,3 +327,50 @@ def test_logreg_free_running_and_posterior(p):
         p.BPS(d, p.LogReg(X, y, s0))
     with pytest.raises(p.UnsupportedError):
         p.ZigZag(d, p.LogReg(X, y, s0), grid_size=0)
+
+
+@pytest.mark.parametrize("kind", ["zigzag", "bps", "boomerang", "fecmc", "logreg"])
+def test_time_horizon_variant_parity(p, kind):
+    """sample_skeleton(sampler, T::Float64, ...) (src/sample.jl:323-439) against the oracle's literal restatement:
+    same ragged column counts, t[end] == T exactly, event columns and the final flowed point within tolerance."""
+    from oracle_cases import logreg_data
+    d, nch, T = 6, 7, 9.0
+    g = np.random.default_rng(5)
+    x0 = 0.3 * g.standard_normal((nch, d))
+    if kind == "zigzag":
+        s, cfg, v0 = p.ZigZagAD(d, p.GaussStd()), oc.make_cfg(0, 0, d), np.where(g.random((nch, d)) < 0.5, -1.0, 1.0)
+    elif kind == "bps":
+        s, cfg = p.BPS(d, p.GaussDiag(np.linspace(0.5, 2, d)), refresh_rate=0.3), oc.make_cfg(1, 1, d, np.linspace(0.5, 2, d), tmax=1.0, refresh_rate=0.3)
+        v0 = g.standard_normal((nch, d)); v0 /= np.linalg.norm(v0, axis=1, keepdims=True)
+    elif kind == "boomerang":
+        s, cfg = p.Boomerang(d, p.GaussStd(), refresh_rate=0.4, AD_backend="ForwardDiff"), oc.make_cfg(3, 0, d, tmax=1.0, refresh_rate=0.4)
+        v0 = g.standard_normal((nch, d))
+    elif kind == "fecmc":
+        s, cfg = p.ForwardECMC(d, p.GaussStd()), oc.make_cfg(2, 0, d)
+        v0 = g.standard_normal((nch, d)); v0 /= np.linalg.norm(v0, axis=1, keepdims=True)
+    else:
+        X, y, s0 = logreg_data(60, d)
+        s, cfg = p.ZigZagAD(d, p.LogReg(X, y, s0), grid_size=5), oc.make_cfg(0, 5, d, np.concatenate([[60.0, s0], X.ravel(), y]), grid_size=5)
+        v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0); T = 1.5
+    E = g.standard_exponential((nch, 4000)); U = g.random((nch, 4000)); N = g.standard_normal((nch, 4000 * d))
+    r = oc.sample_skeleton_until(cfg, T, 1000, x0, v0, tape=(E, U, N))
+    assert (r.status == 0).all() and (r.ncols >= 2).all()
+    hs = p.sample_skeleton(s, T, x0, v0, tape=(E, U, N), batch=True)     # float T -> time-horizon method
+    assert [len(h) for h in hs] == r.ncols.tolist()
+    tol = 1e-9
+    for c, h in enumerate(hs):
+        n = r.ncols[c]
+        assert h.t[-1] == T and h.X.shape == (d, n)
+        assert relerr(h.X.T, r.X[c, :n]) < tol and relerr(h.V.T, r.V[c, :n]) < tol and relerr(h.t, r.t[c, :n]) < tol
+        assert np.array_equal(h.rejected, r.rejected[c, :n]) and np.array_equal(h.hitting_horizon, r.hitting_horizon[c, :n])
+        assert h.ar[-1] == 0 and h.rejected[-1] == 0 and h.hitting_horizon[-1] == 0
+    # capacity growth path (reference: _grow_history doubling) and the single-chain return type
+    h1 = p.sample_skeleton_until(s, T, x0[0], v0[0], tape=(E[:1], U[:1], N[:1]), init_capacity=2)
+    assert len(h1) == r.ncols[0] and h1.t[-1] == T and relerr(h1.X.T, r.X[0, :r.ncols[0]]) < tol
+    h0 = p.sample_skeleton(s, 0.0, x0[0], v0[0], seed=1)
+    assert len(h0) == 1 and h0.t[0] == 0.0
+    with pytest.raises(p.ArgumentError):
+        p.sample_skeleton(s, -1.0, x0[0], v0[0], seed=1)
+    # sample_from_skeleton on the ragged result uses t[end] == T as its time scale
+    xs = p.sample_from_skeleton(s, 50, hs[0])
+    assert xs.shape == (d, 50) and np.isfinite(xs).all()

@@ -183,3 +183,23 @@ def test_error_paths():
     with pytest.raises(FloatingPointError):
         s = onp.Sampler(2, onp.GaussStd(), onp.Config(sampler=0))
         s.velocity_jump(np.zeros(2), np.ones(2), onp.make_tape(0, 4, 4, 4))
+
+
+def test_time_horizon_variant_oracle():
+    """sample_skeleton(sampler, T) (src/sample.jl:323-439): t[end] == T exactly (test_samplers.jl:56-62), the last
+    column is the flow of the previous state, event columns agree with the n_sk variant on the same draws."""
+    d, T = 3, 7.5
+    cfg = oc.make_cfg(0, 0, d)
+    x0 = np.zeros((2, d)); v0 = np.ones((2, d))
+    r = oc.sample_skeleton_until(cfg, T, 400, x0, v0, seed=3)
+    full = oc.sample_skeleton(cfg, 400, x0, v0, seed=3)
+    for c in range(2):
+        n = r.ncols[c]
+        assert 2 < n < 400 and r.t[c, n - 1] == T and np.all(np.diff(r.t[c, :n]) > 0)
+        assert np.array_equal(r.X[c, :n - 1], full.X[c, :n - 1]) and np.array_equal(r.t[c, :n - 1], full.t[c, :n - 1])
+        tau = T - r.t[c, n - 2]
+        assert np.allclose(r.X[c, n - 1], r.X[c, n - 2] + r.V[c, n - 2] * tau, rtol=0, atol=1e-15)
+        assert np.array_equal(r.V[c, n - 1], r.V[c, n - 2]) and r.ar[c, n - 1] == 0 and full.t[c, n - 1] > T
+    # T == 0: the initial point alone; too small a capacity is reported
+    assert oc.sample_skeleton_until(cfg, 0.0, 4, x0, v0, seed=3).ncols.tolist() == [1, 1]
+    assert oc.sample_skeleton_until(cfg, T, 3, x0, v0, seed=3).ncols.tolist() == [-1, -1]
