@@ -202,6 +202,14 @@ int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t 
                                   const double* V, const double* t, int64_t N, int32_t discard_vt, double* out,
                                   int32_t on_device, void* cuda_stream);
 
+/* replaces sample_from_skeleton(sampler, dt::Float64, history) (src/sample.jl:573-646): samples at times j*dt,
+ * j = 1..n_out with n_out = floor(t[end]/dt) computed by the caller; and, with n_sk < ld_sk, the (N, dt) method
+ * (src/sample.jl:649-682) that only uses the first n_sk columns of slabs whose leading dimension is ld_sk.
+ * All chains must share n_out (pass chains one at a time for ragged skeletons). */
+int pdmpflux_sample_from_skeleton_dt(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int64_t n_chains,
+                                     const double* X, const double* V, const double* t, double dt, int64_t n_out,
+                                     int32_t discard_vt, double* out, int32_t on_device, void* cuda_stream);
+
 /* Closed-form time integrals over each chain's skeleton (no reference equivalent; feeds moments / ESS,
  * SURVEY.md 8d): m1[C][d] = int x_i dt, m2[C][d] = int x_i^2 dt over [t[col_begin], t[n_sk-1]], T[C] = length. */
 int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, int64_t col_begin,

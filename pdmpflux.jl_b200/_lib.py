@@ -97,6 +97,9 @@ SIGNATURES = {
     "pdmpflux_chains_destroy": (C.c_int, [C.c_void_p]),
     "pdmpflux_sample_from_skeleton": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdmpflux_sample_from_skeleton_dt": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int32, C.c_void_p,
+                                                   C.c_int32, C.c_void_p]),
     "pdmpflux_skeleton_moments": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_void_p]),

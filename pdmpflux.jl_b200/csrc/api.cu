@@ -194,12 +194,15 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
 // ---- sample_from_skeleton (src/sample.jl:475-513) -------------------------------------------------------
 // One thread per output element (sample j, coordinate a) of one chain; neighbouring threads share j, so the
 // binary search over the chain's event times is a broadcast and X/V/out accesses are coalesced.
-__global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64_t n_sk, int64_t N, int discard_vt,
-                                                     const double* __restrict__ X, const double* __restrict__ V,
-                                                     const double* __restrict__ T, double* __restrict__ out) {
+// `dt_fixed > 0`: the dt method (src/sample.jl:573-646), sample times j * dt_fixed; otherwise dt = t[end] / N (:475-513).
+// `ld_sk` is the leading dimension of the history slabs (>= n_sk: the (N, dt) method uses the first n_sk columns).
+__global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64_t n_sk, int64_t ld_sk, int64_t N,
+                                                     int discard_vt, double dt_fixed, const double* __restrict__ X,
+                                                     const double* __restrict__ V, const double* __restrict__ T,
+                                                     double* __restrict__ out) {
     const int64_t c = blockIdx.x;  // chains on grid.x (up to 2^31 - 1), output elements grid-strided over grid.y
-    const double* t = T + c * n_sk;
-    const double dt = t[n_sk - 1] / (double)N;
+    const double* t = T + c * ld_sk;
+    const double dt = dt_fixed > 0.0 ? dt_fixed : t[n_sk - 1] / (double)N;
     const int ld = discard_vt ? d : 2 * d + 1;
     const int64_t total = N * (int64_t)ld;
     for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.y * blockDim.x) {
@@ -213,8 +216,8 @@ __global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64
             if (t[mid] <= tm) lo = mid; else hi = mid - 1;
         }
         const double tau = tm - t[lo];
-        const double* x0 = X + (c * n_sk + lo) * d;
-        const double* v0 = V + (c * n_sk + lo) * d;
+        const double* x0 = X + (c * ld_sk + lo) * d;
+        const double* v0 = V + (c * ld_sk + lo) * d;
         double r;
         if (a == 2 * d) r = tm;
         else {
@@ -761,10 +764,28 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
     return finish(pdmpflux_chains_status(ch, hist->status, hist->tape_pos, hist->counters));
 }
 
+static int interp_impl(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int64_t n_chains, const double* X,
+                       const double* V, const double* t, int64_t N, double dt_fixed, int32_t discard_vt, double* out,
+                       int32_t on_device, void* stream_);
+
 int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, const double* X,
                                   const double* V, const double* t, int64_t N, int32_t discard_vt, double* out,
                                   int32_t on_device, void* stream_) {
     if (N <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "N must be positive. Current value: " + std::to_string(N));
+    return interp_impl(flow_kind, dim, n_sk, n_sk, n_chains, X, V, t, N, 0.0, discard_vt, out, on_device, stream_);
+}
+
+int pdmpflux_sample_from_skeleton_dt(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int64_t n_chains,
+                                     const double* X, const double* V, const double* t, double dt, int64_t n_out,
+                                     int32_t discard_vt, double* out, int32_t on_device, void* stream_) {
+    if (!(dt > 0.0) || !std::isfinite(dt)) return fail(PDMPFLUX_ERR_ARGUMENT, "dt must be positive and finite");
+    if (n_out <= 0 || ld_sk < n_sk) return fail(PDMPFLUX_ERR_ARGUMENT, "n_out must be positive and ld_sk >= n_sk");
+    return interp_impl(flow_kind, dim, n_sk, ld_sk, n_chains, X, V, t, n_out, dt, discard_vt, out, on_device, stream_);
+}
+
+static int interp_impl(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int64_t n_chains, const double* X,
+                       const double* V, const double* t, int64_t N, double dt_fixed, int32_t discard_vt, double* out,
+                       int32_t on_device, void* stream_) {
     if (!X || !V || !t || !out || dim <= 0 || n_sk <= 0 || n_chains <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
     if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear) or 1 (rotation)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -775,17 +796,17 @@ int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t 
     if (!on_device) {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: no CPU fallback");
-        const size_t nx = sizeof(double) * dim * n_sk * n_chains;
-        CUDA_TRY(dX.alloc(nx)); CUDA_TRY(dV.alloc(nx)); CUDA_TRY(dt.alloc(sizeof(double) * n_sk * n_chains));
+        const size_t nx = sizeof(double) * dim * ld_sk * n_chains;
+        CUDA_TRY(dX.alloc(nx)); CUDA_TRY(dV.alloc(nx)); CUDA_TRY(dt.alloc(sizeof(double) * ld_sk * n_chains));
         CUDA_TRY(dout.alloc(sizeof(double) * ld * N * n_chains));
         CUDA_TRY(cudaMemcpyAsync(dX.p, X, nx, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(dV.p, V, nx, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(dt.p, t, sizeof(double) * n_sk * n_chains, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dt.p, t, sizeof(double) * ld_sk * n_chains, cudaMemcpyHostToDevice, stream));
         pX = dX.as<double>(); pV = dV.as<double>(); pt = dt.as<double>(); po = dout.as<double>();
     }
     const int64_t total = N * (int64_t)ld;
     dim3 grid((unsigned)n_chains, (unsigned)std::min<int64_t>((total + 255) / 256, 65535));
-    interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, N, discard_vt, pX, pV, pt, po);
+    interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, ld_sk, N, discard_vt, dt_fixed, pX, pV, pt, po);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     if (!on_device) {

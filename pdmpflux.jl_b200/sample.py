@@ -135,9 +135,15 @@ def _as_batch_arrays(history):
             np.ascontiguousarray(history.t)[None])
 
 
-def sample_from_skeleton(sampler: AbstractPDMP, N, history, *, discard_vt=True):
-    """sample_from_skeleton(sampler, N, history; discard_vt) (src/sample.jl:475-513).  Returns a (d, N) array
-    (or (2d+1, N)) for a `PDMPHistory`, like the reference's Matrix; (C, N, d) for a batch."""
+def sample_from_skeleton(sampler: AbstractPDMP, N, history, dt=None, *, discard_vt=True):
+    """The three methods of the reference, dispatched like Julia on the argument types:
+      sample_from_skeleton(sampler, N::Int, history)            N equidistant samples, dt = t[end]/N   (sample.jl:475-513)
+      sample_from_skeleton(sampler, dt::Float64, history)       samples at j*dt, j = 1..floor(t[end]/dt) (sample.jl:573-646)
+      sample_from_skeleton(sampler, N::Int, dt::Float64, history) -> call as (sampler, N, history, dt): first N skeleton
+                                                                points, samples at dt:dt:t[N]           (sample.jl:649-682)
+    Returns a (d, M) array (or (2d+1, M) with discard_vt=False) for a `PDMPHistory`; (C, M, d) for a batch."""
+    if dt is not None or isinstance(N, (float, np.floating)):
+        return _sample_from_skeleton_dt(sampler, N, history, dt, discard_vt)
     if N <= 0:
         raise _lib.ArgumentError(f"N must be positive. Current value: {N}")
     X, V, t = _as_batch_arrays(history)
@@ -146,6 +152,31 @@ def sample_from_skeleton(sampler: AbstractPDMP, N, history, *, discard_vt=True):
     out = np.empty((n_chains, int(N), ld))
     _lib.check(_lib.lib().pdmpflux_sample_from_skeleton(sampler.flow_kind, d, n_sk, n_chains, _ptr(X), _ptr(V), _ptr(t),
                                                         int(N), int(bool(discard_vt)), _ptr(out), 0, None))
+    return out if isinstance(history, PDMPHistoryBatch) else out[0].T
+
+
+def _sample_from_skeleton_dt(sampler, N, history, dt, discard_vt):
+    X, V, t = _as_batch_arrays(history)
+    n_chains, ld_sk, d = X.shape
+    if dt is None:            # (sampler, dt, history)
+        dt, n_sk = float(N), ld_sk
+    else:                     # (sampler, N, dt, history): only the first N skeleton points
+        dt, n_sk = float(dt), int(N)
+        if not 1 <= n_sk <= ld_sk:
+            raise _lib.ArgumentError(f"N must be in 1..{ld_sk}. Current value: {N}")
+    if not (dt > 0 and math.isfinite(dt)):
+        raise _lib.ArgumentError(f"dt must be positive. Current value: {dt}")
+    t_end = t[:, n_sk - 1]
+    # floor(T_end / dt) (sample.jl:609) and length(dt:dt:t[end]) (:655) agree up to the range's rounding guard
+    n_out = np.floor(t_end / dt).astype(np.int64)
+    if not np.all(n_out == n_out[0]):
+        raise _lib.ArgumentError("chains have different t[end]: call per chain (ragged output)")
+    M = int(n_out[0])
+    ld = d if discard_vt else 2 * d + 1
+    out = np.empty((n_chains, M, ld))
+    if M > 0:
+        _lib.check(_lib.lib().pdmpflux_sample_from_skeleton_dt(sampler.flow_kind, d, n_sk, ld_sk, n_chains, _ptr(X), _ptr(V),
+                                                               _ptr(t), dt, M, int(bool(discard_vt)), _ptr(out), 0, None))
     return out if isinstance(history, PDMPHistoryBatch) else out[0].T
 
 

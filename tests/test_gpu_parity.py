@@ -374,3 +374,36 @@ def test_time_horizon_variant_parity(p, kind):
     # sample_from_skeleton on the ragged result uses t[end] == T as its time scale
     xs = p.sample_from_skeleton(s, 50, hs[0])
     assert xs.shape == (d, 50) and np.isfinite(xs).all()
+
+
+def test_sample_from_skeleton_dt_methods(p):
+    """The dt method (src/sample.jl:573-646) and the (N, dt) method (:649-682) against a direct numpy evaluation."""
+    d, n_sk = 4, 500
+    for s, fk in ((p.ZigZagAD(d, p.GaussStd()), 0), (p.Boomerang(d, p.GaussStd(), refresh_rate=0.5), 1)):
+        h = p.sample_skeleton(s, n_sk, np.zeros(d), np.ones(d), seed=4)
+
+        def ref(nuse, dt):
+            tt = h.t[:nuse]
+            M = int(np.floor(tt[-1] / dt))
+            out = np.empty((2 * d + 1, M))
+            for j in range(1, M + 1):
+                tm = j * dt
+                i = np.searchsorted(tt, tm, side="right") - 1
+                tau = tm - tt[i]
+                if fk:
+                    out[:d, j - 1] = h.X[:, i] * np.cos(tau) + h.V[:, i] * np.sin(tau)
+                    out[d:2 * d, j - 1] = -h.X[:, i] * np.sin(tau) + h.V[:, i] * np.cos(tau)
+                else:
+                    out[:d, j - 1] = h.X[:, i] + h.V[:, i] * tau
+                    out[d:2 * d, j - 1] = h.V[:, i]
+                out[2 * d, j - 1] = tm
+            return out
+        dt = h.t[-1] / 333.3
+        a = p.sample_from_skeleton(s, dt, h)                       # (sampler, dt, history)
+        r = ref(n_sk, dt)
+        assert a.shape == (d, r.shape[1]) and np.allclose(a, r[:d], rtol=1e-12, atol=1e-13)
+        b = p.sample_from_skeleton(s, 200, h, dt, discard_vt=False)  # (sampler, N, dt, history)
+        r2 = ref(200, dt)
+        assert b.shape == r2.shape and np.allclose(b, r2, rtol=1e-12, atol=1e-13)
+    with pytest.raises(p.ArgumentError):
+        p.sample_from_skeleton(s, -0.1, h)
