@@ -181,6 +181,11 @@ int pdmpflux_chains_set_state(pdmpflux_chains_t ch, const double* t, const doubl
                               int32_t on_device);
 int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double* t, double* horizon,
                               int32_t on_device);
+/* Fused moments (no reference equivalent; feeds moments / ESS without materialising a skeleton): after enabling,
+ * every later chains_advance accumulates int x_i dt and int x_i^2 dt per chain and coordinate ([C][d]) inside the
+ * flows (closed form per segment); chains_advance may then be called with a NULL history. */
+int pdmpflux_chains_enable_moments(pdmpflux_chains_t ch);
+int pdmpflux_chains_get_moments(pdmpflux_chains_t ch, double* m1, double* m2, int32_t on_device);
 /* time-horizon mode for chains_advance: chains stop (status PDMPFLUX_CHAIN_DONE) at exactly t = T; NaN disables */
 int pdmpflux_chains_set_stop_time(pdmpflux_chains_t ch, double T);
 /* columns recorded so far per chain (host pointer, [C]) */

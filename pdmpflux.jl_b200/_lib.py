@@ -85,6 +85,8 @@ SIGNATURES = {
     "pdmpflux_sample_skeleton_until": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
                                                  C.c_uint64, C.c_int64, C.POINTER(Tape), C.POINTER(History), C.c_void_p,
                                                  C.c_void_p]),
+    "pdmpflux_chains_enable_moments": (C.c_int, [C.c_void_p]),
+    "pdmpflux_chains_get_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "pdmpflux_chains_set_stop_time": (C.c_int, [C.c_void_p, C.c_double]),
     "pdmpflux_chains_get_ncols": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pdmpflux_chains_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),

@@ -90,7 +90,8 @@ struct pdmpflux_chains_s {
     int team = 32, n_own = 0, scratch_in_smem = 1, path = 0, vec_elems = 0, dpad = 0;
     size_t smem = 0;
     unsigned grid = 0;
-    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols;
+    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols, m1, m2;
+    int moments = 0;
     double t_stop = 0.0;
     int use_t_stop = 0;
     // draws
@@ -141,6 +142,7 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     p.counters = ch->counters.as<int64_t>();
     p.ncols = ch->ncols.as<int64_t>();
     p.use_t_stop = ch->use_t_stop; p.t_stop = ch->t_stop;
+    p.accumulate_moments = ch->moments; p.M1 = ch->m1.as<double>(); p.M2 = ch->m2.as<double>();
     p.draw_mode = ch->draw_mode; p.tE = ch->dE; p.tU = ch->dU; p.tN = ch->dN;
     p.nE = ch->nE; p.nU = ch->nU; p.nN = ch->nN;
     if (h) {
@@ -175,15 +177,17 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
         if (fe != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("zero-fill of diagnostic columns: ") + cudaGetErrorString(fe));
     }
     cudaError_t e;
+    const size_t smem_launch = ch->smem + (ch->moments ? 2 * (size_t)ch->vec_elems * sizeof(double) : 0);
+    if (smem_launch > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "fused moments: shared memory exhausted for this dimension");
     if (s->pot->kind == PDMPFLUX_LOGREG) {
         p.vec32 = 0; p.bulk_rows = 0;
         e = launch_logreg_zigzag(p, ch->grid, ch->smem, stream);
     } else
     switch (s->kind) {
-    case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
-    case PDMPFLUX_BPS: e = launch_skeleton_bps(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
-    case PDMPFLUX_FECMC: e = launch_skeleton_fecmc(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
-    case PDMPFLUX_BOOMERANG: e = launch_skeleton_boomerang(ch->team, s->pot->kind, ch->path, p, ch->grid, ch->smem, stream); break;
+    case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
+    case PDMPFLUX_BPS: e = launch_skeleton_bps(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
+    case PDMPFLUX_FECMC: e = launch_skeleton_fecmc(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
+    case PDMPFLUX_BOOMERANG: e = launch_skeleton_boomerang(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
     default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("skeleton kernel launch: ") + cudaGetErrorString(e));
@@ -502,6 +506,26 @@ int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double
     if (v) CUDA_TRY(cudaMemcpy(v, ch->v.p, nd, k));
     if (t) CUDA_TRY(cudaMemcpy(t, ch->t.p, sizeof(double) * ch->n_chains, k));
     if (horizon) CUDA_TRY(cudaMemcpy(horizon, ch->horizon.p, sizeof(double) * ch->n_chains, k));
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_enable_moments(pdmpflux_chains_t ch) {
+    if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
+    if (ch->s->pot->kind == PDMPFLUX_LOGREG) return fail(PDMPFLUX_ERR_UNSUPPORTED, "fused moments are not available for the logistic-regression kernel");
+    if (ch->moments) return PDMPFLUX_OK;
+    const size_t nd = sizeof(double) * ch->s->dim * ch->n_chains;
+    CUDA_TRY(ch->m1.alloc(nd)); CUDA_TRY(ch->m2.alloc(nd));
+    CUDA_TRY(cudaMemset(ch->m1.p, 0, nd)); CUDA_TRY(cudaMemset(ch->m2.p, 0, nd));
+    ch->moments = 1;
+    return PDMPFLUX_OK;
+}
+
+int pdmpflux_chains_get_moments(pdmpflux_chains_t ch, double* m1, double* m2, int32_t on_device) {
+    if (!ch || !ch->moments) return fail(PDMPFLUX_ERR_ARGUMENT, "moments are not enabled on these chains");
+    const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t nd = sizeof(double) * ch->s->dim * ch->n_chains;
+    if (m1) CUDA_TRY(cudaMemcpy(m1, ch->m1.p, nd, k));
+    if (m2) CUDA_TRY(cudaMemcpy(m2, ch->m2.p, nd, k));
     return PDMPFLUX_OK;
 }
 

@@ -34,6 +34,8 @@ extern __shared__ __align__(128) double g_smem[];
 #define VS(j) g_smem[off_v + (j) * kStr]
 #define AS(j) g_smem[off_a + (j) * kStr]
 #define BS(j) g_smem[off_b + (j) * kStr]
+#define M1S(j) g_smem[off_m1 + (j) * kStr]
+#define M2S(j) g_smem[off_m2 + (j) * kStr]
 #define BOX(k) g_smem[off_box + (k) * kBStr]
 #define CUM(k) g_smem[off_cum + (k) * kBStr]
 
@@ -65,6 +67,7 @@ struct Chain {
     static constexpr int kBStr = (TEAM == 1) ? kBlockThreads : 1;    // stride between a chain's box / cum entries
 
     const KernelParams& p;
+    int off_m1, off_m2;              // fused-moment accumulators (owned columns, only when p.accumulate_moments)
     int off_x, off_v, off_a, off_b;  // element offsets into g_smem of this thread's owned columns of x, v, A, B
     double* sc0; // scratch owned vectors (FECMC)
     double* sc1;
@@ -239,9 +242,27 @@ struct Chain {
         }
     }
 
+    // closed-form int_0^tt x_i(s) ds and int_0^tt x_i(s)^2 ds along the flow from the current (x, v); tt may be
+    // negative (time-horizon variant stepping back to T), which subtracts the overshoot
+    __device__ void accumulate_segment(double tt, const Flow& f) {
+        for (int j = 0; j < nown; ++j)
+            if (owns(j)) {
+                const double x = XS(j), v = VS(j);
+                if constexpr (kRot) {  // x cos s + v sin s  (f.a = cos tt, f.b = sin tt)
+                    const double s2t = 2.0 * f.b * f.a;
+                    M1S(j) += x * f.b + v * (1.0 - f.a);
+                    M2S(j) += x * x * (0.5 * tt + 0.25 * s2t) + v * v * (0.5 * tt - 0.25 * s2t) + x * v * f.b * f.b;
+                } else {
+                    M1S(j) += tt * (x + 0.5 * v * tt);
+                    M2S(j) += tt * (x * x + tt * (x * v + v * v * tt * (1.0 / 3.0)));
+                }
+            }
+    }
+
     __device__ void flow_inplace(double tt) {
         wait_row_stores();  // x / v are about to change: the TMA engine must have read the previous row
         const Flow f = flow_coef(tt);
+        if (p.accumulate_moments) accumulate_segment(tt, f);
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
                 double xt, vt;
@@ -1078,6 +1099,7 @@ struct Chain {
     // by the acceptance (u < S / lambda_bar), hence Categorical's isprobvec check cannot fail here.
     __device__ void accept_zigzag(double tt, double S) {
         wait_row_stores();
+        if (p.accumulate_moments) accumulate_segment(tt, flow_coef(tt));
         double Lxn[KK];
 #pragma unroll
         for (int k = 0; k < KK; ++k) Lxn[k] = Lx[k] + Lv[k] * tt;
@@ -1452,6 +1474,17 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
         ch.sc2 = base + 2 * (size_t)vec;
         if (p.scratch_in_smem && SAMPLER == PDMPFLUX_FECMC) used += 3;
     }
+    ch.off_m1 = ch.off_m2 = 0;
+    if (p.accumulate_moments) {
+        ch.off_m1 = used * vec + toff;
+        ch.off_m2 = (used + 1) * vec + toff;
+        used += 2;
+        for (int j = 0; j < ch.nown; ++j)
+            if (ch.owns(j)) {
+                g_smem[ch.off_m1 + j * ch.kStr] = p.M1[c * p.d + ch.coord(j)];
+                g_smem[ch.off_m2 + j * ch.kStr] = p.M2[c * p.d + ch.coord(j)];
+            }
+    }
     ch.off_f = used * vec + (int)threadIdx.x;  // TEAM == 1 only: 6 carry slots per thread
     {
         const int gb = p.G > 2 ? p.G : 2;      // entries per array (Brent uses 1 + 2)
@@ -1507,6 +1540,12 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
             p.sx[c * p.d + ch.coord(j)] = g_smem[ch.off_x + j * ch.kStr];
             p.sv[c * p.d + ch.coord(j)] = g_smem[ch.off_v + j * ch.kStr];
         }
+    if (p.accumulate_moments)
+        for (int j = 0; j < ch.nown; ++j)
+            if (ch.owns(j)) {
+                p.M1[c * p.d + ch.coord(j)] = g_smem[ch.off_m1 + j * ch.kStr];
+                p.M2[c * p.d + ch.coord(j)] = g_smem[ch.off_m2 + j * ch.kStr];
+            }
     if (ch.tl == 0) {
         p.st[c] = ch.t;
         p.shorizon[c] = ch.horizon;

@@ -46,6 +46,11 @@ struct KernelParams {
     int32_t* status;   // [C]
     int64_t* counters; // [C][2]
     int64_t* ncols;    // [C] history columns recorded so far (time-horizon variant)
+    // fused moments (no reference equivalent): running time integrals of x_i and x_i^2 per chain,
+    // accumulated segment by segment inside the flows, so moments / ESS need no stored skeleton
+    int accumulate_moments;
+    double* M1;        // [C][d] int x_i dt
+    double* M2;        // [C][d] int x_i^2 dt
     // time-horizon variant (src/sample.jl:323-439): stop each chain at exactly t_stop
     int use_t_stop;
     double t_stop;

@@ -80,6 +80,20 @@ class DeviceChains:
         _lib.check(rc, st)
         return st, pos, cnt
 
+    def enable_moments(self):
+        """Accumulate int x dt and int x^2 dt per chain inside the kernel from now on (no skeleton needed)."""
+        _lib.check(_lib.lib().pdmpflux_chains_enable_moments(self._h))
+
+    def moments(self):
+        """(int x dt, int x^2 dt) accumulated since enable_moments(), each (n_chains, d)."""
+        d = self.sampler.dim
+        m1 = np.empty((self.n_chains, d)); m2 = np.empty((self.n_chains, d))
+        _lib.check(_lib.lib().pdmpflux_chains_get_moments(self._h, m1.ctypes.data, m2.ctypes.data, 0))
+        return m1, m2
+
+    def set_stop_time(self, T):
+        _lib.check(_lib.lib().pdmpflux_chains_set_stop_time(self._h, float(T)))
+
     def get_state(self):
         d = self.sampler.dim
         x = np.empty((self.n_chains, d)); v = np.empty((self.n_chains, d))

@@ -407,3 +407,48 @@ def test_sample_from_skeleton_dt_methods(p):
         assert b.shape == r2.shape and np.allclose(b, r2, rtol=1e-12, atol=1e-13)
     with pytest.raises(p.ArgumentError):
         p.sample_from_skeleton(s, -0.1, h)
+
+
+@pytest.mark.parametrize("kind", ["zigzag", "bps", "boomerang", "fecmc"])
+def test_fused_moments_match_skeleton_integrals(p, kind):
+    """In-kernel running integrals of x and x^2 (no stored skeleton needed) equal the closed-form integrals over the
+    stored skeleton, also across several advance() calls, with a NULL history and in the time-horizon mode."""
+    import torch
+    d, nch, n_ev = 12, 40, 300
+    g = np.random.default_rng(8)
+    x0 = g.standard_normal((nch, d))
+    v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0) if kind == "zigzag" else g.standard_normal((nch, d))
+    s = {"zigzag": lambda: p.ZigZagAD(d, p.Banana()), "bps": lambda: p.BPS(d, p.GaussEquicorr(0.5), refresh_rate=0.3),
+         "boomerang": lambda: p.Boomerang(d, p.GaussDiag(np.linspace(0.5, 2, d)), refresh_rate=0.4),
+         "fecmc": lambda: p.ForwardECMC(d, p.GaussStd())}[kind]()
+    dev = torch.device("cuda")
+    f64 = torch.float64
+    ch = p.DeviceChains(s, x0, v0, seed=21)
+    ch.enable_moments()
+    X = torch.empty((nch, n_ev + 1, d), dtype=f64, device=dev); V = torch.empty_like(X)
+    t = torch.empty((nch, n_ev + 1), dtype=f64, device=dev)
+    view = p.device_history_view(n_ev + 1, X=X, V=V, t=t)
+    ch.record(view, 0)
+    ch.advance(100, view, 1)
+    ch.advance(n_ev - 100, view, 101)
+    torch.cuda.synchronize()
+    m1, m2 = ch.moments()
+    hb = p.PDMPHistoryBatch(nch, n_ev + 1, d)
+    hb.X[:] = X.cpu().numpy(); hb.V[:] = V.cpu().numpy(); hb.t[:] = t.cpu().numpy()
+    r1, r2, T = p.skeleton_moments(s, hb)
+    assert np.allclose(m1, r1 * T[:, None], rtol=1e-10, atol=1e-11) and np.allclose(m2, r2 * T[:, None], rtol=1e-10, atol=1e-11)
+    # no history at all + stop at T: the integrals cover exactly [0, T]
+    ch2 = p.DeviceChains(s, x0, v0, seed=21)
+    ch2.enable_moments()
+    Tstop = float(hb.t[:, 150].min())
+    ch2.set_stop_time(Tstop)
+    ch2.advance(400)
+    a1, a2 = ch2.moments()
+    _, _, tt, _ = ch2.get_state()
+    assert np.all(tt == Tstop)
+    # reference value: integrate the stored skeleton up to Tstop with dense sampling of the exact path
+    dense = p.sample_from_skeleton(s, 200000, hb)  # (C, N, d) over [0, t_end]
+    for c in range(0, nch, 13):
+        n_in = int(np.floor(Tstop / (hb.t[c, -1] / 200000)))
+        approx = dense[c, :n_in].mean(axis=0) * Tstop
+        assert np.allclose(a1[c], approx, atol=5e-3 * max(1.0, Tstop))
