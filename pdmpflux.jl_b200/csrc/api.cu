@@ -440,8 +440,9 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
         const size_t gb = s->cfg.grid_size > 2 ? s->cfg.grid_size : 2;      // box_max / cum_sum, one copy per chain
         ch->smem += (ch->team == 1 ? (size_t)kBlockThreads : (size_t)cpb) * 2 * gb * sizeof(double);
     }
-    if (logreg) {  // one CTA per chain
-        ch->grid = (unsigned)n_chains;
+    if (logreg) {  // logreg_chains_per_block() chains per CTA, one warp each
+        const int lcpb = logreg_chains_per_block();
+        ch->grid = (unsigned)((n_chains + lcpb - 1) / lcpb);
         ch->smem = logreg_smem_bytes(d, s->cfg.grid_size);
     }
     if (ch->smem > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "dimension too large for the shared-memory state layout");

@@ -72,9 +72,10 @@ inline int select_path(int sampler, int pot, int grid_size, int vectorized, int 
     return kPathFastGrid;  // BPS / FECMC / Boomerang: closed-form nodes, analytic or finite-difference derivative
 }
 
-// logreg.cu: Zig-Zag x logistic regression, one CTA per chain, FP64 DMMA
+// logreg.cu: Zig-Zag x logistic regression, four chains per CTA sharing each pass over X, FP64 DMMA
 cudaError_t launch_logreg_zigzag(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 size_t logreg_smem_bytes(int d, int G);
+int logreg_chains_per_block();
 
 cudaError_t launch_skeleton_zigzag(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_skeleton_bps(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);

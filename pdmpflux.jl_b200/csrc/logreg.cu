@@ -1,4 +1,4 @@
-// Zig-Zag on a Bayesian logistic-regression posterior (BASELINE.json config 4): one CTA per chain.
+// Zig-Zag on a Bayesian logistic-regression posterior (BASELINE.json config 4): four chains per CTA.
 //
 //   U(theta) = sum_r [log(1 + exp(z_r)) - y_r z_r] + |theta|^2 / (2 sigma0^2),  z = X theta,  X: n x d row-major
 //   grad U   = X^T (sigma(z) - y) + theta / sigma0^2
@@ -10,19 +10,33 @@
 // (ZigZagSamplers.jl:101-107) and record! (Composites.jl:239-260).
 //
 // Affine trick: along the flow line X (x + t v) = z + t w with z = X x, w = X v, so one pass over the
-// rows of X yields the gradient and the Hessian-vector product at ALL grid times:
-//     [G | HV] (d x 2G)  =  X^T (n x d)^T  .  [sigma(z + t_k w) - y | sigma'(z + t_k w) .* w]_k (n x 2G)
-// Per row tile (64 rows, staged in shared memory) the CTA computes z, w (DMMA, N padded to 8), the 2G residual columns
-// (exp), and accumulates the d x 2G product with FP64 tensor-core MMAs (mma.sync.m8n8k4.f64 = SASS DMMA; tcgen05 has
-// no FP64 kind).  X (n d 8 bytes, 80 MB for C4) stays resident in the 126 MB L2 across chains.
+// rows of X yields the gradient and the Hessian-vector product at ALL grid times of a bound:
+//     [G | HV] (d x 2G)  =  X^T  .  [sigma(z + t_k w) - y | sigma'(z + t_k w) .* w]_k (n x 2G)
+// and the rate at a proposal time is the same pass with one column.
+//
+// Execution: a CTA of 4 warps owns 4 chains.  Between passes warp c runs chain c's thinning state machine; whenever
+// the chains need gradients they post a request (a bound: G times with Hessian columns, or a rate: 1 time) and the
+// whole CTA makes ONE pass over X serving all four:
+//   * 32-row tiles of X (rows are contiguous in row-major X) and of y arrive by TMA bulk copies
+//     (cp.async.bulk + mbarrier expect-tx, SASS UBLKCP.S.G) into a two-deep ring;
+//   * z, w of all four chains: one DMMA product with B = [x1 v1 x2 v2 x3 v3 x4 v4] -- exactly the 8 columns of
+//     mma.sync.m8n8k4.f64, no padding;
+//   * residual columns (exp) for every requested time of every chain, packed side by side (up to 4 * 2G = 80);
+//   * acc (d x columns) += Xtile^T . R with FP64 tensor-core MMAs (SASS DMMA; tcgen05 has no FP64 kind).
+// Four chains share every byte of X read from L2 and fill the MMA tile widths that a single chain would pad
+// (z/w: 2 of 8 columns, a rate request: 1 of 8).  X (80 MB at C4 size) stays resident in the 126 MB L2.
 #include "common.cuh"
 #include "philox.cuh"
 
 namespace pdmpflux {
 
 constexpr int kLrThreads = 128;
-constexpr int kLrRows = 32;    // rows of X per tile (two tiles in flight per CTA, three CTAs per SM at d = 100)
-constexpr int kLrMaxG = 12;    // 2G <= 24 residual columns = 3 n-tiles
+constexpr int kLrChains = 4;   // chains per CTA = warps per CTA
+constexpr int kLrRows = 32;    // rows of X per tile
+constexpr int kLrMaxG = 12;    // grid_size limit: 2G <= 24 columns per chain
+constexpr int kLrMaxNt = 8;    // n-tiles (of 8 residual columns) one pass can carry: requests beyond wait a round
+constexpr int kLrMaxCols = 8 * kLrMaxNt;
+constexpr int kLrNcs = 68;     // residual-column stride in shared memory (== 4 mod 16: conflict-free B fragments)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -55,56 +69,61 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
 }
 
 struct LrShared {  // offsets (in doubles) into dynamic shared memory
-    int bar, x, v, xv, Xt, ybuf, rs, acc, z, w, lam, box, cum, red, ncs, tile, total;
+    int bar, Xt, rs, ybuf, xv, zw, lam, box, cum, sched, tile, acc_stride, total;
 };
-__host__ __device__ inline LrShared lr_layout(int d, int G) {
+// request schedule of one pass (shared memory, written by the chain warps, read by everybody)
+struct LrSched {
+    int n_entries;                 // (chain, time) pairs to evaluate
+    int n_cols;                    // packed residual columns
+    int col0[kLrChains];           // first column of chain c
+    int want[kLrChains];           // times chain c asks for (0: none, 1: rate, G: bound)
+    int nt[kLrChains];             // times granted to chain c this pass (0 when it has to wait for the next one)
+    int ent_chain[kLrChains * kLrMaxG];
+    int ent_col_r[kLrChains * kLrMaxG];
+    int ent_col_s[kLrChains * kLrMaxG];  // -1: no Hessian column
+    double ent_time[kLrChains * kLrMaxG];
+};
+__host__ __device__ inline LrShared lr_layout(int d) {
     LrShared L;
     const int dp = (d + 7) / 8 * 8;
-    const int dm = dp + 8;  // accumulator rows (m-tiles of 8, +1 spare)
-    // residual-column stride: >= 2G and == 4 (mod 16) so the B fragments (4 rows x 8 columns) hit 32 distinct banks
-    int ncs = 4;
-    while (ncs < 2 * G) ncs += 16;
-    L.ncs = ncs;
-    L.tile = kLrRows * d + 32;                 // one X tile, rows contiguous (+ slack for fragment over-reads)
+    L.tile = kLrRows * d + 32;                  // one X tile, rows contiguous (+ slack for fragment over-reads)
+    L.acc_stride = kLrMaxCols;
     int o = 0;
     L.bar = o; o += 2;                          // two mbarriers (8 bytes each)
     L.Xt = o; o += 2 * L.tile;                  // double-buffered X tiles (16-byte aligned: tile is even)
+    L.rs = o; o += kLrRows * kLrNcs + 32;       // residual columns
+    // after a pass the accumulators (dp+8 rows x kLrMaxCols) overlay [Xt ring | rs]; make sure they fit
+    const int need = (dp + 8) * kLrMaxCols;
+    if (o - L.Xt < need) o = L.Xt + need;
     L.ybuf = o; o += 2 * kLrRows;
-    L.x = o; o += dp;
-    L.v = o; o += dp;
-    L.xv = o; o += (dp + 4) * 8;                // [k][8]: (x_k, v_k, 0...) B operand of the z/w product
-    L.rs = o; o += kLrRows * ncs + 32;          // residual columns
-    L.acc = o; o += dm * 24;                    // X^T R accumulators [i][24]
-    L.z = o; o += kLrRows;
-    L.w = o; o += kLrRows;
-    L.lam = o; o += dp;
-    L.box = o; o += kLrMaxG + 4;
-    L.cum = o; o += kLrMaxG + 4;
-    L.red = o; o += 64;
+    L.xv = o; o += (dp + 4) * 8;                // [k][8]: columns (2c, 2c+1) = (x, v) of chain c -- state AND B operand
+    L.zw = o; o += kLrRows * 8;                 // [row][8]: (z, w) of chain c in columns (2c, 2c+1)
+    L.lam = o; o += kLrChains * dp;
+    L.box = o; o += kLrChains * 16;
+    L.cum = o; o += kLrChains * 16;
+    L.sched = o; o += (int)((sizeof(LrSched) + 7) / 8);
     L.total = o;
     return L;
 }
-size_t logreg_smem_bytes(int d, int G) { return sizeof(double) * (size_t)lr_layout(d, G).total; }
+size_t logreg_smem_bytes(int d, int G) { (void)G; return sizeof(double) * (size_t)lr_layout(d).total; }
 
-// One pass over all rows of X: acc[i][c] = sum_r X[r][i] * R[r][c] for nt times tt[0..nt) (c = k: sigma - y,
-// c = nt + k: sigma' * w when want_h).  All threads of the CTA participate.  X tiles and y arrive by TMA bulk copies
-// into a two-deep ring; `phase` carries the mbarrier parities across calls.
-__device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, const double* tt, int nt, bool want_h,
-                        uint32_t (&phase)[2]) {
+// One pass over all rows of X serving every posted request:
+//   acc[i][col] = sum_r X[r][i] * R[r][col]   (stored to shared memory, row stride L.acc_stride, overlaying the tile ring)
+template <int NT>
+__device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, uint32_t (&phase)[2]) {
     const int d = p.d, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int64_t n = p.pot.n;
-    const int ncs = L.ncs;
-    const int ncols = want_h ? 2 * nt : nt;
-    const int n_nt = (ncols + 7) / 8;                // n-tiles of the main product
-    const int n_mt = (d + 7) / 8;                    // m-tiles (coordinates)
+    const LrSched* S = reinterpret_cast<const LrSched*>(sm + L.sched);
+    const int n_mt = (d + 7) / 8;                    // m-tiles (coordinates), <= 16
     const int kz = (d + 3) / 4;                      // k-steps of the z/w product
+    const int n_ent = S->n_entries;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
-    double acc[4][3][2];                             // up to 4 m-tiles per warp x 3 n-tiles
+    double acc[4][NT][2];                            // up to 4 m-tiles per warp x NT n-tiles
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 3; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     const int64_t ntiles = (n + kLrRows - 1) / kLrRows;
     auto issue = [&](int64_t tile) {  // thread 0: TMA the tile's rows of X and y into ring slot tile & 1
@@ -116,7 +135,10 @@ __device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, co
         if (xb) bulk_load(sm + L.Xt + slot * L.tile, p.pot.vec + r0 * d, xb, &bar[slot]);
         if (yb) bulk_load(sm + L.ybuf + slot * kLrRows, p.pot.vec2 + r0, yb, &bar[slot]);
     };
-    __syncthreads();  // the ring is free (previous pass fully consumed)
+    // The accumulators of the previous pass overlaid the ring: every warp is done with them (caller's barrier), but the
+    // overlay was written through the generic proxy, so order it before the TMA (async proxy) refills the ring.
+    fence_async_smem();
+    __syncthreads();
     if (tid == 0) issue(0);
     for (int64_t tile = 0; tile < ntiles; ++tile) {
         const int slot = (int)(tile & 1);
@@ -132,7 +154,7 @@ __device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, co
             if (rows & 1) ys[rows - 1] = __ldg(p.pot.vec2 + r0 + rows - 1);
         }
         if ((rows & 1) || ((rows * d) & 1)) __syncthreads();
-        // ---- z = X x, w = X v for the tile: DMMA with B = [x v 0 ...] (k x 8); one m-tile (8 rows) per warp ----
+        // ---- (z, w) of the four chains for the tile: DMMA with B = [x1 v1 .. x4 v4] (k x 8); 8 rows per warp ----
         {
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: halves the dependent MMA chain
             const double* arow = Xs + (warp * 8 + gid) * d + tig;
@@ -143,83 +165,91 @@ __device__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, co
                 dmma(e0, e1, arow[4 * ks + 4], bcol[32 * ks + 32]);
             }
             if (ks < kz) dmma(c0, c1, arow[4 * ks], bcol[32 * ks]);
-            if (tig == 0) { sm[L.z + warp * 8 + gid] = c0 + e0; sm[L.w + warp * 8 + gid] = c1 + e1; }
+            double* zr = sm + L.zw + (warp * 8 + gid) * 8 + 2 * tig;  // C[row][2 tig], C[row][2 tig + 1] = (z, w) of chain tig
+            zr[0] = c0 + e0;
+            zr[1] = c1 + e1;
         }
         __syncthreads();
-        // ---- residual columns: thread -> (row, quarter of the times) ----
+        // ---- residual columns: thread -> (row, every 4th schedule entry) ----
         {
-            const int row = tid & (kLrRows - 1), part = tid / kLrRows;  // 4 parts
-            const double z = sm[L.z + row], w = sm[L.w + row], yy = ys[row];
+            const int row = tid & (kLrRows - 1), part = tid / kLrRows;
             const bool live = row < rows;
-            for (int k = part; k < nt; k += kLrThreads / kLrRows) {
-                const double eta = z + tt[k] * w;
+            const double yy = ys[row];
+            for (int e = part; e < n_ent; e += kLrThreads / kLrRows) {
+                const int ce = S->ent_chain[e];
+                const double z = sm[L.zw + row * 8 + 2 * ce], w = sm[L.zw + row * 8 + 2 * ce + 1];
+                const double eta = z + S->ent_time[e] * w;
                 const double sg = 1.0 / (1.0 + exp(-eta));
-                sm[L.rs + row * ncs + k] = live ? sg - yy : 0.0;
-                if (want_h) sm[L.rs + row * ncs + nt + k] = live ? sg * (1.0 - sg) * w : 0.0;
+                sm[L.rs + row * kLrNcs + S->ent_col_r[e]] = live ? sg - yy : 0.0;
+                const int cs = S->ent_col_s[e];
+                if (cs >= 0) sm[L.rs + row * kLrNcs + cs] = live ? sg * (1.0 - sg) * w : 0.0;
             }
         }
         __syncthreads();
         // ---- acc += Xtile^T . R : A[m][k] = Xt[row0 + k][i0 + m], B[k][n] = R[row0 + k][n0 + n] ----
+        {
+            const double* ap = Xs + tig * d + warp * 8 + gid;  // m-tiles warp, warp + 4, ... (the last may not exist)
+            const double* bp = sm + L.rs + tig * kLrNcs + gid;
+            const int n_a = (n_mt - warp + 3) >> 2;  // m-tiles of this warp
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int mt = warp + 4 * a;
-            if (mt < n_mt) {
-                const double* ap = Xs + tig * d + mt * 8 + gid;
-                const double* bp = sm + L.rs + tig * ncs + gid;
+            for (int ks = 0; ks < kLrRows / 4; ++ks) {
+                double bv[NT];
 #pragma unroll
-                for (int ks = 0; ks < kLrRows / 4; ++ks) {
-                    const double av = ap[4 * ks * d];
+                for (int b = 0; b < NT; ++b) bv[b] = bp[4 * ks * kLrNcs + 8 * b];
 #pragma unroll
-                    for (int b = 0; b < 3; ++b)
-                        if (b < n_nt) dmma(acc[a][b][0], acc[a][b][1], av, bp[4 * ks * ncs + 8 * b]);
-                }
+                for (int a = 0; a < 4; ++a)
+                    if (a < n_a) {
+                        const double av = ap[4 * ks * d + 32 * a];
+#pragma unroll
+                        for (int b = 0; b < NT; ++b) dmma(acc[a][b][0], acc[a][b][1], av, bv[b]);
+                    }
             }
         }
-        __syncthreads();  // tile consumed: its ring slot may be refilled, z / w / rs may be overwritten
+        __syncthreads();  // tile consumed: its ring slot may be refilled, zw / rs may be overwritten
     }
-    // ---- accumulator fragments -> shared memory acc[i][c] ----
+    // ---- accumulator fragments -> shared memory acc[i][col], overlaying the (now idle) tile ring ----
+    double* A = sm + L.Xt;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int mt = warp + 4 * a;
         if (mt < n_mt) {
 #pragma unroll
-            for (int b = 0; b < 3; ++b)
-                if (b < n_nt) {
-                    const int i = mt * 8 + gid, c = 8 * b + 2 * tig;
-                    sm[L.acc + i * 24 + c] = acc[a][b][0];
-                    sm[L.acc + i * 24 + c + 1] = acc[a][b][1];
-                }
+            for (int b = 0; b < NT; ++b) {
+                const int i = mt * 8 + gid, c = 8 * b + 2 * tig;
+                A[i * L.acc_stride + c] = acc[a][b][0];
+                A[i * L.acc_stride + c + 1] = acc[a][b][1];
+            }
         }
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ double lr_block_sum(double v, double* red) {  // all threads get the sum
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < kLrThreads / 32; ++k) s += red[k];
-    return s;
+    return v;
 }
 
 __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_constant__ KernelParams p) {
     extern __shared__ __align__(128) double sm[];
-    const int d = p.d, G = p.G, tid = threadIdx.x;
-    const int64_t c = blockIdx.x;
-    const LrShared L = lr_layout(d, G);
+    const int d = p.d, G = p.G, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const LrShared L = lr_layout(d);
+    const int dp = (d + 7) / 8 * 8;
     const double inv_s2 = p.pot.inv_s2;
+    LrSched* S = reinterpret_cast<LrSched*>(sm + L.sched);
+    const int64_t c_raw = (int64_t)blockIdx.x * kLrChains + w;  // warp w runs chain c
+    const bool valid = c_raw < p.n_chains;
+    const int64_t c = valid ? c_raw : 0;
 
-    // ---- PDMPState ----
-    for (int i = tid; i < (d + 7) / 8 * 8; i += kLrThreads) {
-        sm[L.x + i] = i < d ? p.sx[c * d + i] : 0.0;
-        sm[L.v + i] = i < d ? p.sv[c * d + i] : 0.0;
-    }
-    for (int e = tid; e < 2 * L.tile; e += kLrThreads) sm[L.Xt + e] = 0.0;            // incl. the slack fragment over-reads touch
-    for (int e = tid; e < kLrRows * L.ncs + 32; e += kLrThreads) sm[L.rs + e] = 0.0;
+    // ---- shared state: xv[k][8] holds (x, v) of chain w in columns (2w, 2w+1); it is also the z/w B operand ----
+    for (int e = tid; e < (dp + 4) * 8; e += kLrThreads) sm[L.xv + e] = 0.0;
+    for (int e = tid; e < 2 * L.tile + kLrRows * kLrNcs + 32; e += kLrThreads) sm[L.Xt + e] = 0.0;  // ring, slack, rs
+    __syncthreads();
+    if (valid)
+        for (int i = lane; i < d; i += 32) {
+            sm[L.xv + i * 8 + 2 * w] = p.sx[c * d + i];
+            sm[L.xv + i * 8 + 2 * w + 1] = p.sv[c * d + i];
+        }
     fence_async_smem();  // order these generic-proxy writes before the TMA (async-proxy) writes into the same buffers
     uint32_t phase[2] = {0u, 0u};
     if (tid == 0) {
@@ -229,13 +259,15 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
+    // ---- PDMPState scalars of chain w (warp-uniform registers) ----
     double t = p.st[c], horizon = p.shorizon[c], ar = p.sar[c];
-    int status = p.status[c];
+    int status = valid ? p.status[c] : 0;
     int64_t n_builds = p.counters[2 * c], n_rates = p.counters[2 * c + 1];
     DrawKey key;
     const uint64_t gchain = (uint64_t)(p.chain_offset + c);
     key.k0 = (uint32_t)p.seed; key.k1 = (uint32_t)(p.seed >> 32);
     key.chain_lo = (uint32_t)gchain; key.chain_hi8 = (uint32_t)(gchain >> 32) << 8;
+    key.event = 0;
     uint32_t sE = 0, sU = 0;
     int64_t pE = p.tape_pos[3 * c], pU = p.tape_pos[3 * c + 1];
     const double* tE = p.tE + c * p.nE;
@@ -251,16 +283,22 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         if (pU >= p.nU) { exhausted = true; return 0.5; }
         return __ldg(tU + pU++);
     };
-    __syncthreads();
+    auto xr = [&](int i) -> double& { return sm[L.xv + i * 8 + 2 * w]; };
+    auto vr = [&](int i) -> double& { return sm[L.xv + i * 8 + 2 * w + 1]; };
+    double* lam = sm + L.lam + w * dp;
+    double* box = sm + L.box + w * 16;
+    double* cum = sm + L.cum + w * 16;
 
-    auto record = [&](int64_t col, int eb, int rej, int hh, const double* eva) {  // Composites.jl:239-260
+    int eb = 0, rej = 0, hh = 0;
+    double eva[5] = {0, 0, 0, 0, 0};
+    auto record = [&](int64_t col) {  // Composites.jl:239-260 (one warp writes its chain's row)
         const int64_t o = c * p.ld_cols + col;
         const int64_t orow = c * p.ld_rows + (col - p.col0) + p.col0_rows;
-        for (int i = tid; i < d; i += kLrThreads) {
-            if (p.X) p.X[orow * d + i] = sm[L.x + i];
-            if (p.V) p.V[orow * d + i] = sm[L.v + i];
+        for (int i = lane; i < d; i += 32) {
+            if (p.X) p.X[orow * d + i] = xr(i);
+            if (p.V) p.V[orow * d + i] = vr(i);
         }
-        if (tid == 0) {
+        if (lane == 0) {
             if (p.T) p.T[o] = t;
             if (p.H) p.H[o] = horizon;
             if (p.AR) p.AR[o] = ar;
@@ -272,184 +310,242 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
             if ((!p.sparse_cols || hh != 0) && p.HH) p.HH[o] = hh;
         }
     };
+    __syncthreads();
 
     if (p.n_events == 0) {
-        const double zero5[5] = {0, 0, 0, 0, 0};
-        record(p.col0, 0, 0, 0, zero5);
-        if (tid == 0) p.ncols[c] += 1;
+        if (valid) {
+            record(p.col0);
+            if (lane == 0) p.ncols[c] += 1;
+        }
         return;
     }
 
-    // grid nodes, UpperBound.jl:204 (same construction as chain.cuh:make_grid)
+    // grid nodes of the current bound, UpperBound.jl:204 (same construction as chain.cuh:make_grid)
     double gc = 0, grem = 0, gh = 0, step = 0;
     auto grid_t = [&](int k) -> double {
         if (k >= G - 1) return gh;
         const double kk = (double)k;
         return fma(kk, gc, kk * grem);
     };
-    // upper_bound_grid_vect, UpperBound.jl:203-247 (analytic derivative): fills box / cum in shared memory
-    auto build_bound = [&](double h) {
-        ++n_builds;
-        const double m = (double)(G - 1);
-        gc = h / m; grem = fma(-gc, m, h) * p.inv_gm1; gh = h;
-        step = grid_t(1);
-        // B operand of the z/w product: [k][8] = (x_k, v_k, 0, ...)
-        for (int e = tid; e < ((d + 7) / 8 * 8 + 4) * 8; e += kLrThreads) {
-            const int k = e >> 3, col = e & 7;
-            sm[L.xv + e] = (k < d && col == 0) ? sm[L.x + k] : ((k < d && col == 1) ? sm[L.v + k] : 0.0);
-        }
-        double tt[kLrMaxG];
-#pragma unroll
-        for (int k = 0; k < kLrMaxG; ++k) tt[k] = grid_t(min(k, G - 1));
-        lr_pass(p, sm, L, tt, G, true, phase);
-        // per-coordinate cells (thread i = coordinate i), QUIRK-preserving tangent formula (UpperBound.jl:229-241)
-        double bpart[kLrMaxG];
-#pragma unroll
-        for (int k = 0; k < kLrMaxG; ++k) bpart[k] = 0.0;
-        for (int i = tid; i < d; i += kLrThreads) {
-            const double xi = sm[L.x + i], vi = sm[L.v + i];
-            double vl = 0, gl = 0;
-#pragma unroll
-            for (int k = 0; k < kLrMaxG; ++k)
-                if (k < G) {
-                    const double g = sm[L.acc + i * 24 + k] + (xi + tt[k] * vi) * inv_s2;
-                    const double hv = sm[L.acc + i * 24 + G + k] + vi * inv_s2;
-                    double val = g * vi, dval = hv * vi;
-                    if (!p.signed_bound) { dval = (0.0 > val) ? 0.0 : dval; val = (val > 0.0 ? val : 0.0); }
-                    if (k > 0) {
-                        double pos = (vl - val + dval * tt[k] - gl * tt[k - 1]) / (dval - gl);
-                        if (pos != pos) pos = 0.0;
-                        pos = fmin(fmax(pos, 0.0), step);
-                        const double inter = vl + gl * pos;
-                        bpart[k - 1] += fmax(fmax(fmax(vl, val), inter), 0.0);
-                    }
-                    vl = val; gl = dval;
-                }
-        }
-        double cs = 0.0;
-        if (tid == 0) sm[L.cum] = 0.0;
-        for (int k = 0; k < G - 1; ++k) {
-            const double b = lr_block_sum(bpart[k], sm + L.red);
-            cs += b;
-            if (tid == 0) { sm[L.box + k] = b; sm[L.cum + k + 1] = cs * step; }
-        }
-        __syncthreads();
-    };
     auto next_event = [&](double e, double& tp_out, double& lb_out) {  // UpperBound.jl:264-273
         int idx = 0;
-        while (idx < G && sm[L.cum + idx] < e) ++idx;
-        if (idx >= G) { tp_out = CUDART_INF; lb_out = sm[L.box + G - 2]; return; }
-        if (idx == 0) { tp_out = CUDART_NAN; lb_out = sm[L.box]; return; }
-        tp_out = grid_t(idx - 1) + (e - sm[L.cum + idx - 1]) / (sm[L.cum + idx] - sm[L.cum + idx - 1]) * step;
-        lb_out = sm[L.box + idx - 1];
-    };
-    // sampler.rate at tp (ZigZagSamplers.jl:83-86); leaves lambda_i = max(0, g_i v_i) in shared memory for the jump.
-    // Uses the xv operand staged by the last build_bound (x, v unchanged since).
-    auto rate_at = [&](double tp) -> double {
-        double tt1[1] = {tp};
-        lr_pass(p, sm, L, tt1, 1, false, phase);
-        double part = 0.0;
-        for (int i = tid; i < d; i += kLrThreads) {
-            const double vi = sm[L.v + i];
-            const double g = sm[L.acc + i * 24] + (sm[L.x + i] + tp * vi) * inv_s2;
-            const double y = g * vi;
-            const double lam = (y > 0.0 ? y : 0.0);
-            sm[L.lam + i] = lam;
-            part += lam;
-        }
-        return lr_block_sum(part, sm + L.red);
+        for (int k = 0; k < G; ++k) idx += (cum[k] < e) ? 1 : 0;  // searchsortedfirst on a non-decreasing vector
+        if (idx >= G) { tp_out = CUDART_INF; lb_out = box[G - 2]; return; }
+        if (idx == 0) { tp_out = CUDART_NAN; lb_out = box[0]; return; }
+        tp_out = grid_t(idx - 1) + (e - cum[idx - 1]) / (cum[idx] - cum[idx - 1]) * step;
+        lb_out = box[idx - 1];
     };
     auto flow = [&](double tt) {  // ZigZagSamplers.jl:80
-        for (int i = tid; i < d; i += kLrThreads) sm[L.x + i] += sm[L.v + i] * tt;
-        __syncthreads();
+        for (int i = lane; i < d; i += 32) xr(i) += vr(i) * tt;
+        __syncwarp();
     };
 
-    int64_t n_rec = 0;
+    // ---- flattened thinning state machine of chain w (same structure as chain.cuh:run_events) ----
+    int64_t ev = 0;
+    int steps = 0;
+    double ts = 0.0, tp = 0.0, lambda_bar = 0.0, exp_rv = 0.0, hbound = 0.0;
+    bool need_build = true, half = false;
     if (p.use_t_stop && status == 0 && !(t < p.t_stop)) status = PDMPFLUX_CHAIN_DONE;
-    if (status == 0) {
-        for (int64_t ev = 0; ev < p.n_events; ++ev) {
-            key.event = (uint32_t)(p.event0 + ev + 1);
-            sE = sU = 0;
-            int eb = 0, rej = 0, hh = 0, steps = 0;
-            double eva[5] = {0, 0, 0, 0, 0};
-            double ts = 0.0, tp = 0.0, lambda_bar = 0.0, exp_rv = 0.0;
-            bool accept = false;
-            while (!accept && status == 0) {  // get_event_state!, SamplingLoopInplace.jl:27-39
-                if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; break; }
-                build_bound(horizon);        // one_step_of_thinning!, :65-85
-                double e = rand_exp();
-                next_event(e, tp, lambda_bar);
-                exp_rv = e;
-                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; break; }
-                if (tp > horizon) {          // move_to_horizon!, :87-101
-                    flow(horizon);
-                    ts += horizon; hh += 1;
-                    horizon = p.adaptive ? horizon * 1.01 : horizon;
-                    continue;
+    bool live = valid && status == 0;
+    key.event = (uint32_t)(p.event0 + 1);
+    enum { REQ_NONE = 0, REQ_BOUND = 1, REQ_RATE = 2 };
+    unsigned round = 0;
+
+    while (true) {
+        // ---- 1. every chain posts its request ----
+        int req = REQ_NONE;
+        if (live) {
+            if (need_build) {
+                if (!half && steps >= p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; live = false; }
+                else {
+                    hbound = half ? horizon / 2 : horizon;  // erroneous_acceptance_rate! rebuilds over half the horizon
+                    const double m = (double)(G - 1);
+                    gc = hbound / m; grem = fma(-gc, m, hbound) * p.inv_gm1; gh = hbound;
+                    step = grid_t(1);
+                    req = REQ_BOUND;
                 }
-                while (tp < horizon && !accept && status == 0) {  // moves_until_horizon!, :103-111
-                    ++n_rates;
-                    const double lt = rate_at(tp);   // ac_step!, :113-129
-                    ar = lt / lambda_bar;
-                    if (ar > 1.0) {                  // erroneous_acceptance_rate!, :131-151
-                        const double h2 = horizon / 2;
-                        build_bound(h2);
-                        e = rand_exp();
-                        next_event(e, tp, lambda_bar);
-                        exp_rv = e;
-                        horizon = p.adaptive ? h2 : horizon;
-                        eb += 1;
-                        eva[eb % 5] = ar;
-                    } else if (rand_uniform() < ar) {  // if_accept!, :170-186
-                        if (p.use_t_stop && t + tp + ts > p.t_stop) {  // time-horizon variant, src/sample.jl:385-420
-                            flow(p.t_stop - (t + ts));
-                            t = p.t_stop;
-                            ar = 0.0; eb = 0; rej = 0; hh = 0;
-                            for (int k = 0; k < 5; ++k) eva[k] = 0.0;
-                            status = PDMPFLUX_CHAIN_DONE;
-                            accept = true;
-                            break;
-                        }
-                        const double uS = rand_uniform() * lt;  // categorical draw against the rates just computed
-                        flow(tp);
-                        if (tid == 0) {                          // first index with cumulative lambda > u S
-                            double cp = 0.0;
-                            int m = d - 1;
-                            for (int i = 0; i < d; ++i) { cp += sm[L.lam + i]; if (cp > uS) { m = i; break; } }
-                            sm[L.v + m] = -sm[L.v + m];
-                        }
-                        __syncthreads();
-                        t = t + tp + ts;
-                        ts = 0.0; tp = 0.0;
-                        accept = true;
-                    } else {                           // if_reject!, :188-203
-                        const double e3 = exp_rv + rand_exp();
-                        next_event(e3, tp, lambda_bar);
-                        horizon = p.adaptive ? horizon / 1.04 : horizon;
-                        exp_rv = e3;
-                        rej += 1;
-                        if (tp > horizon) { flow(horizon); ts += horizon; hh += 1; }  // move_to_horizon2!, :205-217
-                    }
-                    if (exhausted) status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED;
-                }
-            }
-            if (status != 0 && status != PDMPFLUX_CHAIN_DONE) break;
-            record(p.col0 + ev, eb, rej, hh, eva);
-            ++n_rec;
-            if (status == PDMPFLUX_CHAIN_DONE) break;
-            if (p.use_t_stop && !(t < p.t_stop)) { status = PDMPFLUX_CHAIN_DONE; break; }
+            } else if (!(tp < horizon)) need_build = true;  // moves_until_horizon! falls through: fresh outer step next round
+            else req = REQ_RATE;
         }
+        if (lane == 0) S->want[w] = req == REQ_BOUND ? G : (req == REQ_RATE ? 1 : 0);
+        __syncthreads();
+        if (tid == 0) {  // pack the columns: a rate request takes 1 column, a bound G residual + G Hessian columns.
+            // A pass carries kLrMaxCols columns; a request that does not fit waits for the next pass (the chain's state
+            // is untouched, it simply asks again).  The chain served first rotates so nobody starves.
+            int col = 0, ne = 0;
+            for (int j = 0; j < kLrChains; ++j) {
+                const int cc = (j + (int)(round & (kLrChains - 1))) & (kLrChains - 1);
+                const int wn = S->want[cc], wc = (wn == 1) ? 1 : 2 * wn;
+                const bool fits = col + wc <= kLrMaxCols;
+                S->col0[cc] = col;
+                S->nt[cc] = fits ? wn : 0;
+                col += fits ? wc : 0;
+                ne += fits ? wn : 0;
+            }
+            S->n_cols = col;
+            S->n_entries = ne;
+        }
+        __syncthreads();
+        if (S->nt[w] == 0) req = REQ_NONE;  // nothing asked, or deferred to the next pass
+        if (req == REQ_BOUND) { ++n_builds; if (!half) ++steps; }
+        if (req == REQ_RATE) ++n_rates;
+        if (lane == 0 && req != REQ_NONE) {  // this chain's (time, column) entries, after those of the chains before it
+            int e0 = 0;
+            for (int cc = 0; cc < w; ++cc) e0 += S->nt[cc];  // any fixed order of the entries will do
+            const int nt = S->nt[w], col0 = S->col0[w];
+            for (int k = 0; k < nt; ++k) {
+                S->ent_chain[e0 + k] = w;
+                S->ent_time[e0 + k] = req == REQ_BOUND ? grid_t(k) : tp;
+                S->ent_col_r[e0 + k] = col0 + k;
+                S->ent_col_s[e0 + k] = req == REQ_BOUND ? col0 + nt + k : -1;
+            }
+        }
+        // the CTA goes on while any chain has work left (a request, or a pending fall-through transition)
+        const int any = __syncthreads_or(live ? 1 : 0);
+        if (!any) break;
+        ++round;
+        if (S->n_cols == 0) continue;  // only fall-through transitions this round
+
+        // ---- 2. one pass over X for all requests (specialised on the number of 8-column tiles) ----
+        switch ((S->n_cols + 7) >> 3) {
+            case 1: lr_pass<1>(p, sm, L, phase); break;
+            case 2: lr_pass<2>(p, sm, L, phase); break;
+            case 3: lr_pass<3>(p, sm, L, phase); break;
+            case 4: lr_pass<4>(p, sm, L, phase); break;
+            case 5: lr_pass<5>(p, sm, L, phase); break;
+            case 6: lr_pass<6>(p, sm, L, phase); break;
+            case 7: lr_pass<7>(p, sm, L, phase); break;
+            default: lr_pass<8>(p, sm, L, phase); break;
+        }
+        const double* A = sm + L.Xt;
+        const int col0 = S->col0[w];
+
+        // ---- 3. every chain consumes its columns ----
+        if (req == REQ_BOUND) {
+            // upper_bound_grid_vect, UpperBound.jl:203-247 (analytic derivative), cells of this lane's coordinates
+            double bpart[kLrMaxG];
+#pragma unroll
+            for (int k = 0; k < kLrMaxG; ++k) bpart[k] = 0.0;
+            for (int i = lane; i < d; i += 32) {
+                const double xi = xr(i), vi = vr(i);
+                double vl = 0, gl = 0, tl_ = 0;
+#pragma unroll
+                for (int k = 0; k < kLrMaxG; ++k)
+                    if (k < G) {
+                        const double tk = grid_t(k);
+                        const double g = A[i * L.acc_stride + col0 + k] + (xi + tk * vi) * inv_s2;
+                        const double hv = A[i * L.acc_stride + col0 + G + k] + vi * inv_s2;
+                        double val = g * vi, dval = hv * vi;
+                        if (!p.signed_bound) { dval = (0.0 > val) ? 0.0 : dval; val = (val > 0.0 ? val : 0.0); }
+                        if (k > 0) {  // QUIRK-preserving tangent formula (UpperBound.jl:229-241)
+                            double pos = (vl - val + dval * tk - gl * tl_) / (dval - gl);
+                            if (pos != pos) pos = 0.0;
+                            pos = fmin(fmax(pos, 0.0), step);
+                            const double inter = vl + gl * pos;
+                            bpart[k - 1] += fmax(fmax(fmax(vl, val), inter), 0.0);
+                        }
+                        vl = val; gl = dval; tl_ = tk;
+                    }
+            }
+            double cs = 0.0;
+            if (lane == 0) cum[0] = 0.0;
+#pragma unroll
+            for (int k = 0; k < kLrMaxG; ++k)
+                if (k < G - 1) {
+                    const double b = warp_sum(bpart[k]);
+                    cs += b;
+                    if (lane == 0) { box[k] = b; cum[k + 1] = cs * step; }
+                }
+            __syncwarp();
+            const double e = rand_exp();
+            next_event(e, tp, lambda_bar);
+            exp_rv = e;
+            if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; }
+            else if (half) {  // erroneous_acceptance_rate!, SamplingLoopInplace.jl:131-151
+                horizon = p.adaptive ? hbound : horizon;
+                eb += 1;
+                eva[eb % 5] = ar;
+                half = false;
+                need_build = false;
+            } else if (tp > horizon) {  // move_to_horizon!, :87-101
+                flow(horizon);
+                ts += horizon; hh += 1;
+                horizon = p.adaptive ? horizon * 1.01 : horizon;
+            } else need_build = false;
+        } else if (req == REQ_RATE) {
+            // sampler.rate at tp (ZigZagSamplers.jl:83-86); lambda_i are also the categorical weights of the flip
+            double part = 0.0;
+            for (int i = lane; i < d; i += 32) {
+                const double vi = vr(i);
+                const double g = A[i * L.acc_stride + col0] + (xr(i) + tp * vi) * inv_s2;
+                const double y = g * vi;
+                const double l = (y > 0.0 ? y : 0.0);
+                lam[i] = l;
+                part += l;
+            }
+            const double lt = warp_sum(part);
+            __syncwarp();
+            ar = lt / lambda_bar;  // ac_step!, :113-129
+            if (ar > 1.0) { need_build = true; half = true; }
+            else if (rand_uniform() < ar) {  // if_accept!, :170-186
+                if (p.use_t_stop && t + tp + ts > p.t_stop) {  // time-horizon variant, src/sample.jl:385-420
+                    flow(p.t_stop - (t + ts));
+                    t = p.t_stop;
+                    ar = 0.0; eb = 0; rej = 0; hh = 0;
+                    for (int k = 0; k < 5; ++k) eva[k] = 0.0;
+                    record(p.col0 + ev);
+                    ++ev;
+                    status = PDMPFLUX_CHAIN_DONE;
+                    live = false;
+                } else {
+                    const double uS = rand_uniform() * lt;  // categorical draw against the rates just computed
+                    flow(tp);
+                    if (lane == 0) {                         // first index with cumulative lambda > u S, else the last
+                        double cp = 0.0;
+                        int m = d - 1;
+                        for (int i = 0; i < d; ++i) { cp += lam[i]; if (cp > uS) { m = i; break; } }
+                        vr(m) = -vr(m);
+                    }
+                    __syncwarp();
+                    t = t + tp + ts;
+                    ts = 0.0; tp = 0.0;
+                    if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; }
+                    else {
+                        record(p.col0 + ev);
+                        ++ev;
+                        steps = 0;
+                        eb = 0; rej = 0; hh = 0;
+                        for (int k = 0; k < 5; ++k) eva[k] = 0.0;
+                        key.event = (uint32_t)(p.event0 + ev + 1);
+                        sE = sU = 0;
+                        need_build = true;
+                        live = ev < p.n_events;
+                        if (p.use_t_stop && !(t < p.t_stop)) { status = PDMPFLUX_CHAIN_DONE; live = false; }
+                    }
+                }
+            } else {  // if_reject!, :188-203
+                const double e3 = exp_rv + rand_exp();
+                next_event(e3, tp, lambda_bar);
+                horizon = p.adaptive ? horizon / 1.04 : horizon;
+                exp_rv = e3;
+                rej += 1;
+                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; }
+                else if (tp > horizon) { flow(horizon); ts += horizon; hh += 1; need_build = true; }  // move_to_horizon2!
+            }
+        }
+        __syncthreads();  // accumulators consumed before the next pass reuses the ring
     }
-    __syncthreads();
-    for (int i = tid; i < d; i += kLrThreads) {
-        p.sx[c * d + i] = sm[L.x + i];
-        p.sv[c * d + i] = sm[L.v + i];
+
+    if (!valid) return;
+    for (int i = lane; i < d; i += 32) {
+        p.sx[c * d + i] = xr(i);
+        p.sv[c * d + i] = vr(i);
     }
-    if (tid == 0) {
+    if (lane == 0) {
         p.st[c] = t; p.shorizon[c] = horizon; p.sar[c] = ar; p.status[c] = status;
         p.counters[2 * c] = n_builds; p.counters[2 * c + 1] = n_rates;
         p.tape_pos[3 * c] = pE; p.tape_pos[3 * c + 1] = pU;
-        p.ncols[c] += n_rec;
+        p.ncols[c] += ev;
     }
 }
 
@@ -461,5 +557,6 @@ cudaError_t launch_logreg_zigzag(const KernelParams& p, unsigned grid, size_t sm
     logreg_zigzag_kernel<<<grid, kLrThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
+int logreg_chains_per_block() { return kLrChains; }
 
 }  // namespace pdmpflux

@@ -24,3 +24,9 @@ for i in range(3):
     e0.record(); ch.advance(n_ev, view, 0, st); e1.record(); torch.cuda.synchronize()
     print(f"{cfg} team={team} chains={nch} n_ev={n_ev}: {e0.elapsed_time(e1):.2f} ms  {nch*n_ev/e0.elapsed_time(e1)/1e3:.2f} Mev/s")
 ch.status()
+_, _, cnt = ch.status()
+import numpy as np
+tot = cnt.sum(axis=1)
+g = tot[: nch // 4 * 4].reshape(-1, 4)
+print("per chain (3 launches): builds mean %.2f rates mean %.2f total mean %.2f max %d; max-of-4 mean %.2f; max-of-4 over CTA max %d" % (
+    cnt[:, 0].mean(), cnt[:, 1].mean(), tot.mean(), tot.max(), g.max(axis=1).mean(), g.max(axis=1).max()))
