@@ -73,15 +73,12 @@ struct LrShared {  // offsets (in doubles) into dynamic shared memory
 };
 // request schedule of one pass (shared memory, written by the chain warps, read by everybody)
 struct LrSched {
-    int n_entries;                 // (chain, time) pairs to evaluate
     int n_cols;                    // packed residual columns
     int col0[kLrChains];           // first column of chain c
     int want[kLrChains];           // times chain c asks for (0: none, 1: rate, G: bound)
     int nt[kLrChains];             // times granted to chain c this pass (0 when it has to wait for the next one)
-    int ent_chain[kLrChains * kLrMaxG];
-    int ent_col_r[kLrChains * kLrMaxG];
-    int ent_col_s[kLrChains * kLrMaxG];  // -1: no Hessian column
-    double ent_time[kLrChains * kLrMaxG];
+    double tp[kLrChains];          // rate request: the proposal time
+    double gc[kLrChains], grem[kLrChains], gh[kLrChains];  // bound request: its time grid (see grid_t)
 };
 __host__ __device__ inline LrShared lr_layout(int d) {
     LrShared L;
@@ -117,7 +114,9 @@ __device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const Lr
     const LrSched* S = reinterpret_cast<const LrSched*>(sm + L.sched);
     const int n_mt = (d + 7) / 8;                    // m-tiles (coordinates), <= 16
     const int kz = (d + 3) / 4;                      // k-steps of the z/w product
-    const int n_ent = S->n_entries;
+    // warp -> m-tiles {mrot, mrot + 4, ..}; rotated by CTA parity so that the warp carrying the odd extra tile sits on
+    // a different SM sub-partition in the two co-resident CTAs
+    const int mrot = (warp + 2 * (int)(blockIdx.x & 1)) & 3;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
     double acc[4][NT][2];                            // up to 4 m-tiles per warp x NT n-tiles
 #pragma unroll
@@ -170,27 +169,46 @@ __device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const Lr
             zr[1] = c1 + e1;
         }
         __syncthreads();
-        // ---- residual columns: thread -> (row, every 4th schedule entry) ----
+        // ---- residual columns: warp c evaluates chain c's requested times, lane = row of the tile ----
         {
-            const int row = tid & (kLrRows - 1), part = tid / kLrRows;
-            const bool live = row < rows;
-            const double yy = ys[row];
-            for (int e = part; e < n_ent; e += kLrThreads / kLrRows) {
-                const int ce = S->ent_chain[e];
-                const double z = sm[L.zw + row * 8 + 2 * ce], w = sm[L.zw + row * 8 + 2 * ce + 1];
-                const double eta = z + S->ent_time[e] * w;
-                const double sg = 1.0 / (1.0 + exp(-eta));
-                sm[L.rs + row * kLrNcs + S->ent_col_r[e]] = live ? sg - yy : 0.0;
-                const int cs = S->ent_col_s[e];
-                if (cs >= 0) sm[L.rs + row * kLrNcs + cs] = live ? sg * (1.0 - sg) * w : 0.0;
+            const int nt = S->nt[warp];
+            if (nt) {
+                const bool live = lane < rows;
+                const double z = sm[L.zw + lane * 8 + 2 * warp], w = sm[L.zw + lane * 8 + 2 * warp + 1], yy = ys[lane];
+                double* rp = sm + L.rs + lane * kLrNcs + S->col0[warp];
+                if (nt == 1) {  // rate at the proposal time
+                    const double sg = 1.0 / (1.0 + exp(-(z + S->tp[warp] * w)));
+                    rp[0] = live ? sg - yy : 0.0;
+                } else {        // bound: residual and Hessian-weight columns at the G grid times
+                    const double gc = S->gc[warp], grem = S->grem[warp], gh = S->gh[warp];
+                    if (fabs(z) + fabs(gh * w) < 600.0) {
+                        // eta_k = z + t_k w on a uniform grid: exp(-eta_k) is a geometric progression -- two exps
+                        // per row instead of G (the accumulated rounding, <= G ulp, is far inside the parity tolerance)
+                        double q = exp(-z);
+                        const double rho = exp(-fma(1.0, gc, grem) * w);
+                        for (int k = 0; k < nt; ++k) {
+                            const double sg = 1.0 / (1.0 + q);
+                            rp[k] = live ? sg - yy : 0.0;
+                            rp[nt + k] = live ? q * sg * sg * w : 0.0;  // sigma (1 - sigma) w with 1 - sigma = q sigma
+                            q *= rho;
+                        }
+                    } else {  // extreme logits: evaluate every node on its own
+                        for (int k = 0; k < nt; ++k) {
+                            const double kk = (double)k, tk = (k >= nt - 1) ? gh : fma(kk, gc, kk * grem);
+                            const double sg = 1.0 / (1.0 + exp(-(z + tk * w)));
+                            rp[k] = live ? sg - yy : 0.0;
+                            rp[nt + k] = live ? sg * (1.0 - sg) * w : 0.0;
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
         // ---- acc += Xtile^T . R : A[m][k] = Xt[row0 + k][i0 + m], B[k][n] = R[row0 + k][n0 + n] ----
         {
-            const double* ap = Xs + tig * d + warp * 8 + gid;  // m-tiles warp, warp + 4, ... (the last may not exist)
+            const double* ap = Xs + tig * d + mrot * 8 + gid;  // m-tiles mrot, mrot + 4, ... (the last may not exist)
             const double* bp = sm + L.rs + tig * kLrNcs + gid;
-            const int n_a = (n_mt - warp + 3) >> 2;  // m-tiles of this warp
+            const int n_a = (n_mt - mrot + 3) >> 2;  // m-tiles of this warp
 #pragma unroll
             for (int ks = 0; ks < kLrRows / 4; ++ks) {
                 double bv[NT];
@@ -211,7 +229,7 @@ __device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const Lr
     double* A = sm + L.Xt;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const int mt = warp + 4 * a;
+        const int mt = mrot + 4 * a;
         if (mt < n_mt) {
 #pragma unroll
             for (int b = 0; b < NT; ++b) {
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         if (tid == 0) {  // pack the columns: a rate request takes 1 column, a bound G residual + G Hessian columns.
             // A pass carries kLrMaxCols columns; a request that does not fit waits for the next pass (the chain's state
             // is untouched, it simply asks again).  The chain served first rotates so nobody starves.
-            int col = 0, ne = 0;
+            int col = 0;
             for (int j = 0; j < kLrChains; ++j) {
                 const int cc = (j + (int)(round & (kLrChains - 1))) & (kLrChains - 1);
                 const int wn = S->want[cc], wc = (wn == 1) ? 1 : 2 * wn;
@@ -380,25 +398,16 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
                 S->col0[cc] = col;
                 S->nt[cc] = fits ? wn : 0;
                 col += fits ? wc : 0;
-                ne += fits ? wn : 0;
             }
             S->n_cols = col;
-            S->n_entries = ne;
         }
         __syncthreads();
         if (S->nt[w] == 0) req = REQ_NONE;  // nothing asked, or deferred to the next pass
         if (req == REQ_BOUND) { ++n_builds; if (!half) ++steps; }
         if (req == REQ_RATE) ++n_rates;
-        if (lane == 0 && req != REQ_NONE) {  // this chain's (time, column) entries, after those of the chains before it
-            int e0 = 0;
-            for (int cc = 0; cc < w; ++cc) e0 += S->nt[cc];  // any fixed order of the entries will do
-            const int nt = S->nt[w], col0 = S->col0[w];
-            for (int k = 0; k < nt; ++k) {
-                S->ent_chain[e0 + k] = w;
-                S->ent_time[e0 + k] = req == REQ_BOUND ? grid_t(k) : tp;
-                S->ent_col_r[e0 + k] = col0 + k;
-                S->ent_col_s[e0 + k] = req == REQ_BOUND ? col0 + nt + k : -1;
-            }
+        if (lane == 0 && req != REQ_NONE) {  // the times this chain wants evaluated
+            S->tp[w] = tp;
+            S->gc[w] = gc; S->grem[w] = grem; S->gh[w] = gh;
         }
         // the CTA goes on while any chain has work left (a request, or a pending fall-through transition)
         const int any = __syncthreads_or(live ? 1 : 0);
