@@ -221,6 +221,18 @@ int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_ch
                               const double* X, const double* V, const double* t, double* m1, double* m2,
                               double* T, int32_t on_device, void* cuda_stream);
 
+/* replaces RV_diagnostic(history, U; B) (src/diagnostic.jl:37-75) for a batch of skeletons: rv[c] = sum over B blocks
+ * of (U(x(t_b)) - U(x(t_{b-1})))^2 / t[end], positions by the linear interpolation of _history_position_linear!
+ * (src/diagnostic.jl:23-35) when flow_kind = 0; flow_kind = 1 interpolates with the Boomerang rotation, which is what
+ * the online sample_skeleton_with_diagnostic (src/sample.jl:75-236) accumulates through sampler.flow.  U is the value
+ * plugin of `pot` (Gaussians and banana; LOGREG / GAUSS_DENSE -> PDMPFLUX_ERR_UNSUPPORTED).  X, V: [C][ld_sk][d],
+ * t: [C][ld_sk]; chain c uses its first ncols[c] columns (ncols == NULL: n_sk for all).  B = 0 -> floor(sqrt(n)) like
+ * the reference, B < 0 -> PDMPFLUX_ERR_ARGUMENT (the reference's ArgumentError).  A chain whose t[end] is negative or
+ * not finite gets rv = NaN (the binding raises the reference's ArgumentError). */
+int pdmpflux_rv_diagnostic(pdmpflux_potential_t pot, int flow_kind, int64_t n_sk, int64_t ld_sk, int64_t n_chains,
+                           const int64_t* ncols, int64_t B, const double* X, const double* V, const double* t,
+                           double* rv, int32_t on_device, void* cuda_stream);
+
 /* pinned host memory for the host-buffer (end-to-end) path */
 int pdmpflux_host_alloc(void** ptr, size_t bytes);
 int pdmpflux_host_free(void* ptr);

@@ -128,6 +128,25 @@ function sample_from_skeleton(s::CuPDMP, N::Int, h::PDMPHistory; discard_vt::Boo
     return out
 end
 
+"""
+Replaces `PDMPFlux.RV_diagnostic(history, U; B)` (src/diagnostic.jl:37-75): `U` is the value plugin of the sampler's
+device potential.  `online=true` interpolates with the sampler's flow, i.e. the value
+`sample_skeleton_with_diagnostic` (src/sample.jl:75-236) accumulates.
+"""
+function RV_diagnostic(h::PDMPHistory, s::CuPDMP; B::Int64=0, online::Bool=false)
+    B < 0 && throw(ArgumentError("B must be non-negative. Current value: $B"))
+    n_sk = length(h.t)
+    n_sk == 0 && return 0.0
+    T = h.t[end]
+    (!isfinite(T) || T < 0.0) && throw(ArgumentError("history.t[end] must be finite and non-negative. Current value: $T"))
+    rv = Ref{Float64}(0.0)
+    check(ccall((:pdmpflux_rv_diagnostic, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Ref{Float64}, Int32, Ptr{Cvoid}),
+                s.pot, online ? s.flow_kind : Int32(0), n_sk, n_sk, 1, C_NULL, B, h.X, h.V, h.t, rv, 0, C_NULL))
+    return rv[]
+end
+
 sample(s::CuPDMP, N_sk::Int, N::Int, xinit::Vector{Float64}, vinit::Vector{Float64}; seed=nothing, discard_vt=true) =
     sample_from_skeleton(s, N, sample_skeleton(s, N_sk, xinit, vinit; seed=seed); discard_vt=discard_vt)
 

@@ -82,6 +82,9 @@ class GaussStd:
     """U = sum(x.^2)/2   (README.md:36-38)"""
     kind = 0
 
+    def value(self, x):
+        return float(np.dot(x, x)) / 2.0
+
     def grad(self, x):
         return x.copy()
 
@@ -95,6 +98,9 @@ class GaussDiag:
 
     def __init__(self, prec):
         self.p = np.asarray(prec, dtype=np.float64)
+
+    def value(self, x):
+        return float(np.sum(self.p * x * x)) / 2.0
 
     def grad(self, x):
         return self.p * x
@@ -112,6 +118,10 @@ class GaussEquicorr:
         self.alpha = 1.0 / (1.0 - rho)
         self.beta = rho / ((1.0 - rho) * (1.0 - rho + d * rho))
 
+    def value(self, x):
+        s = float(np.sum(x))
+        return (self.alpha * float(np.dot(x, x)) - self.beta * s * s) / 2.0
+
     def grad(self, x):
         return self.alpha * x - self.beta * np.sum(x)
 
@@ -122,6 +132,10 @@ class GaussEquicorr:
 class Banana:
     """U = (x1^2 + (x2 - x1^2 + 1)^2 + sum_{i>=3} x_i^2)/2   (test/test_config.jl:33-36)"""
     kind = 3
+
+    def value(self, x):
+        r = x[1] - x[0] * x[0] + 1.0
+        return (x[0] * x[0] + r * r + float(np.dot(x[2:], x[2:]))) / 2.0
 
     def grad(self, x):
         g = x.copy()
@@ -141,6 +155,8 @@ class Banana:
 class BananaReadmeScalar:
     """README.md:62-65: the manual 'gradient' returns a scalar that `.*` broadcasts to every coordinate."""
     kind = 4
+
+    value = Banana.value  # README.md:56-60: the same U; only the hand-written 'gradient' differs
 
     def grad(self, x):
         s = x[0] + (x[1] - (x[0] * x[0] - 1.0)) + np.sum(x[2:])
@@ -785,3 +801,36 @@ def sample_from_skeleton(sampler_kind, N, X, V, t, discard_vt=True):
             out[d:2 * d, j - 1] = vn
             out[2 * d, j - 1] = tm
     return out
+
+
+def rv_diagnostic(X, V, t, U, B=0):
+    """RV_diagnostic(history, U; B) (src/diagnostic.jl:37-75): realised volatility of U along the skeleton,
+    sampled at B+1 equidistant boundaries with the *linear* interpolation of _history_position_linear!
+    (src/diagnostic.jl:23-35; is_active all true for the non-sticky samplers).  X, V are (d, n) like the Julia
+    matrices, U a callable on a d-vector."""
+    N = t.shape[0]
+    if N == 0:
+        return 0.0
+    T = float(t[-1])
+    if not math.isfinite(T) or T < 0.0:
+        raise ValueError("history.t[end] must be finite and non-negative")
+    if B == 0:
+        B = max(1, int(math.floor(math.sqrt(X.shape[1]))))
+    elif B < 0:
+        raise ValueError("B must be non-negative")
+    if T == 0.0:
+        return 0.0
+    boundaries = grid_times(T, B + 1)      # range(0.0, T; length=B+1)
+    x_left = X[:, 0].copy()
+    RV = 0.0
+    i = 0
+    for b in range(1, B + 1):
+        tb = boundaries[b]
+        while i < N - 1 and t[i + 1] <= tb:
+            i += 1
+        tau = tb - t[i]
+        x_right = X[:, i] + V[:, i] * tau
+        inc = U(x_right) - U(x_left)
+        RV += inc * inc
+        x_left = x_right
+    return RV / T

@@ -105,6 +105,8 @@ SIGNATURES = {
     "pdmpflux_skeleton_moments": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_void_p]),
+    "pdmpflux_rv_diagnostic": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pdmpflux_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "pdmpflux_host_free": (C.c_int, [C.c_void_p]),
     "pdmpflux_launch_count": (C.c_int64, []),

@@ -876,6 +876,47 @@ int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_ch
     return PDMPFLUX_OK;
 }
 
+int pdmpflux_rv_diagnostic(pdmpflux_potential_t pot, int flow_kind, int64_t n_sk, int64_t ld_sk, int64_t n_chains,
+                           const int64_t* ncols, int64_t B, const double* X, const double* V, const double* t,
+                           double* rv, int32_t on_device, void* stream_) {
+    if (!pot || !X || !V || !t || !rv || n_sk <= 0 || ld_sk < n_sk || n_chains <= 0)
+        return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
+    if (B < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "B must be non-negative");  // diagnostic.jl:49-51
+    if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear) or 1 (rotation)");
+    if (pot->kind == PDMPFLUX_LOGREG || pot->kind == PDMPFLUX_GAUSS_DENSE)
+        return fail(PDMPFLUX_ERR_UNSUPPORTED, "no device U(x) plugin for this potential");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: no CPU fallback");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int dim = pot->dim;
+    const int64_t ld_u = (B > 0 ? B : (int64_t)std::floor(std::sqrt((double)n_sk)) + 1) + 1;
+    DevBuf dX, dV, dt, dn, du, drv;
+    const double *pX = X, *pV = V, *pt = t;
+    const int64_t* pn = ncols;
+    double* prv = rv;
+    CUDA_TRY(du.alloc(sizeof(double) * ld_u * n_chains));
+    if (!on_device) {
+        const size_t nx = sizeof(double) * dim * ld_sk * n_chains;
+        CUDA_TRY(dX.alloc(nx)); CUDA_TRY(dV.alloc(nx)); CUDA_TRY(dt.alloc(sizeof(double) * ld_sk * n_chains));
+        CUDA_TRY(drv.alloc(sizeof(double) * n_chains));
+        CUDA_TRY(cudaMemcpyAsync(dX.p, X, nx, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dV.p, V, nx, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dt.p, t, sizeof(double) * ld_sk * n_chains, cudaMemcpyHostToDevice, stream));
+        if (ncols) {
+            CUDA_TRY(dn.alloc(sizeof(int64_t) * n_chains));
+            CUDA_TRY(cudaMemcpyAsync(dn.p, ncols, sizeof(int64_t) * n_chains, cudaMemcpyHostToDevice, stream));
+            pn = dn.as<int64_t>();
+        }
+        pX = dX.as<double>(); pV = dV.as<double>(); pt = dt.as<double>(); prv = drv.as<double>();
+    }
+    CUDA_TRY(launch_rv_diagnostic(pot->kind, pot->pp, flow_kind, dim, ld_sk, n_sk, n_chains, pn, B, pX, pV, pt,
+                                  du.as<double>(), ld_u, prv, stream));
+    g_launches.fetch_add(1);
+    if (!on_device) CUDA_TRY(cudaMemcpyAsync(rv, prv, sizeof(double) * n_chains, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));  // the scratch row is freed on return
+    return PDMPFLUX_OK;
+}
+
 int pdmpflux_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(PDMPFLUX_ERR_ARGUMENT, "ptr is NULL");
     CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));

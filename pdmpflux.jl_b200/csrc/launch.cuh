@@ -77,6 +77,11 @@ cudaError_t launch_logreg_zigzag(const KernelParams& p, unsigned grid, size_t sm
 size_t logreg_smem_bytes(int d, int G);
 int logreg_chains_per_block();
 
+// diagnostic.cu: RV_diagnostic (src/diagnostic.jl:37-75) over a batch of skeletons; uval is a [C][ld_u >= B+1] scratch
+cudaError_t launch_rv_diagnostic(int kind, const PotParams& pp, int flow_kind, int d, int64_t ld_sk, int64_t n_sk,
+                                 int64_t n_chains, const int64_t* ncols, int64_t B, const double* X, const double* V,
+                                 const double* t, double* uval, int64_t ld_u, double* rv, cudaStream_t stream);
+
 cudaError_t launch_skeleton_zigzag(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_skeleton_bps(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_skeleton_fecmc(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);

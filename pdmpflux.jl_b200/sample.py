@@ -180,6 +180,64 @@ def _sample_from_skeleton_dt(sampler, N, history, dt, discard_vt):
     return out if isinstance(history, PDMPHistoryBatch) else out[0].T
 
 
+def RV_diagnostic(history, potential, *, B=0, flow_kind=0):
+    """RV_diagnostic(history, U; B) (src/diagnostic.jl:37-75): realised volatility of U along the skeleton, on the
+    device.  `potential` is the descriptor whose U(x) plugin is evaluated (the reference takes a Julia closure).
+    `history`: a `PDMPHistory` -> float; a `PDMPHistoryBatch` or a list of (ragged) `PDMPHistory` -> array (C,).
+    B = 0 picks floor(sqrt(n)) like the reference; B < 0 raises ArgumentError.  flow_kind = 1 interpolates with the
+    Boomerang rotation (the online variant's sampler.flow) instead of the offline diagnostic's straight lines."""
+    if B < 0:
+        raise _lib.ArgumentError(f"B must be non-negative. Current value: {B}")
+    ncols = None
+    if isinstance(history, (list, tuple)):
+        if not history:
+            return np.zeros(0)
+        d = history[0].X.shape[0]
+        ncols = np.array([h.t.shape[0] for h in history], dtype=np.int64)
+        ld = max(1, int(ncols.max()))
+        X = np.zeros((len(history), ld, d)); V = np.zeros((len(history), ld, d)); t = np.zeros((len(history), ld))
+        for c, h in enumerate(history):
+            n = int(ncols[c])
+            X[c, :n] = h.X.T; V[c, :n] = h.V.T; t[c, :n] = h.t
+        t_end = np.array([h.t[-1] if h.t.shape[0] else 0.0 for h in history])
+    else:
+        X, V, t = _as_batch_arrays(history)
+        t_end = t[:, -1] if t.shape[1] else np.zeros(t.shape[0])
+    n_chains, ld, d = X.shape
+    if ld == 0:
+        out = np.zeros(n_chains)      # N == 0 -> 0.0 (diagnostic.jl:40)
+        return out if isinstance(history, (list, tuple, PDMPHistoryBatch)) else float(out[0])
+    bad = ~(np.isfinite(t_end) & (t_end >= 0.0))
+    if bad.any():
+        raise _lib.ArgumentError(f"history.t[end] must be finite and non-negative. Current value: {t_end[bad][0]}")
+    h = potential._create(d)
+    try:
+        rv = np.empty(n_chains)
+        _lib.check(_lib.lib().pdmpflux_rv_diagnostic(h, int(flow_kind), ld, ld, n_chains, _ptr(ncols), int(B), _ptr(X),
+                                                     _ptr(V), _ptr(t), _ptr(rv), 0, None))
+    finally:
+        _lib.lib().pdmpflux_potential_destroy(h)
+    return rv if isinstance(history, (list, tuple, PDMPHistoryBatch)) else float(rv[0])
+
+
+def sample_skeleton_with_diagnostic(sampler: AbstractPDMP, T, xinit, vinit, potential=None, *, B=1000, seed=None,
+                                    verbose=True, init_capacity=1024, tape=None):
+    """sample_skeleton_with_diagnostic(sampler, T, xinit, vinit, U; B, seed) (src/sample.jl:75-236): the time-horizon
+    skeleton plus the realised volatility of U over B blocks of [0, T].  The reference accumulates the increments
+    online through sampler.flow; the sum telescopes to the per-boundary form, so the value is computed here from the
+    finished skeleton on the device with the sampler's own flow (equal to the online value up to rounding, and to
+    RV_diagnostic for the straight-line samplers -- the reference's own 1e-10 check, test/test_diagnostics.jl:126-143).
+    Returns (history, rv); for a (C, d) init (list of histories, array of rv)."""
+    if B <= 0:
+        raise _lib.ArgumentError(f"B must be positive. Current value: {B}")
+    hist = sample_skeleton_until(sampler, T, xinit, vinit, seed=seed, verbose=verbose, tape=tape,
+                                 init_capacity=init_capacity)
+    pot = sampler.potential if potential is None else potential
+    if float(T) == 0.0:   # the initial point alone (sample.jl:111-114)
+        return hist, (np.zeros(len(hist)) if isinstance(hist, list) else 0.0)
+    return hist, RV_diagnostic(hist, pot, B=B, flow_kind=sampler.flow_kind)
+
+
 def sample(sampler: AbstractPDMP, N_sk, N_samples, xinit, vinit, *, seed=None, verbose=True, discard_vt=True):
     """sample(sampler, N_sk, N_samples, xinit, vinit; seed) = sample_from_skeleton o sample_skeleton
     (src/sample.jl:27-58)."""

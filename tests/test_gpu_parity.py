@@ -452,3 +452,83 @@ def test_fused_moments_match_skeleton_integrals(p, kind):
         n_in = int(np.floor(Tstop / (hb.t[c, -1] / 200000)))
         approx = dense[c, :n_in].mean(axis=0) * Tstop
         assert np.allclose(a1[c], approx, atol=5e-3 * max(1.0, Tstop))
+
+
+def test_rv_diagnostic_reference_kat_and_errors(p):
+    """The reference's own known answer (test/test_diagnostics.jl:100-124) through the C ABI, plus its error paths."""
+    X = np.array([[0.0, 0.5, 1.0]]); V = np.ones((1, 3)); t = np.array([0.0, 0.5, 1.0])
+    z = np.zeros(3); zi = np.zeros(3, dtype=np.int32)
+    h = p.PDMPHistory(X, V, t, z, z, zi, np.zeros((5, 3)), zi, zi)
+    U = lambda x: x ** 2 / 2
+    expected = sum((U(k / 4) - U((k - 1) / 4)) ** 2 for k in range(1, 5))
+    assert p.RV_diagnostic(h, p.GaussStd(), B=4) == pytest.approx(expected, rel=1e-14)
+    assert p.RV_diagnostic(h, p.GaussStd(), B=0) > 0.0
+    with pytest.raises(p.ArgumentError):
+        p.RV_diagnostic(h, p.GaussStd(), B=-1)
+    h0 = p.PDMPHistory(X[:, :1], V[:, :1], t[:1], z[:1], z[:1], zi[:1], np.zeros((5, 1)), zi[:1], zi[:1])
+    assert p.RV_diagnostic(h0, p.GaussStd(), B=3) == 0.0                    # T == 0
+    hneg = p.PDMPHistory(X, V, np.array([0.0, 0.5, np.inf]), z, z, zi, np.zeros((5, 3)), zi, zi)
+    with pytest.raises(p.ArgumentError):
+        p.RV_diagnostic(hneg, p.GaussStd())
+    with pytest.raises(p.UnsupportedError):
+        p.RV_diagnostic(h, p.LogReg(np.ones((4, 1)), np.array([0.0, 1.0, 0.0, 1.0])), B=2)
+
+
+@pytest.mark.parametrize("kind", ["zigzag_banana", "zigzag_readme", "bps_equicorr", "fecmc_std", "boomerang_diag"])
+def test_rv_diagnostic_matches_oracle(p, kind):
+    """Device RV_diagnostic against the oracle's literal restatement (src/diagnostic.jl:37-75) on sampled skeletons,
+    1e-10 relative: batches, B = 0 and explicit, and the offline diagnostic's straight lines even for Boomerang."""
+    import pdmp_oracle_np as onp
+    d, nch, n_sk = 9, 6, 400
+    g = np.random.default_rng(17)
+    mk = {"zigzag_banana": (lambda: p.ZigZagAD(d, p.Banana()), onp.Banana()),
+          "zigzag_readme": (lambda: p.ZigZag(d, p.GaussStd()), onp.BananaReadmeScalar()),
+          "bps_equicorr": (lambda: p.BPS(d, p.GaussEquicorr(0.6), refresh_rate=0.2), onp.GaussEquicorr(d, 0.6)),
+          "fecmc_std": (lambda: p.ForwardECMC(d, p.GaussStd()), onp.GaussStd()),
+          "boomerang_diag": (lambda: p.Boomerang(d, p.GaussDiag(np.linspace(0.5, 2, d)), refresh_rate=0.3),
+                             onp.GaussDiag(np.linspace(0.5, 2, d)))}[kind]
+    s, opot = mk[0](), mk[1]
+    dev_pot = {"zigzag_readme": p.BananaReadmeScalar()}.get(kind, s.potential)
+    x0 = g.standard_normal((nch, d))
+    v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0) if kind.startswith("zigzag") else g.standard_normal((nch, d))
+    hb = p.sample_skeleton(s, n_sk, x0, v0, seed=5)
+    for B in (0, 7, 250):
+        rv = p.RV_diagnostic(hb, dev_pot, B=B)
+        ref = np.array([onp.rv_diagnostic(hb.X[c].T, hb.V[c].T, hb.t[c], opot.value, B=B) for c in range(nch)])
+        assert rv.shape == (nch,) and np.allclose(rv, ref, rtol=1e-10, atol=0), (B, rv, ref)
+    one = p.RV_diagnostic(hb.chain(2), dev_pot, B=31)
+    assert one == pytest.approx(onp.rv_diagnostic(hb.X[2].T, hb.V[2].T, hb.t[2], opot.value, B=31), rel=1e-10)
+
+
+def test_sample_skeleton_with_diagnostic_online_equals_offline(p):
+    """test/test_diagnostics.jl:126-143: ForwardECMCAD(3, |x|^2/2, grid_size=8, tmax=1, adaptive=false), T = 3, B = 20,
+    seed = 42: the online value equals RV_diagnostic(history; B = 20) to rtol 1e-10; ragged batches; the Boomerang
+    variant follows its rotation flow (checked against a direct evaluation)."""
+    import pdmp_oracle_np as onp
+    dim = 3
+    s = p.ForwardECMCAD(dim, p.GaussStd(), grid_size=8, tmax=1.0, adaptive=False)
+    xinit = np.zeros(dim); vinit = np.ones(dim) / np.sqrt(dim)
+    hist, rv_online = p.sample_skeleton_with_diagnostic(s, 3.0, xinit, vinit, B=20, seed=42, verbose=False)
+    assert hist.t[-1] == 3.0
+    rv_offline = p.RV_diagnostic(hist, p.GaussStd(), B=20)
+    assert rv_online == pytest.approx(rv_offline, rel=1e-10, abs=1e-12)
+    assert rv_online == pytest.approx(onp.rv_diagnostic(hist.X, hist.V, hist.t, onp.GaussStd().value, B=20), rel=1e-10)
+    # ragged batch: every chain ends at T with its own number of events
+    g = np.random.default_rng(2)
+    hs, rvs = p.sample_skeleton_with_diagnostic(s, 40.0, g.standard_normal((5, dim)), np.tile(vinit, (5, 1)), B=20, seed=7)
+    assert len({h.t.shape[0] for h in hs}) > 1 and rvs.shape == (5,)
+    for h, r in zip(hs, rvs):
+        assert r == pytest.approx(onp.rv_diagnostic(h.X, h.V, h.t, onp.GaussStd().value, B=20), rel=1e-10)
+    # Boomerang: online value goes through the rotation flow
+    sb = p.Boomerang(dim, p.GaussDiag(np.array([0.5, 1.0, 2.0])), refresh_rate=0.5)
+    hbm, rvb = p.sample_skeleton_with_diagnostic(sb, 4.0, np.array([0.3, -0.2, 0.1]), np.array([1.0, 0.5, -0.7]), B=16, seed=3)
+    U = onp.GaussDiag(np.array([0.5, 1.0, 2.0])).value
+    tb = onp.grid_times(4.0, 17)
+    idx = np.searchsorted(hbm.t, tb, side="right") - 1
+    tau = tb - hbm.t[idx]
+    pos = hbm.X[:, idx] * np.cos(tau) + hbm.V[:, idx] * np.sin(tau)
+    vals = np.array([U(pos[:, k]) for k in range(17)])
+    vals[0] = U(hbm.X[:, 0])
+    assert rvb == pytest.approx(np.sum(np.diff(vals) ** 2) / 4.0, rel=1e-10)
+    with pytest.raises(p.ArgumentError):
+        p.sample_skeleton_with_diagnostic(s, -1.0, xinit, vinit, B=20)

@@ -203,3 +203,31 @@ def test_time_horizon_variant_oracle():
     # T == 0: the initial point alone; too small a capacity is reported
     assert oc.sample_skeleton_until(cfg, 0.0, 4, x0, v0, seed=3).ncols.tolist() == [1, 1]
     assert oc.sample_skeleton_until(cfg, T, 3, x0, v0, seed=3).ncols.tolist() == [-1, -1]
+
+
+def test_rv_diagnostic_reference_kat():
+    """The reference's own known answer for this path (test/test_diagnostics.jl:100-124): hand-built straight-line
+    history x(t) = t on [0, 1], U = x_1^2 / 2, B = 4 -> sum_k (U(k/4) - U((k-1)/4))^2; B = 0 -> positive;
+    B < 0 -> ArgumentError.  Pins the interpolation + blocking of the oracle's RV_diagnostic restatement."""
+    X = np.array([[0.0, 0.5, 1.0]]); V = np.ones((1, 3)); t = np.array([0.0, 0.5, 1.0])
+    U = lambda x: x[0] ** 2 / 2
+    expected = sum((U([k / 4]) - U([(k - 1) / 4])) ** 2 for k in range(1, 5))
+    assert onp.rv_diagnostic(X, V, t, U, B=4) == pytest.approx(expected, rel=1e-15)
+    assert onp.rv_diagnostic(X, V, t, onp.GaussStd().value, B=4) == pytest.approx(expected, rel=1e-15)
+    assert onp.rv_diagnostic(X, V, t, U, B=0) > 0.0
+    with pytest.raises(ValueError):
+        onp.rv_diagnostic(X, V, t, U, B=-1)
+    assert onp.rv_diagnostic(X[:, :0], V[:, :0], t[:0], U) == 0.0        # empty history (diagnostic.jl:40)
+    assert onp.rv_diagnostic(X[:, :1], V[:, :1], t[:1], U, B=3) == 0.0   # T == 0 (diagnostic.jl:53)
+
+
+def test_potential_values_match_their_gradients():
+    """U plugins used by RV_diagnostic: central differences of value() reproduce grad() (the README-scalar banana keeps
+    the true U; only its hand-written gradient is wrong, README.md:56-65)."""
+    g = np.random.default_rng(3)
+    d = 6
+    for pot in (onp.GaussStd(), onp.GaussDiag(np.linspace(0.5, 2, d)), onp.GaussEquicorr(d, 0.7), onp.Banana()):
+        x = g.standard_normal(d)
+        num = np.array([(pot.value(x + 1e-6 * e) - pot.value(x - 1e-6 * e)) / 2e-6 for e in np.eye(d)])
+        assert np.allclose(num, pot.grad(x), rtol=1e-7, atol=1e-8)
+    assert onp.BananaReadmeScalar().value(np.arange(1.0, 5.0)) == onp.Banana().value(np.arange(1.0, 5.0))
