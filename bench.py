@@ -72,7 +72,7 @@ def make_sampler(p, name):
     raise SystemExit(f"unknown config {name}")
 
 
-FP64_PEAK_TFLOPS = 33.4  # measured DFMA throughput (scratch/fp64_peak.cu); datasheet FP64 / FP64-tensor: 37-40
+FP64_PEAK_TFLOPS = 37.0  # measured FP64 tensor (DMMA) throughput, scratch/dmma_peak.cu; plain DFMA measures 33.4 (scratch/fp64_peak.cu)
 
 
 def pin_to_gpu_numa_node(index):
@@ -399,7 +399,7 @@ def extra_workloads(p, main, peak):
             flop = 2.0 * n_rows * d * ((2 + 2 * G) * builds + 3 * rates)
             out[f"{name}@{nch}"].update({"fp64_tflops": flop / best / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
                                          "fp64_frac": flop / best / 1e12 / FP64_PEAK_TFLOPS,
-                                         "fp64_peak_source": "scratch/fp64_peak.cu DFMA microbenchmark on this pool's B200 (MEASURED_PEAKS.json has no FP64 entry)"})
+                                         "fp64_peak_source": "scratch/dmma_peak.cu DMMA microbenchmark on this pool's B200 (MEASURED_PEAKS.json has no FP64 entry)"})
         del bufs, view, ch
         torch.cuda.empty_cache()
     return out

@@ -291,7 +291,7 @@ def test_vector_and_bulk_store_paths_match_scalar_stores(p, d, team, n_sk, nch):
 
 
 def test_logreg_free_running_and_posterior(p):
-    """Config C4 in miniature: Zig-Zag on a logistic-regression posterior (CTA-per-chain DMMA kernel).  Free-running
+    """Config C4 in miniature: Zig-Zag on a logistic-regression posterior (four-chains-per-CTA DMMA kernel).  Free-running
     parity with injected draws, Philox determinism across sharding, and a posterior sanity check against a Laplace
     approximation."""
     from oracle_cases import logreg_data
@@ -306,6 +306,14 @@ def test_logreg_free_running_and_posterior(p):
     assert relerr(h.X, r.X) < 1e-9 and relerr(h.t, r.t) < 1e-9 and np.array_equal(h.V, r.V)
     assert np.array_equal(h.rejected, r.rejected) and np.array_equal(h.hitting_horizon, r.hitting_horizon)
     assert np.array_equal(h.tape_pos[:, :2], r.tape_used[:, :2])
+    # smallest / largest grid (a pass carries 64 residual columns: with G = 12 only two bound requests fit, the
+    # others wait a round) and a chain count that leaves the last CTA partly empty
+    for G in (2, 12):
+        xg, vg, tape_g = case_inputs("logreg_grid%d" % G, 0, d, 80, n_chains=9)
+        rg = oc.sample_skeleton(oc.make_cfg(0, 5, d, pp, grid_size=G), 80, xg, vg, tape=tape_g)
+        hg = p.sample_skeleton(p.ZigZagAD(d, p.LogReg(X, y, s0), grid_size=G), 80, xg, vg, tape=tape_g)
+        assert (rg.status == 0).all() and relerr(hg.X, rg.X) < 1e-9 and relerr(hg.t, rg.t) < 1e-9
+        assert np.array_equal(hg.V, rg.V) and np.array_equal(hg.rejected, rg.rejected)
     # Philox mode: shards reproduce the big run
     hp = p.sample_skeleton(s, 60, x0, v0, seed=3)
     hp2 = p.sample_skeleton(s, 60, x0[2:5], v0[2:5], seed=3, chain_offset=2)
