@@ -540,3 +540,32 @@ def test_sample_skeleton_with_diagnostic_online_equals_offline(p):
     assert rvb == pytest.approx(np.sum(np.diff(vals) ** 2) / 4.0, rel=1e-10)
     with pytest.raises(p.ArgumentError):
         p.sample_skeleton_with_diagnostic(s, -1.0, xinit, vinit, B=20)
+
+
+def test_edge_sizes_match_oracle(p):
+    """Smallest and largest shapes the path accepts: n_sk = 1 (the initial column only, src/sample.jl:266-268), d = 1,
+    grid_size = 2 (smallest valid; 1 indexes t[2] out of bounds upstream, UpperBound.jl:95,205) and 64 (device maximum),
+    a single chain and a chain count that is not a multiple of any team/CTA packing."""
+    g = np.random.default_rng(4)
+    # n_sk = 1: one column = the initial state, zero statistics, no draws consumed
+    s = p.BPS(4, p.GaussStd())
+    x0 = g.standard_normal((3, 4)); v0 = g.standard_normal((3, 4))
+    h = p.sample_skeleton(s, 1, x0, v0, seed=1)
+    assert np.array_equal(h.X[:, 0], x0) and np.array_equal(h.V[:, 0], v0) and np.all(h.t == 0.0)
+    assert not h.rejected.any() and not h.hitting_horizon.any() and not h.errored_bound.any()
+    # grid sizes 2 and 64, teacher-free short runs against the C oracle with an injected tape
+    for (sk, d, G, nch) in ((0, 1, 2, 1), (0, 5, 64, 7), (1, 3, 2, 5), (1, 6, 64, 3), (3, 1, 64, 2), (2, 2, 2, 3)):
+        name = "edge_%d_%d_%d" % (sk, d, G)
+        xg, vg, tape = case_inputs(name, sk, d, 60, n_chains=nch)
+        kw = dict(grid_size=G, **({1: dict(tmax=1.0, refresh_rate=0.1), 3: dict(tmax=1.0, refresh_rate=0.1)}.get(sk, {})))
+        r = oc.sample_skeleton(oc.make_cfg(sk, 0, d, np.zeros(0), **kw), 60, xg, vg, tape=tape)
+        hg = p.sample_skeleton(make_sampler(p, sk, 0, np.zeros(0), d, kw), 60, xg, vg, tape=tape)
+        ok = r.status == 0
+        assert ok.any(), name
+        assert np.array_equal(hg.status == 0, ok), name
+        assert relerr(hg.X[ok], r.X[ok]) < 1e-9 and relerr(hg.t[ok], r.t[ok]) < 1e-9, name
+        assert np.array_equal(hg.rejected[ok], r.rejected[ok]) and np.array_equal(hg.hitting_horizon[ok], r.hitting_horizon[ok]), name
+    with pytest.raises(p.ArgumentError):
+        p.ZigZag(3, p.GaussStd(), grid_size=1)
+    with pytest.raises(p.UnsupportedError):
+        p.ZigZag(3, p.GaussStd(), grid_size=65)
