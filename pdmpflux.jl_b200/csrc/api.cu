@@ -337,7 +337,9 @@ int pdmpflux_potential_create(int kind, int dim, const double* params, int64_t n
         if (n <= 0 || !(s0 > 0.0) || !need(2 + n * dim + n)) { rc = fail(PDMPFLUX_ERR_ARGUMENT, "LOGREG: bad n / sigma0 / parameter length"); break; }
         if (dim > 128) { rc = fail(PDMPFLUX_ERR_UNSUPPORTED, "LOGREG supports dim <= 128 on the device path"); break; }
         const size_t yoff = ((size_t)n * dim + 1) & ~size_t(1);  // y starts 16-byte aligned (TMA bulk source)
-        if (pot->params.alloc(sizeof(double) * (yoff + n)) != cudaSuccess ||
+        // two zeroed doubles of padding: the TMA tile copies round odd tails up to 16 bytes (logreg.cu: issue)
+        if (pot->params.alloc(sizeof(double) * (yoff + n + 2)) != cudaSuccess ||
+            cudaMemset(pot->params.p, 0, sizeof(double) * (yoff + n + 2)) != cudaSuccess ||
             cudaMemcpy(pot->params.p, params + 2, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMemcpy(pot->params.as<double>() + yoff, params + 2 + (size_t)n * dim, sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
             rc = fail(PDMPFLUX_ERR_CUDA, "LOGREG design-matrix upload failed (is a CUDA device present?)");

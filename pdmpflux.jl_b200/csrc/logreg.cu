@@ -30,8 +30,10 @@
 
 namespace pdmpflux {
 
-constexpr int kLrThreads = 128;
-constexpr int kLrChains = 4;   // chains per CTA = warps per CTA
+constexpr int kLrThreads = 384; // warpgroup 0: consumers (chain logic + main product); warpgroups 1, 2: producers
+constexpr int kLrChains = 4;   // chains per CTA = consumer warps
+constexpr int kLrXStages = 5;  // X-tile ring (TMA); 4 or 3 when d is so large that five tiles do not fit
+constexpr int kLrRStages = 3;  // residual-tile ring (producers -> consumers)
 constexpr int kLrRows = 32;    // rows of X per tile
 constexpr int kLrMaxG = 12;    // grid_size limit: 2G <= 24 columns per chain
 constexpr int kLrMaxNt = 8;    // n-tiles (of 8 residual columns) one pass can carry: requests beyond wait a round
@@ -63,13 +65,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {  // named barrier of one warpgroup
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 struct LrShared {  // offsets (in doubles) into dynamic shared memory
-    int bar, Xt, rs, ybuf, xv, zw, lam, box, cum, sched, tile, acc_stride, total;
+    int bar, Xt, rs, ybuf, xv, zw, lam, box, cum, sched, tile, rs_tile, acc_stride, xstages, total;
 };
 // request schedule of one pass (shared memory, written by the chain warps, read by everybody)
 struct LrSched {
@@ -80,21 +88,25 @@ struct LrSched {
     double tp[kLrChains];          // rate request: the proposal time
     double gc[kLrChains], grem[kLrChains], gh[kLrChains];  // bound request: its time grid (see grid_t)
 };
-__host__ __device__ inline LrShared lr_layout(int d) {
+// mbarriers: full_x[s] (TMA landed), empty_x[s] (consumers done with the tile), full_rs[r] (residual tile written),
+// empty_rs[r] (consumers done with it)
+constexpr int kBarFullX = 0, kBarEmptyX = kLrXStages, kBarFullR = 2 * kLrXStages, kBarEmptyR = 2 * kLrXStages + kLrRStages;
+constexpr int kLrBars = 2 * kLrXStages + 2 * kLrRStages;
+__host__ __device__ inline LrShared lr_layout(int d, int xstages) {
     LrShared L;
     const int dp = (d + 7) / 8 * 8;
+    L.xstages = xstages;
     L.tile = kLrRows * d + 32;                  // one X tile, rows contiguous (+ slack for fragment over-reads)
+    L.rs_tile = kLrRows * kLrNcs + 32;          // one residual tile
     L.acc_stride = kLrMaxCols;
     int o = 0;
-    L.bar = o; o += 2;                          // two mbarriers (8 bytes each)
-    L.Xt = o; o += 2 * L.tile;                  // double-buffered X tiles (16-byte aligned: tile is even)
-    L.rs = o; o += kLrRows * kLrNcs + 32;       // residual columns
-    // after a pass the accumulators (dp+8 rows x kLrMaxCols) overlay [Xt ring | rs]; make sure they fit
-    const int need = (dp + 8) * kLrMaxCols;
-    if (o - L.Xt < need) o = L.Xt + need;
-    L.ybuf = o; o += 2 * kLrRows;
+    L.bar = o; o += kLrBars;
+    L.Xt = o; o += xstages * L.tile;            // X-tile ring (16-byte aligned: tile is even)
+    L.rs = o; o += kLrRStages * L.rs_tile;      // residual-tile ring
+    // after a pass the accumulators ((dp + 24) rows x kLrMaxCols) overlay [X ring | rs ring]: they fit by a wide margin
+    L.ybuf = o; o += xstages * kLrRows;
     L.xv = o; o += (dp + 4) * 8;                // [k][8]: columns (2c, 2c+1) = (x, v) of chain c -- state AND B operand
-    L.zw = o; o += kLrRows * 8;                 // [row][8]: (z, w) of chain c in columns (2c, 2c+1)
+    L.zw = o; o += 4 * kLrRows * 8;             // [producer group][parity][row][8]: (z, w) of chain c in columns (2c, 2c+1)
     L.lam = o; o += kLrChains * dp;
     L.box = o; o += kLrChains * 16;
     L.cum = o; o += kLrChains * 16;
@@ -102,61 +114,60 @@ __host__ __device__ inline LrShared lr_layout(int d) {
     L.total = o;
     return L;
 }
+__host__ __device__ inline LrShared lr_layout(int d) {  // the deepest X ring that fits the 227 KB of one SM
+    int xs = kLrXStages;
+    while (xs > 3 && sizeof(double) * (size_t)lr_layout(d, xs).total > 227u * 1024u) --xs;
+    return lr_layout(d, xs);
+}
 size_t logreg_smem_bytes(int d, int G) { (void)G; return sizeof(double) * (size_t)lr_layout(d).total; }
 
-// One pass over all rows of X serving every posted request:
-//   acc[i][col] = sum_r X[r][i] * R[r][col]   (stored to shared memory, row stride L.acc_stride, overlaying the tile ring)
-template <int NT>
-__device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const LrShared& L, uint32_t (&phase)[2]) {
-    const int d = p.d, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Ring bookkeeping is stateless: tile g (counted across passes, modulo 120 = lcm of the rings' parity periods for 3, 4
+// or 5 X stages) lives in X slot g % xstages / residual slot g % 3, and the mbarrier phase parity of its use is
+// (g / xstages) & 1 resp. (g / 3) & 1.
+struct LrRing {
+    int xs, rs;
+    uint32_t xpar, rpar;
+};
+__device__ __forceinline__ LrRing lr_ring(uint32_t g, int xstages) {
+    LrRing r;
+    r.xs = (int)(g % (uint32_t)xstages); r.xpar = (g / (uint32_t)xstages) & 1u;
+    r.rs = (int)(g % kLrRStages); r.rpar = (g / kLrRStages) & 1u;
+    return r;
+}
+
+// ---- producer warpgroup pg (0 or 1): tiles pg, pg + 2, ...: TMA feed, (z, w) of the four chains, residual columns ----
+__device__ void lr_produce(const KernelParams& p, double* sm, const LrShared& L, uint32_t gbase, int pg, int ptid) {
+    const int d = p.d, lane = ptid & 31, pw = ptid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int64_t n = p.pot.n;
     const LrSched* S = reinterpret_cast<const LrSched*>(sm + L.sched);
-    const int n_mt = (d + 7) / 8;                    // m-tiles (coordinates), <= 16
     const int kz = (d + 3) / 4;                      // k-steps of the z/w product
-    // warp -> m-tiles {mrot, mrot + 4, ..}; rotated by CTA parity so that the warp carrying the odd extra tile sits on
-    // a different SM sub-partition in the two co-resident CTAs
-    const int mrot = (warp + 2 * (int)(blockIdx.x & 1)) & 3;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
-    double acc[4][NT][2];                            // up to 4 m-tiles per warp x NT n-tiles
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
     const int64_t ntiles = (n + kLrRows - 1) / kLrRows;
-    auto issue = [&](int64_t tile) {  // thread 0: TMA the tile's rows of X and y into ring slot tile & 1
-        const int slot = (int)(tile & 1);
+    auto issue = [&](int64_t tile) {  // one thread: wait until the slot is free, then TMA the tile's rows of X and y
+        const LrRing r = lr_ring(gbase + (uint32_t)tile, L.xstages);
+        mbar_wait(&bar[kBarEmptyX + r.xs], r.xpar ^ 1u);
         const int64_t r0 = tile * kLrRows;
         const int rows = (int)min((int64_t)kLrRows, n - r0);
-        const uint32_t xb = ((uint32_t)rows * d * 8u) & ~15u, yb = ((uint32_t)rows * 8u) & ~15u;
-        mbar_expect_tx(&bar[slot], xb + yb);
-        if (xb) bulk_load(sm + L.Xt + slot * L.tile, p.pot.vec + r0 * d, xb, &bar[slot]);
-        if (yb) bulk_load(sm + L.ybuf + slot * kLrRows, p.pot.vec2 + r0, yb, &bar[slot]);
+        // sizes rounded up to 16 bytes: the odd tail reads one double past the tile (zero padding behind X and y)
+        const uint32_t xb = ((uint32_t)rows * d * 8u + 15u) & ~15u, yb = ((uint32_t)rows * 8u + 15u) & ~15u;
+        mbar_expect_tx(&bar[kBarFullX + r.xs], xb + yb);
+        bulk_load(sm + L.Xt + r.xs * L.tile, p.pot.vec + r0 * d, xb, &bar[kBarFullX + r.xs]);
+        bulk_load(sm + L.ybuf + r.xs * kLrRows, p.pot.vec2 + r0, yb, &bar[kBarFullX + r.xs]);
     };
-    // The accumulators of the previous pass overlaid the ring: every warp is done with them (caller's barrier), but the
-    // overlay was written through the generic proxy, so order it before the TMA (async proxy) refills the ring.
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) issue(0);
-    for (int64_t tile = 0; tile < ntiles; ++tile) {
-        const int slot = (int)(tile & 1);
-        const int64_t r0 = tile * kLrRows;
-        const int rows = (int)min((int64_t)kLrRows, n - r0);
-        if (tid == 0 && tile + 1 < ntiles) issue(tile + 1);  // slot (tile+1)&1 was released by the barrier below
-        mbar_wait(&bar[slot], phase[slot]);
-        phase[slot] ^= 1u;
-        double* Xs = sm + L.Xt + slot * L.tile;
-        double* ys = sm + L.ybuf + slot * kLrRows;
-        if (tid == 0) {  // odd tails that a 16-byte granular bulk copy cannot carry
-            if ((rows * d) & 1) Xs[rows * d - 1] = __ldg(p.pot.vec + r0 * d + rows * d - 1);
-            if (rows & 1) ys[rows - 1] = __ldg(p.pot.vec2 + r0 + rows - 1);
-        }
-        if ((rows & 1) || ((rows * d) & 1)) __syncthreads();
+    if (ptid == 0 && pg < ntiles) issue(pg);
+    for (int64_t tile = pg; tile < ntiles; tile += 2) {
+        const LrRing r = lr_ring(gbase + (uint32_t)tile, L.xstages);
+        const int rows = (int)min((int64_t)kLrRows, n - tile * kLrRows);
+        if (ptid == 0 && tile + 2 < ntiles) issue(tile + 2);  // this group's next tile: two consumer periods ahead
+        mbar_wait(&bar[kBarFullX + r.xs], r.xpar);
+        const double* Xs = sm + L.Xt + r.xs * L.tile;
+        const double* ys = sm + L.ybuf + r.xs * kLrRows;
+        double* zwb = sm + L.zw + (pg * 2 + (int)((tile >> 1) & 1)) * (kLrRows * 8);
         // ---- (z, w) of the four chains for the tile: DMMA with B = [x1 v1 .. x4 v4] (k x 8); 8 rows per warp ----
         {
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: halves the dependent MMA chain
-            const double* arow = Xs + (warp * 8 + gid) * d + tig;
+            const double* arow = Xs + (pw * 8 + gid) * d + tig;
             const double* bcol = sm + L.xv + tig * 8 + gid;
             int ks = 0;
             for (; ks + 1 < kz; ks += 2) {
@@ -164,34 +175,48 @@ __device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const Lr
                 dmma(e0, e1, arow[4 * ks + 4], bcol[32 * ks + 32]);
             }
             if (ks < kz) dmma(c0, c1, arow[4 * ks], bcol[32 * ks]);
-            double* zr = sm + L.zw + (warp * 8 + gid) * 8 + 2 * tig;  // C[row][2 tig], C[row][2 tig + 1] = (z, w) of chain tig
+            double* zr = zwb + (pw * 8 + gid) * 8 + 2 * tig;  // C[row][2 tig], C[row][2 tig + 1] = (z, w) of chain tig
             zr[0] = c0 + e0;
             zr[1] = c1 + e1;
         }
-        __syncthreads();
+        group_barrier(1 + pg, 128);
+        mbar_wait(&bar[kBarEmptyR + r.rs], r.rpar ^ 1u);  // consumers are done with the tile that used this slot
         // ---- residual columns: warp c evaluates chain c's requested times, lane = row of the tile ----
         {
-            const int nt = S->nt[warp];
+            const int nt = S->nt[pw];
             if (nt) {
                 const bool live = lane < rows;
-                const double z = sm[L.zw + lane * 8 + 2 * warp], w = sm[L.zw + lane * 8 + 2 * warp + 1], yy = ys[lane];
-                double* rp = sm + L.rs + lane * kLrNcs + S->col0[warp];
+                const double z = zwb[lane * 8 + 2 * pw], w = zwb[lane * 8 + 2 * pw + 1], yy = ys[lane];
+                double* rp = sm + L.rs + r.rs * L.rs_tile + lane * kLrNcs + S->col0[pw];
                 if (nt == 1) {  // rate at the proposal time
-                    const double sg = 1.0 / (1.0 + exp(-(z + S->tp[warp] * w)));
+                    const double sg = 1.0 / (1.0 + exp(-(z + S->tp[pw] * w)));
                     rp[0] = live ? sg - yy : 0.0;
                 } else {        // bound: residual and Hessian-weight columns at the G grid times
-                    const double gc = S->gc[warp], grem = S->grem[warp], gh = S->gh[warp];
-                    if (fabs(z) + fabs(gh * w) < 600.0) {
-                        // eta_k = z + t_k w on a uniform grid: exp(-eta_k) is a geometric progression -- two exps
-                        // per row instead of G (the accumulated rounding, <= G ulp, is far inside the parity tolerance)
-                        double q = exp(-z);
+                    const double gc = S->gc[pw], grem = S->grem[pw], gh = S->gh[pw];
+                    if (fabs(z) + fabs(gh * w) < 40.0) {
+                        // eta_k = z + t_k w on a uniform grid: exp(-eta_k) is a geometric progression -- two exps per
+                        // row instead of G -- and the G reciprocals 1 / (1 + q_k) come from ONE division (prefix
+                        // products, invert the last, peel backwards).  Every factor is below e^40, so the product of
+                        // up to 12 stays finite; the accumulated rounding (a few tens of ulp) is far inside the parity
+                        // tolerance.
+                        double q[kLrMaxG], pre[kLrMaxG];
                         const double rho = exp(-fma(1.0, gc, grem) * w);
-                        for (int k = 0; k < nt; ++k) {
-                            const double sg = 1.0 / (1.0 + q);
-                            rp[k] = live ? sg - yy : 0.0;
-                            rp[nt + k] = live ? q * sg * sg * w : 0.0;  // sigma (1 - sigma) w with 1 - sigma = q sigma
-                            q *= rho;
+                        q[0] = exp(-z);
+                        pre[0] = 1.0 + q[0];
+#pragma unroll
+                        for (int k = 1; k < kLrMaxG; ++k) {
+                            q[k] = q[k - 1] * rho;
+                            pre[k] = (k < nt) ? pre[k - 1] * (1.0 + q[k]) : pre[k - 1];
                         }
+                        double inv = 1.0 / pre[kLrMaxG - 1];
+#pragma unroll
+                        for (int k = kLrMaxG - 1; k >= 0; --k)
+                            if (k < nt) {
+                                const double sg = (k > 0) ? inv * pre[k - 1] : inv;
+                                inv *= 1.0 + q[k];
+                                rp[k] = live ? sg - yy : 0.0;
+                                rp[nt + k] = live ? q[k] * sg * sg * w : 0.0;  // sigma (1 - sigma) w with 1 - sigma = q sigma
+                            }
                     } else {  // extreme logits: evaluate every node on its own
                         for (int k = 0; k < nt; ++k) {
                             const double kk = (double)k, tk = (k >= nt - 1) ? gh : fma(kk, gc, kk * grem);
@@ -203,34 +228,82 @@ __device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const Lr
                 }
             }
         }
-        __syncthreads();
-        // ---- acc += Xtile^T . R : A[m][k] = Xt[row0 + k][i0 + m], B[k][n] = R[row0 + k][n0 + n] ----
-        {
-            const double* ap = Xs + tig * d + mrot * 8 + gid;  // m-tiles mrot, mrot + 4, ... (the last may not exist)
-            const double* bp = sm + L.rs + tig * kLrNcs + gid;
-            const int n_a = (n_mt - mrot + 3) >> 2;  // m-tiles of this warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[kBarFullR + r.rs]);  // release: this warp's columns of the residual tile are written
+    }
+}
+
+// ---- consumer warpgroup: acc (d x columns) += Xtile^T . R over all tiles, then parked in shared memory ----
+//   A[m][k] = Xt[row0 + k][i0 + m], B[k][n] = R[row0 + k][n0 + n]
+// Work split (compile-time, so that no MMA is predicated -- a predicated mma.sync costs a WARPSYNC per group and ran the
+// loop 1.5x slower): every warp takes NA whole m-tiles {cw, cw + 4, ..} (a tile past the last one computes garbage that
+// is never stored); when n_mt % 4 == 1 (SPLIT) the odd last m-tile is split over the four warps by k-steps (two of the
+// eight each) so that every warp issues the same number of MMAs; its four partial sums are parked in separate row
+// blocks and added by the reader.
+template <int NT, int NA, bool SPLIT>
+__device__ __forceinline__ void lr_consume(const KernelParams& p, double* sm, const LrShared& L, uint32_t gbase, int ctid) {
+    const int d = p.d, lane = ctid & 31, cw = ctid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int64_t n = p.pot.n;
+    const int n_mt = (d + 7) / 8;                    // m-tiles (coordinates), <= 16
+    constexpr int kSlots = NA + (SPLIT ? 1 : 0);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
+    double acc[kSlots][NT][2];
+#pragma unroll
+    for (int a = 0; a < kSlots; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int64_t ntiles = (n + kLrRows - 1) / kLrRows;
+    for (int64_t tile = 0; tile < ntiles; ++tile) {
+        const LrRing r = lr_ring(gbase + (uint32_t)tile, L.xstages);
+        mbar_wait(&bar[kBarFullX + r.xs], r.xpar);
+        mbar_wait(&bar[kBarFullR + r.rs], r.rpar);
+        const double* ap = sm + L.Xt + r.xs * L.tile + tig * d + cw * 8 + gid;
+        const double* bp = sm + L.rs + r.rs * L.rs_tile + tig * kLrNcs + gid;
+        if constexpr (NA > 0) {
+            // Operands of k-step ks + 1 are loaded while the MMAs of k-step ks issue (register double buffer).  Rows
+            // past this warp's last real m-tile stay inside the rings, so the loads need no guard either.
+            double av[2][NA], bv[2][NT];
+            auto load = [&](int ks, int buf) {
+#pragma unroll
+                for (int b = 0; b < NT; ++b) bv[buf][b] = bp[4 * ks * kLrNcs + 8 * b];
+#pragma unroll
+                for (int a = 0; a < NA; ++a) av[buf][a] = ap[4 * ks * d + 32 * a];
+            };
+            load(0, 0);
 #pragma unroll
             for (int ks = 0; ks < kLrRows / 4; ++ks) {
-                double bv[NT];
+                const int cur = ks & 1;
+                if (ks + 1 < kLrRows / 4) load(ks + 1, cur ^ 1);
 #pragma unroll
-                for (int b = 0; b < NT; ++b) bv[b] = bp[4 * ks * kLrNcs + 8 * b];
+                for (int a = 0; a < NA; ++a)
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    if (a < n_a) {
-                        const double av = ap[4 * ks * d + 32 * a];
-#pragma unroll
-                        for (int b = 0; b < NT; ++b) dmma(acc[a][b][0], acc[a][b][1], av, bv[b]);
-                    }
+                    for (int b = 0; b < NT; ++b) dmma(acc[a][b][0], acc[a][b][1], av[cur][a], bv[cur][b]);
             }
         }
-        __syncthreads();  // tile consumed: its ring slot may be refilled, zw / rs may be overwritten
+        if constexpr (SPLIT) {  // k-steps 2 cw, 2 cw + 1 of the last m-tile
+            const double* as_ = sm + L.Xt + r.xs * L.tile + tig * d + (n_mt - 1) * 8 + gid;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int ks = 2 * cw + kk;
+                const double a_ = as_[4 * ks * d];
+#pragma unroll
+                for (int b = 0; b < NT; ++b) dmma(acc[NA][b][0], acc[NA][b][1], a_, bp[4 * ks * kLrNcs + 8 * b]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {  // this warp is done with both tiles
+            mbar_arrive(&bar[kBarEmptyR + r.rs]);
+            mbar_arrive(&bar[kBarEmptyX + r.xs]);
+        }
     }
-    // ---- accumulator fragments -> shared memory acc[i][col], overlaying the (now idle) tile ring ----
+    // ---- accumulator fragments -> shared memory acc[i][col], overlaying the (now idle) rings ----
+    group_barrier(3, 128);  // every consumer warp has finished reading the rings
     double* A = sm + L.Xt;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int mt = mrot + 4 * a;
-        if (mt < n_mt) {
+    for (int a = 0; a < NA; ++a) {
+        const int mt = cw + 4 * a;
+        if (mt < n_mt - (SPLIT ? 1 : 0)) {
 #pragma unroll
             for (int b = 0; b < NT; ++b) {
                 const int i = mt * 8 + gid, c = 8 * b + 2 * tig;
@@ -239,7 +312,15 @@ __device__ __noinline__ void lr_pass(const KernelParams& p, double* sm, const Lr
             }
         }
     }
-    __syncthreads();
+    if constexpr (SPLIT) {
+        const int i = (cw == 0 ? (n_mt - 1) * 8 : n_mt * 8 + (cw - 1) * 8) + gid;
+#pragma unroll
+        for (int b = 0; b < NT; ++b) {
+            const int c = 8 * b + 2 * tig;
+            A[i * L.acc_stride + c] = acc[NA][b][0];
+            A[i * L.acc_stride + c + 1] = acc[NA][b][1];
+        }
+    }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -248,20 +329,23 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_constant__ KernelParams p) {
+template <int NA, bool SPLIT>
+__global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __grid_constant__ KernelParams p) {
     extern __shared__ __align__(128) double sm[];
-    const int d = p.d, G = p.G, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int d = p.d, G = p.G, tid = threadIdx.x, lane = tid & 31;
+    const int wgroup = tid >> 7;                     // 0: consumers, 1 / 2: producers
+    const int w = (tid >> 5) & (kLrChains - 1);      // consumer warp w runs chain w
     const LrShared L = lr_layout(d);
     const int dp = (d + 7) / 8 * 8;
     const double inv_s2 = p.pot.inv_s2;
     LrSched* S = reinterpret_cast<LrSched*>(sm + L.sched);
     const int64_t c_raw = (int64_t)blockIdx.x * kLrChains + w;  // warp w runs chain c
-    const bool valid = c_raw < p.n_chains;
+    const bool valid = wgroup == 0 && c_raw < p.n_chains;
     const int64_t c = valid ? c_raw : 0;
 
     // ---- shared state: xv[k][8] holds (x, v) of chain w in columns (2w, 2w+1); it is also the z/w B operand ----
     for (int e = tid; e < (dp + 4) * 8; e += kLrThreads) sm[L.xv + e] = 0.0;
-    for (int e = tid; e < 2 * L.tile + kLrRows * kLrNcs + 32; e += kLrThreads) sm[L.Xt + e] = 0.0;  // ring, slack, rs
+    for (int e = tid; e < L.xstages * L.tile + kLrRStages * L.rs_tile; e += kLrThreads) sm[L.Xt + e] = 0.0;  // rings, slack
     __syncthreads();
     if (valid)
         for (int i = lane; i < d; i += 32) {
@@ -269,14 +353,21 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
             sm[L.xv + i * 8 + 2 * w + 1] = p.sv[c * d + i];
         }
     fence_async_smem();  // order these generic-proxy writes before the TMA (async-proxy) writes into the same buffers
-    uint32_t phase[2] = {0u, 0u};
     if (tid == 0) {
         uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        for (int s = 0; s < kLrXStages; ++s) {
+            mbar_init(&bar[kBarFullX + s], 1);             // the feeding thread's expect-tx arrival (+ the TMA bytes)
+            mbar_init(&bar[kBarEmptyX + s], kLrChains);    // one arrival per consumer warp
+        }
+        for (int s = 0; s < kLrRStages; ++s) {
+            mbar_init(&bar[kBarFullR + s], 4);             // one arrival per warp of the producer group
+            mbar_init(&bar[kBarEmptyR + s], kLrChains);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
+    uint32_t gbase = 0;  // tiles streamed so far, modulo 120 (see lr_ring)
+    const int64_t ntiles_pass = (p.pot.n + kLrRows - 1) / kLrRows;
     // ---- PDMPState scalars of chain w (warp-uniform registers) ----
     double t = p.st[c], horizon = p.shorizon[c], ar = p.sar[c];
     int status = valid ? p.status[c] : 0;
@@ -337,6 +428,26 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         }
         return;
     }
+
+    if (wgroup != 0) {
+        // ---- producer warpgroups: mirror the consumers' CTA-wide barriers, work only inside the passes ----
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+        while (true) {
+            __syncthreads();                       // requests posted
+            __syncthreads();                       // schedule packed
+            const int any = __syncthreads_or(0);
+            if (!any) break;
+            if (S->n_cols == 0) continue;
+            fence_async_smem();
+            __syncthreads();                       // pass start: the accumulator overlay of the last pass is dead
+            lr_produce(p, sm, L, gbase, wgroup - 1, tid & 127);
+            gbase = (gbase + (uint32_t)(ntiles_pass % 120)) % 120u;
+            __syncthreads();                       // pass end: accumulators parked
+            __syncthreads();                       // accumulators consumed
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
 
     // grid nodes of the current bound, UpperBound.jl:204 (same construction as chain.cuh:make_grid)
     double gc = 0, grem = 0, gh = 0, step = 0;
@@ -416,17 +527,33 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
         if (S->n_cols == 0) continue;  // only fall-through transitions this round
 
         // ---- 2. one pass over X for all requests (specialised on the number of 8-column tiles) ----
+        // The accumulators of the previous pass overlaid the rings through the generic proxy: order that before the
+        // TMA (async proxy) refills them.
+        fence_async_smem();
+        __syncthreads();
         switch ((S->n_cols + 7) >> 3) {
-            case 1: lr_pass<1>(p, sm, L, phase); break;
-            case 2: lr_pass<2>(p, sm, L, phase); break;
-            case 3: lr_pass<3>(p, sm, L, phase); break;
-            case 4: lr_pass<4>(p, sm, L, phase); break;
-            case 5: lr_pass<5>(p, sm, L, phase); break;
-            case 6: lr_pass<6>(p, sm, L, phase); break;
-            case 7: lr_pass<7>(p, sm, L, phase); break;
-            default: lr_pass<8>(p, sm, L, phase); break;
+            case 1: lr_consume<1, NA, SPLIT>(p, sm, L, gbase, tid); break;
+            case 2: lr_consume<2, NA, SPLIT>(p, sm, L, gbase, tid); break;
+            case 3: lr_consume<3, NA, SPLIT>(p, sm, L, gbase, tid); break;
+            case 4: lr_consume<4, NA, SPLIT>(p, sm, L, gbase, tid); break;
+            case 5: lr_consume<5, NA, SPLIT>(p, sm, L, gbase, tid); break;
+            case 6: lr_consume<6, NA, SPLIT>(p, sm, L, gbase, tid); break;
+            case 7: lr_consume<7, NA, SPLIT>(p, sm, L, gbase, tid); break;
+            default: lr_consume<8, NA, SPLIT>(p, sm, L, gbase, tid); break;
         }
-        const double* A = sm + L.Xt;
+        gbase = (gbase + (uint32_t)(ntiles_pass % 120)) % 120u;
+        __syncthreads();  // pass end: every warp's accumulators are parked
+        const double* Aov = sm + L.Xt;
+        const int n_mt = (d + 7) / 8;
+        constexpr bool split = SPLIT;
+        auto A = [&](int i, int col) -> double {  // accumulator (i, col); the split last m-tile is the sum of four partials
+            double v = Aov[i * L.acc_stride + col];
+            if (split && i >= (n_mt - 1) * 8) {
+                const double* q = Aov + (n_mt * 8 + (i - (n_mt - 1) * 8)) * L.acc_stride + col;
+                v += q[0] + q[8 * L.acc_stride] + q[16 * L.acc_stride];
+            }
+            return v;
+        };
         const int col0 = S->col0[w];
 
         // ---- 3. every chain consumes its columns ----
@@ -442,8 +569,8 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
                 for (int k = 0; k < kLrMaxG; ++k)
                     if (k < G) {
                         const double tk = grid_t(k);
-                        const double g = A[i * L.acc_stride + col0 + k] + (xi + tk * vi) * inv_s2;
-                        const double hv = A[i * L.acc_stride + col0 + G + k] + vi * inv_s2;
+                        const double g = A(i, col0 + k) + (xi + tk * vi) * inv_s2;
+                        const double hv = A(i, col0 + G + k) + vi * inv_s2;
                         double val = g * vi, dval = hv * vi;
                         if (!p.signed_bound) { dval = (0.0 > val) ? 0.0 : dval; val = (val > 0.0 ? val : 0.0); }
                         if (k > 0) {  // QUIRK-preserving tangent formula (UpperBound.jl:229-241)
@@ -486,7 +613,7 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
             double part = 0.0;
             for (int i = lane; i < d; i += 32) {
                 const double vi = vr(i);
-                const double g = A[i * L.acc_stride + col0] + (xr(i) + tp * vi) * inv_s2;
+                const double g = A(i, col0) + (xr(i) + tp * vi) * inv_s2;
                 const double y = g * vi;
                 const double l = (y > 0.0 ? y : 0.0);
                 lam[i] = l;
@@ -542,7 +669,7 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
                 else if (tp > horizon) { flow(horizon); ts += horizon; hh += 1; need_build = true; }  // move_to_horizon2!
             }
         }
-        __syncthreads();  // accumulators consumed before the next pass reuses the ring
+        __syncthreads();  // accumulators consumed before the next pass reuses the rings
     }
 
     if (!valid) return;
@@ -558,13 +685,30 @@ __global__ void __launch_bounds__(kLrThreads) logreg_zigzag_kernel(const __grid_
     }
 }
 
-cudaError_t launch_logreg_zigzag(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
+template <int NA, bool SPLIT>
+static cudaError_t launch_variant(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(logreg_zigzag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(logreg_zigzag_kernel<NA, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    logreg_zigzag_kernel<<<grid, kLrThreads, smem, stream>>>(p);
+    logreg_zigzag_kernel<NA, SPLIT><<<grid, kLrThreads, smem, stream>>>(p);
     return cudaGetLastError();
+}
+cudaError_t launch_logreg_zigzag(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
+    const int n_mt = (p.d + 7) / 8;              // m-tiles of 8 coordinates (d <= 128: at most 16)
+    const bool split = (n_mt & 3) == 1;          // see lr_consume
+    const int na = split ? (n_mt - 1) / 4 : (n_mt + 3) / 4;
+    switch (na * 2 + (split ? 1 : 0)) {
+        case 1: return launch_variant<0, true>(p, grid, smem, stream);
+        case 3: return launch_variant<1, true>(p, grid, smem, stream);
+        case 5: return launch_variant<2, true>(p, grid, smem, stream);
+        case 7: return launch_variant<3, true>(p, grid, smem, stream);
+        case 2: return launch_variant<1, false>(p, grid, smem, stream);
+        case 4: return launch_variant<2, false>(p, grid, smem, stream);
+        case 6: return launch_variant<3, false>(p, grid, smem, stream);
+        case 8: return launch_variant<4, false>(p, grid, smem, stream);
+    }
+    return cudaErrorInvalidValue;
 }
 int logreg_chains_per_block() { return kLrChains; }
 
