@@ -569,3 +569,20 @@ def test_edge_sizes_match_oracle(p):
         p.ZigZag(3, p.GaussStd(), grid_size=1)
     with pytest.raises(p.UnsupportedError):
         p.ZigZag(3, p.GaussStd(), grid_size=65)
+
+
+@pytest.mark.parametrize("d", [20, 36, 60, 70, 90, 128])
+def test_logreg_every_mma_work_split(p, d):
+    """The logistic-regression kernel is compiled once per (whole m-tiles per warp, split last tile) combination
+    (logreg.cu: lr_consume); d = 5, 8, 13, 100 are covered by the cases above, these dimensions reach the other
+    variants (d = 128 also runs with the shallower X ring).  Free-running parity against the C oracle."""
+    from oracle_cases import logreg_data
+    n, n_sk, nch = 150, 40, 3
+    X, y, s0 = logreg_data(n, d)
+    pp = np.concatenate([[float(n), s0], X.ravel(), y])
+    x0, v0, tape = case_inputs("logreg_split%d" % d, 0, d, n_sk, n_chains=nch)
+    r = oc.sample_skeleton(oc.make_cfg(0, 5, d, pp, grid_size=5), n_sk, x0, v0, tape=tape)
+    h = p.sample_skeleton(p.ZigZagAD(d, p.LogReg(X, y, s0), grid_size=5), n_sk, x0, v0, tape=tape)
+    assert (r.status == 0).all()
+    assert relerr(h.X, r.X) < 1e-9 and relerr(h.t, r.t) < 1e-9 and np.array_equal(h.V, r.V)
+    assert np.array_equal(h.rejected, r.rejected) and np.array_equal(h.hitting_horizon, r.hitting_horizon)
