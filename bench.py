@@ -299,7 +299,11 @@ def main():
     launches = lib.pdmpflux_launch_count() - launches0
     elapsed = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=f64, device=dev)
     kern = torch.tensor([sum(a.elapsed_time(b) for a, b in kern_ms) * 1e-3 / len(kern_ms)], dtype=f64, device=dev)
+    per_rank_kernel_ms = [float(kern) * 1e3]
     if world > 1:
+        gathered = [torch.empty_like(kern) for _ in range(world)]
+        dist.all_gather(gathered, kern)
+        per_rank_kernel_ms = [float(g) * 1e3 for g in gathered]
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern, op=dist.ReduceOp.MAX)
     elapsed = float(elapsed); kern = float(kern)
@@ -336,7 +340,8 @@ def main():
                        "draws": "philox4x32-10 keyed (seed=2024, chain, event)", "stored": "full PDMPHistory row",
                        "l2": "outputs per step (%.2f GB) exceed the 126 MB L2" % (nch * n_ev * bytes_per_event(d) / 1e9)},
             "ess_per_s": ess_per_s, "ess_definition": "min over coordinates of C * Var_pi(x_i) / Var_c(chain time-average of x_i), per step window",
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "host_cpus": numa_cpus}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "host_cpus": numa_cpus,
+            "per_rank_kernel_ms": per_rank_kernel_ms}
 
     chains.close()
     del bufs, view

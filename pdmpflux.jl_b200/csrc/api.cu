@@ -446,6 +446,13 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
         const int lcpb = logreg_chains_per_block();
         ch->grid = (unsigned)((n_chains + lcpb - 1) / lcpb);
         ch->smem = logreg_smem_bytes(d, s->cfg.grid_size);
+        // (z, w) = (X x, X v) cache, [chain][32-row tile][row][2] (logreg.cu: lr_produce).  Optional: when it does not
+        // fit (or PDMPFLUX_LOGREG_NO_ZW_CACHE=1) the kernel recomputes z, w in every pass.
+        const int64_t ntiles = (s->pot->pp.n + 31) / 32;
+        const size_t zw_bytes = (size_t)n_chains * (size_t)ntiles * 64 * sizeof(double);
+        const char* off = getenv("PDMPFLUX_LOGREG_NO_ZW_CACHE");
+        if (!(off && off[0] == '1') && zw_bytes <= ((size_t)32 << 30) && ch->scratch.alloc(zw_bytes) != cudaSuccess)
+            (void)cudaGetLastError();  // out of memory: run without the cache
     }
     if (ch->smem > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "dimension too large for the shared-memory state layout");
     CUDA_TRY(ch->x.alloc(sizeof(double) * d * n_chains));

@@ -87,6 +87,10 @@ struct LrSched {
     int nt[kLrChains];             // times granted to chain c this pass (0 when it has to wait for the next one)
     double tp[kLrChains];          // rate request: the proposal time
     double gc[kLrChains], grem[kLrChains], gh[kLrChains];  // bound request: its time grid (see grid_t)
+    // (z, w) cache in global memory (see lr_produce): mode 1 = the chain's cached z = X x0, w = X v0 are valid up to the
+    // pending move x = x0 + pdt v0 followed by the flip of coordinate pm (whose velocity was pvm); mode 0 = recompute
+    int mode[kLrChains], pm[kLrChains];
+    double pdt[kLrChains], pvm[kLrChains];
 };
 // mbarriers: full_x[s] (TMA landed), empty_x[s] (consumers done with the tile), full_rs[r] (residual tile written),
 // empty_rs[r] (consumers done with it)
@@ -156,6 +160,22 @@ __device__ void lr_produce(const KernelParams& p, double* sm, const LrShared& L,
         bulk_load(sm + L.ybuf + r.xs * kLrRows, p.pot.vec2 + r0, yb, &bar[kBarFullX + r.xs]);
     };
     if (ptid == 0 && pg < ntiles) issue(pg);
+    // (z, w) = (X x, X v) of a chain change between two of its requests only by a straight move and at most one flip:
+    // z += dt w, w -= 2 v_m X[:, m].  When every chain asking in this pass has valid cached rows (global memory,
+    // [chain][tile][row][2], streamed with evict-first hints so that X keeps the L2) the 100-MMA z/w product of the
+    // tile is skipped and each producer warp updates its own chain's rows in registers; any chain without a valid
+    // cache (first request of a launch, periodic exact refresh) makes the pass recompute -- and re-cache -- all of them.
+    bool use_dmma = p.scratch == nullptr;
+#pragma unroll
+    for (int c = 0; c < kLrChains; ++c) use_dmma |= (S->nt[c] > 0 && S->mode[c] == 0);
+    const int my_nt = S->nt[pw];
+    double2* cache = nullptr;
+    if (p.scratch != nullptr && my_nt > 0)
+        cache = reinterpret_cast<double2*>(p.scratch) + (((int64_t)blockIdx.x * kLrChains + pw) * ntiles) * kLrRows + lane;
+    const double pdt = S->pdt[pw], pvm2 = 2.0 * S->pvm[pw];
+    const int pm = S->pm[pw];
+    double2 zw_next = make_double2(0.0, 0.0);
+    if (!use_dmma && cache != nullptr && pg < ntiles) zw_next = __ldcs(cache + (int64_t)pg * kLrRows);
     for (int64_t tile = pg; tile < ntiles; tile += 2) {
         const LrRing r = lr_ring(gbase + (uint32_t)tile, L.xstages);
         const int rows = (int)min((int64_t)kLrRows, n - tile * kLrRows);
@@ -164,6 +184,16 @@ __device__ void lr_produce(const KernelParams& p, double* sm, const LrShared& L,
         const double* Xs = sm + L.Xt + r.xs * L.tile;
         const double* ys = sm + L.ybuf + r.xs * kLrRows;
         double* zwb = sm + L.zw + (pg * 2 + (int)((tile >> 1) & 1)) * (kLrRows * 8);
+        double z = 0.0, w = 0.0;  // this lane's row of this warp's chain
+        if (!use_dmma) {
+            if (cache != nullptr) {
+                z = zw_next.x; w = zw_next.y;
+                if (tile + 2 < ntiles) zw_next = __ldcs(cache + (tile + 2) * kLrRows);  // next own tile, one iteration ahead
+                z = fma(pdt, w, z);
+                if (pm >= 0) w = fma(-pvm2, Xs[lane * d + pm], w);
+                if (pdt != 0.0 || pm >= 0) __stcs(cache + tile * kLrRows, make_double2(z, w));
+            }
+        } else {
         // ---- (z, w) of the four chains for the tile: DMMA with B = [x1 v1 .. x4 v4] (k x 8); 8 rows per warp ----
         {
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: halves the dependent MMA chain
@@ -180,13 +210,16 @@ __device__ void lr_produce(const KernelParams& p, double* sm, const LrShared& L,
             zr[1] = c1 + e1;
         }
         group_barrier(1 + pg, 128);
+        z = zwb[lane * 8 + 2 * pw]; w = zwb[lane * 8 + 2 * pw + 1];
+        if (cache != nullptr) __stcs(cache + tile * kLrRows, make_double2(z, w));
+        }
         mbar_wait(&bar[kBarEmptyR + r.rs], r.rpar ^ 1u);  // consumers are done with the tile that used this slot
         // ---- residual columns: warp c evaluates chain c's requested times, lane = row of the tile ----
         {
-            const int nt = S->nt[pw];
+            const int nt = my_nt;
             if (nt) {
                 const bool live = lane < rows;
-                const double z = zwb[lane * 8 + 2 * pw], w = zwb[lane * 8 + 2 * pw + 1], yy = ys[lane];
+                const double yy = ys[lane];
                 double* rp = sm + L.rs + r.rs * L.rs_tile + lane * kLrNcs + S->col0[pw];
                 if (nt == 1) {  // rate at the proposal time
                     const double sg = 1.0 / (1.0 + exp(-(z + S->tp[pw] * w)));
@@ -431,7 +464,7 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
 
     if (wgroup != 0) {
         // ---- producer warpgroups: mirror the consumers' CTA-wide barriers, work only inside the passes ----
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
         while (true) {
             __syncthreads();                       // requests posted
             __syncthreads();                       // schedule packed
@@ -464,8 +497,14 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
         tp_out = grid_t(idx - 1) + (e - cum[idx - 1]) / (cum[idx] - cum[idx - 1]) * step;
         lb_out = box[idx - 1];
     };
+    // (z, w) cache bookkeeping of this chain (see lr_produce): what happened to (x, v) since its rows were last written
+    const bool cache_on = p.scratch != nullptr;
+    bool cache_valid = false;
+    int served = 0, pend_m = -1;
+    double pend_dt = 0.0, pend_vm = 0.0;
     auto flow = [&](double tt) {  // ZigZagSamplers.jl:80
         for (int i = lane; i < d; i += 32) xr(i) += vr(i) * tt;
+        pend_dt += tt;
         __syncwarp();
     };
 
@@ -519,7 +558,10 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
         if (lane == 0 && req != REQ_NONE) {  // the times this chain wants evaluated
             S->tp[w] = tp;
             S->gc[w] = gc; S->grem[w] = grem; S->gh[w] = gh;
+            S->mode[w] = (cache_valid && (served & 63) != 63) ? 1 : 0;  // every 64th request recomputes exactly
+            S->pdt[w] = pend_dt; S->pm[w] = pend_m; S->pvm[w] = pend_vm;
         }
+        if (req != REQ_NONE) { cache_valid = cache_on; pend_dt = 0.0; pend_m = -1; ++served; }  // rows current after this pass
         // the CTA goes on while any chain has work left (a request, or a pending fall-through transition)
         const int any = __syncthreads_or(live ? 1 : 0);
         if (!any) break;
@@ -636,12 +678,15 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
                 } else {
                     const double uS = rand_uniform() * lt;  // categorical draw against the rates just computed
                     flow(tp);
+                    int m = d - 1;
                     if (lane == 0) {                         // first index with cumulative lambda > u S, else the last
                         double cp = 0.0;
-                        int m = d - 1;
                         for (int i = 0; i < d; ++i) { cp += lam[i]; if (cp > uS) { m = i; break; } }
-                        vr(m) = -vr(m);
                     }
+                    m = __shfl_sync(0xffffffffu, m, 0);
+                    pend_m = m; pend_vm = vr(m);
+                    __syncwarp();
+                    if (lane == 0) vr(m) = -pend_vm;
                     __syncwarp();
                     t = t + tp + ts;
                     ts = 0.0; tp = 0.0;

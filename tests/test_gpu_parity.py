@@ -586,3 +586,25 @@ def test_logreg_every_mma_work_split(p, d):
     assert (r.status == 0).all()
     assert relerr(h.X, r.X) < 1e-9 and relerr(h.t, r.t) < 1e-9 and np.array_equal(h.V, r.V)
     assert np.array_equal(h.rejected, r.rejected) and np.array_equal(h.hitting_horizon, r.hitting_horizon)
+
+
+def test_logreg_zw_cache_matches_recompute(p):
+    """The cached / incrementally updated (z, w) = (X x, X v) rows (logreg.cu: lr_produce) against recomputing them by
+    DMMA in every pass: same skeleton to 1e-10 over several hundred events (long enough to cross the periodic exact
+    refresh), identical discrete decisions."""
+    from oracle_cases import logreg_data
+    n, d, n_sk, nch = 333, 21, 500, 9
+    X, y, s0 = logreg_data(n, d)
+    g = np.random.default_rng(12)
+    x0 = 0.3 * g.standard_normal((nch, d)); v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0)
+    outs = []
+    for off in ("0", "1"):
+        os.environ["PDMPFLUX_LOGREG_NO_ZW_CACHE"] = off
+        try:
+            s = p.ZigZagAD(d, p.LogReg(X, y, s0), grid_size=7)
+            outs.append(p.sample_skeleton(s, n_sk, x0, v0, seed=99))
+        finally:
+            os.environ.pop("PDMPFLUX_LOGREG_NO_ZW_CACHE")
+    a, b = outs
+    assert relerr(a.X, b.X) < 1e-10 and relerr(a.t, b.t) < 1e-10 and np.array_equal(a.V, b.V)
+    assert np.array_equal(a.rejected, b.rejected) and np.array_equal(a.hitting_horizon, b.hitting_horizon)
