@@ -465,8 +465,11 @@ def e2e(p, sampler, name, nch, n_ev, world, dev):
     ok = bool(np.isfinite(arrs["t"][:, -1]).all())
     for ptr in ptrs:
         lib.pdmpflux_host_free(ptr)
-    return {"value": world * nch * n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": 2 * nch * d * 8,
-            "d2h_bytes_per_step": nch * n_sk * bytes_per_event(d), "ms_per_step": dt * 1e3, "finite": ok,
+    h2d, d2h = C.c_int64(0), C.c_int64(0)
+    lib.pdmpflux_last_transfer_bytes(C.byref(h2d), C.byref(d2h))   # counted by the library from the copies it issued
+    return {"value": world * nch * n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": int(h2d.value),
+            "d2h_bytes_per_step": int(d2h.value), "history_bytes_per_step": nch * n_sk * bytes_per_event(d),
+            "ms_per_step": dt * 1e3, "finite": ok,
             "timing": "median of %d individually timed calls (min %.1f ms, max %.1f ms)" % (reps, times[0] * 1e3, times[-1] * 1e3),
             "call": "pdmpflux_sample_skeleton (host buffers, pinned)"}
 

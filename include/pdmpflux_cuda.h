@@ -240,6 +240,11 @@ int pdmpflux_host_free(void* ptr);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 int64_t pdmpflux_launch_count(void);
 
+/* bytes that crossed PCIe in the last host-buffer sample_skeleton call of this process (initial states in; history
+ * out -- for Zig-Zag the V rows travel as sign bits and are rebuilt on the host, so this is less than the size of
+ * the history).  bench.py's e2e.{h2d,d2h}_bytes_per_step. */
+int pdmpflux_last_transfer_bytes(int64_t* h2d, int64_t* d2h);
+
 #ifdef __cplusplus
 }
 #endif

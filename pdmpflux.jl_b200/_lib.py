@@ -110,6 +110,7 @@ SIGNATURES = {
     "pdmpflux_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "pdmpflux_host_free": (C.c_int, [C.c_void_p]),
     "pdmpflux_launch_count": (C.c_int64, []),
+    "pdmpflux_last_transfer_bytes": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -11,7 +11,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__linux__)
+#include <sched.h>
+#endif
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "common.cuh"
 #include "launch.cuh"
@@ -22,6 +29,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // PCIe bytes of the last host-buffer sample_skeleton call
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -73,7 +81,16 @@ struct Workspace {
     Slab slab[2];
     Slab scal;  // full-length scalar columns (t, horizon, ar, error_value_ar, counters) of the host pipeline
     cudaStream_t copy_stream = nullptr;
-    ~Workspace() { if (copy_stream) cudaStreamDestroy(copy_stream); }
+    // Zig-Zag host path: sign bits of every V row of the run, [slice][chain][column in slice][words], device + pinned host
+    DevBuf vbits;
+    uint32_t* vbits_host = nullptr;
+    size_t vbits_host_bytes = 0;
+    std::vector<cudaEvent_t> slice_copied;  // one event per slice: its sign bits have reached the host
+    ~Workspace() {
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (vbits_host) cudaFreeHost(vbits_host);
+        for (cudaEvent_t e : slice_copied) cudaEventDestroy(e);
+    }
 };
 
 struct pdmpflux_sampler_s {
@@ -195,6 +212,25 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     return PDMPFLUX_OK;
 }
 
+// Zig-Zag velocities never change magnitude (ZigZagSamplers.jl:101-107 only flips signs), so on the host-buffer path a
+// V row of d doubles crosses PCIe as d sign bits and is rebuilt bit-exactly on the host as copysign(|vinit_i|, bit).
+// One warp per (chain, column) row: coalesced reads, one ballot per 32 coordinates.  bits: [chain][slab column][words].
+__global__ void __launch_bounds__(256) pack_signs_kernel(const double* __restrict__ V, int d, int64_t n_chains, int64_t n,
+                                                         int64_t ld, int words, uint32_t* __restrict__ bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_chains * n; r += nwarps) {
+        const int64_t c = r / n, k = r - c * n;
+        const double* row = V + (c * ld + k) * d;
+        for (int wd = 0; wd < words; ++wd) {
+            const int i = 32 * wd + lane;
+            const bool neg = i < d && (__double2hiint(row[i]) < 0);
+            const uint32_t m = __ballot_sync(0xffffffffu, neg);
+            if (lane == 0) bits[(c * ld + k) * words + wd] = m;
+        }
+    }
+}
+
 // ---- sample_from_skeleton (src/sample.jl:475-513) -------------------------------------------------------
 // One thread per output element (sample j, coordinate a) of one chain; neighbouring threads share j, so the
 // binary search over the chain's event times is a broadcast and X/V/out accesses are coalesced.
@@ -290,6 +326,11 @@ extern "C" {
 int pdmpflux_version(void) { return PDMPFLUX_VERSION; }
 const char* pdmpflux_last_error(void) { return g_err.c_str(); }
 int64_t pdmpflux_launch_count(void) { return g_launches.load(); }
+int pdmpflux_last_transfer_bytes(int64_t* h2d, int64_t* d2h) {
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+    return PDMPFLUX_OK;
+}
 
 int pdmpflux_device_count(int* count) {
     if (!count) return fail(PDMPFLUX_ERR_ARGUMENT, "count is NULL");
@@ -713,6 +754,96 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         sc.view.hitting_horizon = hist->hitting_horizon ? sc.hh.as<int32_t>() : nullptr;
         sc.view.n_cols = ldS; sc.view.on_device = 1;
     }
+    // Zig-Zag: V rows travel as sign bits (pack_signs_kernel) and are rebuilt on the host by worker threads while the
+    // later slices still run; everything else (and PDMPFLUX_NO_VBITS=1) copies the V rows as they are.
+    // Rebuilding 8 d bytes per event on the host only pays when enough CPUs are free for it (measured: 16 threads beat
+    // the plain copy by 1.2-1.3x on a PCIe Gen5 host, 8 threads lose), so it needs >= 12 usable CPUs unless
+    // PDMPFLUX_VBITS=1 forces it; PDMPFLUX_NO_VBITS=1 (or PDMPFLUX_VBITS=0) turns it off.
+    unsigned avail_cpus = std::max<unsigned>(1, std::thread::hardware_concurrency());
+#if defined(__linux__)
+    {
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) avail_cpus = std::max(1, CPU_COUNT(&set));
+    }
+#endif
+    const char* no_vbits = std::getenv("PDMPFLUX_NO_VBITS");
+    const char* force_vbits = std::getenv("PDMPFLUX_VBITS");
+    bool vbits = hist->V && s->kind == PDMPFLUX_ZIGZAG && avail_cpus >= 12;
+    if (force_vbits) vbits = hist->V && s->kind == PDMPFLUX_ZIGZAG && force_vbits[0] == '1';
+    if (no_vbits && no_vbits[0] == '1') vbits = false;
+    const int vwords = (d + 31) / 32;
+    const int64_t n_slices = (n_sk + slice - 1) / slice;
+    const size_t vstride = (size_t)n_chains * slice * vwords;  // words per slice
+    std::vector<double> absv;
+    int n_threads = 1;
+    if (vbits) {
+        absv.resize((size_t)n_chains * d);
+        for (size_t e = 0; e < absv.size(); ++e) absv[e] = std::fabs(vinit[e]);
+        n_threads = (int)std::min<unsigned>(16, avail_cpus);
+        if (const char* e = std::getenv("PDMPFLUX_HOST_THREADS")) n_threads = std::max(1, std::atoi(e));
+        n_threads = (int)std::min<int64_t>(n_threads, n_chains);
+        const size_t vb = sizeof(uint32_t) * vstride * (size_t)n_slices;
+        CUDA_TRY(ensure(ws.vbits, true, vb));
+        if (ws.vbits_host_bytes < vb) {
+            if (ws.vbits_host) { cudaFreeHost(ws.vbits_host); ws.vbits_host = nullptr; ws.vbits_host_bytes = 0; }
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ws.vbits_host), vb, cudaHostAllocDefault));
+            ws.vbits_host_bytes = vb;
+        }
+        while ((int64_t)ws.slice_copied.size() < n_slices) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ws.slice_copied.push_back(e);
+        }
+    }
+    // worker t rebuilds the V rows of chains [c0, c1) slice by slice, as soon as each slice's bits are on the host
+    std::atomic<int64_t> enqueued{0};
+    std::atomic<bool> abort_workers{false};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    auto worker = [&](int64_t c0, int64_t c1) {
+        cudaSetDevice(cur_dev);
+        for (int64_t it = 0; it < n_slices; ++it) {
+            while (enqueued.load(std::memory_order_acquire) <= it) {
+                if (abort_workers.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            if (cudaEventSynchronize(ws.slice_copied[(size_t)it]) != cudaSuccess) return;
+            const int64_t k0 = it * slice, n = std::min<int64_t>(slice, n_sk - k0);
+            const uint32_t* bits = ws.vbits_host + (size_t)it * vstride;
+            for (int64_t c = c0; c < c1; ++c) {
+                const uint64_t* au = reinterpret_cast<const uint64_t*>(absv.data() + (size_t)c * d);  // |v| >= 0: OR the sign in
+                for (int64_t k = 0; k < n; ++k) {
+                    const uint32_t* w = bits + ((size_t)c * slice + k) * vwords;
+                    uint64_t* ou = reinterpret_cast<uint64_t*>(hist->V + ((size_t)c * hist->n_cols + k0 + k) * d);
+                    int i = 0;
+#if defined(__x86_64__)
+                    if ((reinterpret_cast<uintptr_t>(ou) & 15) == 0) {  // two coordinates per streaming (write-combining) store
+                        alignas(16) static const uint64_t kMask[4][2] = {{0, 0}, {1ull << 63, 0}, {0, 1ull << 63}, {1ull << 63, 1ull << 63}};
+                        for (; i + 2 <= d; i += 2) {
+                            const uint32_t two = (w[i >> 5] >> (i & 31)) & 3u;
+                            const __m128i m = _mm_load_si128(reinterpret_cast<const __m128i*>(kMask[two]));
+                            const __m128i av = _mm_loadu_si128(reinterpret_cast<const __m128i*>(au + i));
+                            _mm_stream_si128(reinterpret_cast<__m128i*>(ou + i), _mm_or_si128(av, m));
+                        }
+                    }
+#endif
+                    for (; i < d; ++i) ou[i] = au[i] | ((uint64_t)((w[i >> 5] >> (i & 31)) & 1u) << 63);
+                }
+            }
+#if defined(__x86_64__)
+            _mm_sfence();
+#endif
+        }
+    };
+    struct Workers {  // joined on every exit path
+        std::vector<std::thread> pool;
+        std::atomic<bool>* abort_flag;
+        bool finished = false;
+        void finish() { for (auto& th : pool) th.join(); pool.clear(); finished = true; }
+        ~Workers() { if (!finished) { abort_flag->store(true); finish(); } }
+    } workers{{}, &abort_workers};
+    if (vbits)
+        for (int t = 0; t < n_threads; ++t) workers.pool.emplace_back(worker, n_chains * t / n_threads, n_chains * (t + 1) / n_threads);
     for (int i = 0; i < n_slabs; ++i) {
         Slab& b = slab[i];
         CUDA_TRY(ensure(b.X, hist->X, sizeof(double) * d * n_chains * slice));
@@ -767,8 +898,21 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         }
         CUDA_TRY(cudaEventRecord(b.done, stream));
         CUDA_TRY(cudaStreamWaitEvent(copy_stream, b.done, 0));
+        if (vbits) {
+            pack_signs_kernel<<<592, 256, 0, stream>>>(b.view.V, d, n_chains, n, slice, vwords,
+                                                       ws.vbits.as<uint32_t>() + (size_t)it * vstride);
+            CUDA_TRY(cudaGetLastError());
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaEventRecord(b.done, stream));
+            CUDA_TRY(cudaStreamWaitEvent(copy_stream, b.done, 0));
+        }
         if (hist->X) CUDA_TRY(copy2d(hist->X, b.view.X, sizeof(double) * d, slice, k0, n));
-        if (hist->V) CUDA_TRY(copy2d(hist->V, b.view.V, sizeof(double) * d, slice, k0, n));
+        if (vbits) {
+            CUDA_TRY(cudaMemcpyAsync(ws.vbits_host + (size_t)it * vstride, ws.vbits.as<uint32_t>() + (size_t)it * vstride,
+                                     sizeof(uint32_t) * vstride, cudaMemcpyDeviceToHost, copy_stream));
+            CUDA_TRY(cudaEventRecord(ws.slice_copied[(size_t)it], copy_stream));
+            enqueued.store(it + 1, std::memory_order_release);
+        } else if (hist->V) CUDA_TRY(copy2d(hist->V, b.view.V, sizeof(double) * d, slice, k0, n));
         if (!full_scalars) {
             if (hist->t) CUDA_TRY(copy2d(hist->t, b.view.t, sizeof(double), slice, k0, n));
             if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, b.view.horizon, sizeof(double), slice, k0, n));
@@ -795,6 +939,17 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaStreamSynchronize(copy_stream));
+    workers.finish();  // the V rows of the last slices
+    {   // what actually crossed PCIe (bench.py reports it next to the end-to-end number)
+        const int64_t cols = n_chains * n_sk;
+        int64_t out = cols * ((hist->X ? 8 * d : 0) + (hist->t ? 8 : 0) + (hist->horizon ? 8 : 0) + (hist->ar ? 8 : 0) +
+                              (hist->error_value_ar ? 40 : 0) + (hist->errored_bound ? 4 : 0) + (hist->rejected ? 4 : 0) +
+                              (hist->hitting_horizon ? 4 : 0));
+        if (vbits) out += (int64_t)(sizeof(uint32_t) * vstride * (size_t)n_slices);
+        else if (hist->V) out += cols * 8 * d;
+        g_d2h_bytes.store(out);
+        g_h2d_bytes.store(2 * 8 * (int64_t)d * n_chains);
+    }
     return finish(pdmpflux_chains_status(ch, hist->status, hist->tape_pos, hist->counters));
 }
 

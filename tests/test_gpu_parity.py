@@ -608,3 +608,30 @@ def test_logreg_zw_cache_matches_recompute(p):
     a, b = outs
     assert relerr(a.X, b.X) < 1e-10 and relerr(a.t, b.t) < 1e-10 and np.array_equal(a.V, b.V)
     assert np.array_equal(a.rejected, b.rejected) and np.array_equal(a.hitting_horizon, b.hitting_horizon)
+
+
+@pytest.mark.parametrize("d,nch,n_sk", [(50, 37, 300), (7, 5, 129), (33, 3, 64), (1, 4, 40)])
+def test_zigzag_sign_bit_transfer_is_bit_identical(p, d, nch, n_sk):
+    """Host-buffer path of Zig-Zag: the V rows cross PCIe as sign bits and are rebuilt by worker threads as
+    copysign(|vinit_i|, bit) (api.cu: pack_signs_kernel).  Must give exactly the bytes of the plain copy: arbitrary
+    velocity magnitudes, -0.0, odd d (unaligned rows), many small slices, the time-horizon variant."""
+    g = np.random.default_rng(d)
+    x0 = g.standard_normal((nch, d))
+    v0 = g.standard_normal((nch, d)) * np.where(g.random((nch, d)) < 0.2, 3.0, 1.0)
+    v0[0, 0] = -0.0 if d > 1 else v0[0, 0]
+    s = p.ZigZagAD(d, p.GaussStd())
+    outs = []
+    for forced in ("1", "0"):
+        os.environ["PDMPFLUX_VBITS"] = forced
+        os.environ["PDMPFLUX_SLAB_BYTES"] = str(1 << 16)
+        os.environ["PDMPFLUX_HOST_THREADS"] = "3"
+        try:
+            outs.append((p.sample_skeleton(s, n_sk, x0, v0, seed=31), p.sample_skeleton(s, 2.5, x0, v0, seed=31)))
+        finally:
+            for k in ("PDMPFLUX_VBITS", "PDMPFLUX_SLAB_BYTES", "PDMPFLUX_HOST_THREADS"):
+                os.environ.pop(k)
+    (a, ta), (b, tb) = outs
+    assert a.V.tobytes() == b.V.tobytes() and a.X.tobytes() == b.X.tobytes() and np.array_equal(a.t, b.t)
+    assert np.array_equal(np.abs(a.V), np.broadcast_to(np.abs(v0)[:, None, :], a.V.shape))
+    for ha, hb in zip(ta, tb):
+        assert ha.V.tobytes() == hb.V.tobytes() and np.array_equal(ha.t, hb.t)
