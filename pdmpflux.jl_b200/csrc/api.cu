@@ -732,8 +732,8 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         return b.alloc(bytes);
     };
     // Scalar columns (76 of the 16d+76 bytes per event) accumulate in full-length device buffers and go to the host
-    // once at the end as wide copies; only the X / V rows are double-buffered through the narrow slabs.  (Slicing
-    // the scalar columns too would mean n_chains x n_slices x 7 strided host rows of a few hundred bytes each.)
+    // in a few wide chunks; only the X / V rows are double-buffered through the narrow slabs.  (Slicing the scalar
+    // columns like the rows would mean n_chains x n_slices x 7 strided host rows of a few hundred bytes each.)
     const int64_t ldS = (n_sk + 3) & ~int64_t(3);
     const bool full_scalars = (size_t)n_chains * ldS * 76 <= (8ull << 30);
     Slab& sc = ws.scal;
@@ -874,7 +874,7 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         return cudaMemcpy2DAsync(static_cast<char*>(dst) + (size_t)k0 * elem, (size_t)hist->n_cols * elem, src,
                                  (size_t)src_ld * elem, (size_t)n * elem, (size_t)n_chains, cudaMemcpyDeviceToHost, copy_stream);
     };
-    int64_t k0 = 0;
+    int64_t k0 = 0, sc_copied = 0;
     int it = 0;
     while (k0 < n_sk) {
         Slab& b = slab[it % n_slabs];
@@ -925,17 +925,20 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         CUDA_TRY(cudaEventRecord(b.copied, copy_stream));
         k0 += n;
         ++it;
-    }
-    if (full_scalars) {  // the scalar columns: one wide copy per column array, after the last kernel
-        CUDA_TRY(cudaEventRecord(sc.done ? sc.done : slab[0].done, stream));
-        CUDA_TRY(cudaStreamWaitEvent(copy_stream, sc.done ? sc.done : slab[0].done, 0));
-        if (hist->t) CUDA_TRY(copy2d(hist->t, sc.view.t, sizeof(double), ldS, 0, n_sk));
-        if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, sc.view.horizon, sizeof(double), ldS, 0, n_sk));
-        if (hist->ar) CUDA_TRY(copy2d(hist->ar, sc.view.ar, sizeof(double), ldS, 0, n_sk));
-        if (hist->error_value_ar) CUDA_TRY(copy2d(hist->error_value_ar, sc.view.error_value_ar, sizeof(double) * 5, ldS, 0, n_sk));
-        if (hist->errored_bound) CUDA_TRY(copy2d(hist->errored_bound, sc.view.errored_bound, sizeof(int32_t), ldS, 0, n_sk));
-        if (hist->rejected) CUDA_TRY(copy2d(hist->rejected, sc.view.rejected, sizeof(int32_t), ldS, 0, n_sk));
-        if (hist->hitting_horizon) CUDA_TRY(copy2d(hist->hitting_horizon, sc.view.hitting_horizon, sizeof(int32_t), ldS, 0, n_sk));
+        // The scalar columns follow in a few wide chunks (rows of >= 256 columns) behind the X rows on the copy stream
+        // (which already waits for this slice's kernel), so that only the last chunk is left after the last kernel.
+        if (full_scalars && (k0 == n_sk || k0 - sc_copied >= 256)) {
+            const int64_t a = sc_copied, m = k0 - sc_copied;
+            auto src = [&](auto* base, size_t elems) { return base + (size_t)a * elems; };
+            if (hist->t) CUDA_TRY(copy2d(hist->t, src(sc.view.t, 1), sizeof(double), ldS, a, m));
+            if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, src(sc.view.horizon, 1), sizeof(double), ldS, a, m));
+            if (hist->ar) CUDA_TRY(copy2d(hist->ar, src(sc.view.ar, 1), sizeof(double), ldS, a, m));
+            if (hist->error_value_ar) CUDA_TRY(copy2d(hist->error_value_ar, src(sc.view.error_value_ar, 5), sizeof(double) * 5, ldS, a, m));
+            if (hist->errored_bound) CUDA_TRY(copy2d(hist->errored_bound, src(sc.view.errored_bound, 1), sizeof(int32_t), ldS, a, m));
+            if (hist->rejected) CUDA_TRY(copy2d(hist->rejected, src(sc.view.rejected, 1), sizeof(int32_t), ldS, a, m));
+            if (hist->hitting_horizon) CUDA_TRY(copy2d(hist->hitting_horizon, src(sc.view.hitting_horizon, 1), sizeof(int32_t), ldS, a, m));
+            sc_copied = k0;
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaStreamSynchronize(copy_stream));
