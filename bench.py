@@ -356,10 +356,10 @@ def main():
             dist.all_gather_object(sharing, local)
             peers = sum(1 for other in sharing if other == local)
             os.environ["PDMPFLUX_HOST_THREADS"] = str(max(1, min(16, len(local) // max(peers, 1))))
-            if len(local) // max(peers, 1) < 12:
-                # too few CPUs per rank to rebuild the V rows faster than PCIe delivers them (measured: one rank with 8
-                # threads loses against the plain copy; two ranks x 12 threads win, 82 vs 97 ms per step)
-                os.environ["PDMPFLUX_VBITS"] = "0"
+            # (one rank alone needs >= 12 threads to beat the plain copy of the V rows -- the library's own default -- but
+            # with several ranks the host's ingest bandwidth saturates (plain copy: 75 ms per step at 1 rank, 97 at 2,
+            # 211 at 4), so moving half the bytes wins even with few threads per rank)
+            os.environ["PDMPFLUX_VBITS"] = "1"
             dist.barrier()
         res = e2e(p, sampler, name, nch, n_ev, world, dev)
         if world > 1:
