@@ -33,6 +33,11 @@ def tobytes(v, u):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
 
 
+for k, (v, u) in get.items():  # pipe utilisation, when the report carries it (ncu --set full)
+    if re.search(r"sm__inst_executed_pipe_tensor_subpipe_dmma\.avg\.pct|sm__pipe_tensor_cycles_active_realtime|"
+                 r"sm__inst_executed_pipe_fp64\.avg\.pct|sm__inst_executed_pipe_lsu\.avg\.pct_of_peak_sustained_active", k):
+        print(f"{k:70s} {v:>18s} {u}", file=out)
+
 rd = tobytes(*get["dram__bytes_read.sum"]); wr = tobytes(*get["dram__bytes_write.sum"])
 print(f"dram traffic per event: read {rd / n_events:.1f} B  write {wr / n_events:.1f} B  total {(rd + wr) / n_events:.1f} B", file=out)
 inst = float(get["smsp__inst_executed.sum"][0])
