@@ -1,4 +1,4 @@
-// Zig-Zag on a Bayesian logistic-regression posterior (BASELINE.json config 4): four chains per CTA.
+// Zig-Zag on a Bayesian logistic-regression posterior (BASELINE.json config 4): four chains per CTA, FP64 DMMA pipeline.
 //
 //   U(theta) = sum_r [log(1 + exp(z_r)) - y_r z_r] + |theta|^2 / (2 sigma0^2),  z = X theta,  X: n x d row-major
 //   grad U   = X^T (sigma(z) - y) + theta / sigma0^2
@@ -14,17 +14,21 @@
 //     [G | HV] (d x 2G)  =  X^T  .  [sigma(z + t_k w) - y | sigma'(z + t_k w) .* w]_k (n x 2G)
 // and the rate at a proposal time is the same pass with one column.
 //
-// Execution: a CTA of 4 warps owns 4 chains.  Between passes warp c runs chain c's thinning state machine; whenever
-// the chains need gradients they post a request (a bound: G times with Hessian columns, or a rate: 1 time) and the
-// whole CTA makes ONE pass over X serving all four:
-//   * 32-row tiles of X (rows are contiguous in row-major X) and of y arrive by TMA bulk copies
-//     (cp.async.bulk + mbarrier expect-tx, SASS UBLKCP.S.G) into a two-deep ring;
-//   * z, w of all four chains: one DMMA product with B = [x1 v1 x2 v2 x3 v3 x4 v4] -- exactly the 8 columns of
-//     mma.sync.m8n8k4.f64, no padding;
-//   * residual columns (exp) for every requested time of every chain, packed side by side (up to 4 * 2G = 80);
-//   * acc (d x columns) += Xtile^T . R with FP64 tensor-core MMAs (SASS DMMA; tcgen05 has no FP64 kind).
+// Execution: a CTA (384 threads, one per SM) owns 4 chains.  Between passes consumer warp c runs chain c's thinning
+// state machine; whenever the chains need gradients they post a request (a bound: G times with Hessian columns, or a
+// rate: 1 time) and the whole CTA makes ONE pass over X serving all of them (up to 64 packed residual columns; a
+// request that does not fit waits a round).  A pass is a warp-specialised pipeline handed over with mbarriers only:
+//   * feed: one producer thread per group issues TMA bulk copies (cp.async.bulk + mbarrier expect-tx, SASS UBLKCP.S.G)
+//     of 32-row tiles of X (rows are contiguous in row-major X) and of y into a 5-deep ring;
+//   * producers (warpgroups 1, 2, alternating tiles): z, w of all four chains by one DMMA product with
+//     B = [x1 v1 x2 v2 x3 v3 x4 v4] -- exactly the 8 columns of mma.sync.m8n8k4.f64, no padding -- or, when every
+//     asking chain has valid cached rows, by the incremental update z += dt w, w -= 2 v_m X[:, m]; then the residual
+//     columns (two exps and one division per row of a bound) into a 3-deep ring;
+//   * consumers (warpgroup 0): acc (d x columns) += Xtile^T . R with FP64 MMAs (SASS DMMA; tcgen05 has no FP64 kind),
+//     accumulators in registers for the whole pass (setmaxnreg: 232 registers per consumer thread, 128 per producer).
 // Four chains share every byte of X read from L2 and fill the MMA tile widths that a single chain would pad
 // (z/w: 2 of 8 columns, a rate request: 1 of 8).  X (80 MB at C4 size) stays resident in the 126 MB L2.
+// DESIGN.md 2b has the measurements behind each of these choices.
 #include "common.cuh"
 #include "philox.cuh"
 
