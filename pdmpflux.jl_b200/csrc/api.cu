@@ -86,9 +86,13 @@ struct Workspace {
     uint32_t* vbits_host = nullptr;
     size_t vbits_host_bytes = 0;
     std::vector<cudaEvent_t> slice_copied;  // one event per slice: its sign bits have reached the host
+    DevBuf zflags;                          // per slice: errored_bound (hence error_value_ar) has a non-zero entry
+    int* zflags_host = nullptr;
+    size_t zflags_host_n = 0;
     ~Workspace() {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (vbits_host) cudaFreeHost(vbits_host);
+        if (zflags_host) cudaFreeHost(zflags_host);
         for (cudaEvent_t e : slice_copied) cudaEventDestroy(e);
     }
 };
@@ -210,6 +214,18 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     if (e != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("skeleton kernel launch: ") + cudaGetErrorString(e));
     g_launches.fetch_add(1);
     return PDMPFLUX_OK;
+}
+
+// errored_bound is zero for (almost) every event, and error_value_ar is zero wherever it is: one flag per slice tells the
+// host path that both columns of the slice are all zero, so they need not cross PCIe (the host zero-fills its rows).
+__global__ void __launch_bounds__(256) flag_nonzero_kernel(const int32_t* __restrict__ eb, int64_t n_chains, int64_t ld,
+                                                           int64_t k0, int64_t n, int* __restrict__ flag) {
+    bool any = false;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_chains * n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e / n, k = e - c * n;
+        any |= eb[c * ld + k0 + k] != 0;
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 // Zig-Zag velocities never change magnitude (ZigZagSamplers.jl:101-107 only flips signs), so on the host-buffer path a
@@ -795,6 +811,17 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
             ws.slice_copied.push_back(e);
         }
     }
+    // all-zero slices of errored_bound / error_value_ar stay on the device (flag_nonzero_kernel); the workers zero-fill
+    const bool zskip = vbits && full_scalars && hist->errored_bound && hist->error_value_ar;
+    if (zskip) {
+        CUDA_TRY(ensure(ws.zflags, true, sizeof(int) * (size_t)n_slices));
+        if (ws.zflags_host_n < (size_t)n_slices) {
+            if (ws.zflags_host) { cudaFreeHost(ws.zflags_host); ws.zflags_host = nullptr; ws.zflags_host_n = 0; }
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ws.zflags_host), sizeof(int) * (size_t)n_slices, cudaHostAllocDefault));
+            ws.zflags_host_n = (size_t)n_slices;
+        }
+        CUDA_TRY(cudaMemsetAsync(ws.zflags.p, 0, sizeof(int) * (size_t)n_slices, stream));
+    }
     // worker t rebuilds the V rows of chains [c0, c1) slice by slice, as soon as each slice's bits are on the host
     std::atomic<int64_t> enqueued{0};
     std::atomic<bool> abort_workers{false};
@@ -809,6 +836,11 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
             }
             if (cudaEventSynchronize(ws.slice_copied[(size_t)it]) != cudaSuccess) return;
             const int64_t k0 = it * slice, n = std::min<int64_t>(slice, n_sk - k0);
+            if (zskip && ws.zflags_host[it] == 0)
+                for (int64_t c = c0; c < c1; ++c) {
+                    std::memset(hist->error_value_ar + ((size_t)c * hist->n_cols + k0) * 5, 0, sizeof(double) * 5 * (size_t)n);
+                    std::memset(hist->errored_bound + (size_t)c * hist->n_cols + k0, 0, sizeof(int32_t) * (size_t)n);
+                }
             const uint32_t* bits = ws.vbits_host + (size_t)it * vstride;
             for (int64_t c = c0; c < c1; ++c) {
                 const uint64_t* au = reinterpret_cast<const uint64_t*>(absv.data() + (size_t)c * d);  // |v| >= 0: OR the sign in
@@ -903,6 +935,11 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
                                                        ws.vbits.as<uint32_t>() + (size_t)it * vstride);
             CUDA_TRY(cudaGetLastError());
             g_launches.fetch_add(1);
+            if (zskip) {
+                flag_nonzero_kernel<<<296, 256, 0, stream>>>(sc.view.errored_bound, n_chains, ldS, k0, n, ws.zflags.as<int>() + it);
+                CUDA_TRY(cudaGetLastError());
+                g_launches.fetch_add(1);
+            }
             CUDA_TRY(cudaEventRecord(b.done, stream));
             CUDA_TRY(cudaStreamWaitEvent(copy_stream, b.done, 0));
         }
@@ -910,6 +947,7 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         if (vbits) {
             CUDA_TRY(cudaMemcpyAsync(ws.vbits_host + (size_t)it * vstride, ws.vbits.as<uint32_t>() + (size_t)it * vstride,
                                      sizeof(uint32_t) * vstride, cudaMemcpyDeviceToHost, copy_stream));
+            if (zskip) CUDA_TRY(cudaMemcpyAsync(ws.zflags_host + it, ws.zflags.as<int>() + it, sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
             CUDA_TRY(cudaEventRecord(ws.slice_copied[(size_t)it], copy_stream));
             enqueued.store(it + 1, std::memory_order_release);
         } else if (hist->V) CUDA_TRY(copy2d(hist->V, b.view.V, sizeof(double) * d, slice, k0, n));
@@ -933,8 +971,8 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
             if (hist->t) CUDA_TRY(copy2d(hist->t, src(sc.view.t, 1), sizeof(double), ldS, a, m));
             if (hist->horizon) CUDA_TRY(copy2d(hist->horizon, src(sc.view.horizon, 1), sizeof(double), ldS, a, m));
             if (hist->ar) CUDA_TRY(copy2d(hist->ar, src(sc.view.ar, 1), sizeof(double), ldS, a, m));
-            if (hist->error_value_ar) CUDA_TRY(copy2d(hist->error_value_ar, src(sc.view.error_value_ar, 5), sizeof(double) * 5, ldS, a, m));
-            if (hist->errored_bound) CUDA_TRY(copy2d(hist->errored_bound, src(sc.view.errored_bound, 1), sizeof(int32_t), ldS, a, m));
+            if (hist->error_value_ar && !zskip) CUDA_TRY(copy2d(hist->error_value_ar, src(sc.view.error_value_ar, 5), sizeof(double) * 5, ldS, a, m));
+            if (hist->errored_bound && !zskip) CUDA_TRY(copy2d(hist->errored_bound, src(sc.view.errored_bound, 1), sizeof(int32_t), ldS, a, m));
             if (hist->rejected) CUDA_TRY(copy2d(hist->rejected, src(sc.view.rejected, 1), sizeof(int32_t), ldS, a, m));
             if (hist->hitting_horizon) CUDA_TRY(copy2d(hist->hitting_horizon, src(sc.view.hitting_horizon, 1), sizeof(int32_t), ldS, a, m));
             sc_copied = k0;
@@ -943,6 +981,17 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaStreamSynchronize(copy_stream));
     workers.finish();  // the V rows of the last slices
+    int64_t z_copied_cols = 0;
+    if (zskip) {  // the rare slices with a non-zero errored_bound: copy their two columns after all
+        for (int64_t i = 0; i < n_slices; ++i)
+            if (ws.zflags_host[i] != 0) {
+                const int64_t a = i * slice, m = std::min<int64_t>(slice, n_sk - a);
+                CUDA_TRY(copy2d(hist->error_value_ar, sc.view.error_value_ar + (size_t)a * 5, sizeof(double) * 5, ldS, a, m));
+                CUDA_TRY(copy2d(hist->errored_bound, sc.view.errored_bound + (size_t)a, sizeof(int32_t), ldS, a, m));
+                z_copied_cols += m;
+            }
+        CUDA_TRY(cudaStreamSynchronize(copy_stream));
+    }
     {   // what actually crossed PCIe (bench.py reports it next to the end-to-end number)
         const int64_t cols = n_chains * n_sk;
         int64_t out = cols * ((hist->X ? 8 * d : 0) + (hist->t ? 8 : 0) + (hist->horizon ? 8 : 0) + (hist->ar ? 8 : 0) +
@@ -950,6 +999,7 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
                               (hist->hitting_horizon ? 4 : 0));
         if (vbits) out += (int64_t)(sizeof(uint32_t) * vstride * (size_t)n_slices);
         else if (hist->V) out += cols * 8 * d;
+        if (zskip) out += n_slices * 4 - (n_sk - z_copied_cols) * n_chains * 44;
         g_d2h_bytes.store(out);
         g_h2d_bytes.store(2 * 8 * (int64_t)d * n_chains);
     }

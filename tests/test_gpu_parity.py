@@ -631,7 +631,33 @@ def test_zigzag_sign_bit_transfer_is_bit_identical(p, d, nch, n_sk):
             for k in ("PDMPFLUX_VBITS", "PDMPFLUX_SLAB_BYTES", "PDMPFLUX_HOST_THREADS"):
                 os.environ.pop(k)
     (a, ta), (b, tb) = outs
+    for f in ("horizon", "ar", "error_value_ar", "errored_bound", "rejected", "hitting_horizon"):
+        assert getattr(a, f).tobytes() == getattr(b, f).tobytes(), f
     assert a.V.tobytes() == b.V.tobytes() and a.X.tobytes() == b.X.tobytes() and np.array_equal(a.t, b.t)
     assert np.array_equal(np.abs(a.V), np.broadcast_to(np.abs(v0)[:, None, :], a.V.shape))
     for ha, hb in zip(ta, tb):
         assert ha.V.tobytes() == hb.V.tobytes() and np.array_equal(ha.t, hb.t)
+
+
+def test_zero_slices_of_error_columns_stay_on_device(p):
+    """Host-buffer path of Zig-Zag: slices whose errored_bound column is all zero are not copied (their error_value_ar /
+    errored_bound rows are zero-filled on the host); slices with a violated bound are.  A coarse 2-node grid on the
+    banana violates its bound now and then, so both kinds of slices occur; every column must equal the plain path."""
+    d, nch, n_sk = 4, 11, 600
+    g = np.random.default_rng(5)
+    x0 = g.standard_normal((nch, d)); v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0)
+    s = p.ZigZagAD(d, p.Banana(), grid_size=2, tmax=3.0, adaptive=False)
+    outs = []
+    for forced in ("1", "0"):
+        os.environ["PDMPFLUX_VBITS"] = forced
+        os.environ["PDMPFLUX_SLAB_BYTES"] = str(1 << 14)
+        try:
+            outs.append(p.sample_skeleton(s, n_sk, x0, v0, seed=4))
+        finally:
+            os.environ.pop("PDMPFLUX_VBITS"); os.environ.pop("PDMPFLUX_SLAB_BYTES")
+    a, b = outs
+    assert a.errored_bound.any() and not a.errored_bound.all()
+    cols_with = a.errored_bound.any(axis=0)
+    assert cols_with.any() and not cols_with.all()
+    for f in ("X", "V", "t", "horizon", "ar", "error_value_ar", "errored_bound", "rejected", "hitting_horizon"):
+        assert getattr(a, f).tobytes() == getattr(b, f).tobytes(), f
