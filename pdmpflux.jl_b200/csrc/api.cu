@@ -733,7 +733,9 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
     int64_t slice = per_col ? (int64_t)std::max<size_t>(1, budget / per_col) : n_sk;
     slice = std::min<int64_t>(slice, n_sk);
     // enough slices for the copies to overlap the kernels, but slices long enough to amortise launches
-    if (n_sk >= 64) slice = std::min<int64_t>(slice, std::max<int64_t>(16, (n_sk + 11) / 12));
+    int64_t want_slices = 16;
+    if (const char* e = std::getenv("PDMPFLUX_SLICES")) want_slices = std::max<int64_t>(1, std::atoll(e));
+    if (n_sk >= 64) slice = std::min<int64_t>(slice, std::max<int64_t>(16, (n_sk + want_slices - 1) / want_slices));
     slice = std::max<int64_t>(slice, 1);
     slice = (slice + 3) & ~int64_t(3);  // keeps every slab column 32-byte aligned for the 256-bit store path
 
