@@ -834,3 +834,207 @@ def rv_diagnostic(X, V, t, U, B=0):
         RV += inc * inc
         x_left = x_right
     return RV / T
+
+
+# --------------------------------------------------------------------------------------------
+# Sticky Zig-Zag: literal restatement of src/StickySamplingLoop.jl:13-164 on top of the
+# masked-velocity variants of the thinning steps (src/SamplingLoopInplace.jl:13-25, 87-217) and the
+# StickyZigZag closures (src/Samplers/StickyZigZagSamplers.jl:69-101, identical to Zig-Zag's).  Oracle only so
+# far: the CUDA path for it is the next row of the scope table.
+# --------------------------------------------------------------------------------------------
+class StickyHistory(History):
+    """PDMPHistory with the is_active BitMatrix that record! stores (Composites.jl:239-260)."""
+
+    def __init__(self, d, n):
+        super().__init__(d, n)
+        self.is_active = np.ones((d, n), dtype=bool, order="F")
+
+    def record(self, k, s):
+        super().record(k, s)
+        self.is_active[:, k] = s.is_active
+
+
+class StickyChain(Chain):
+    """get_event_state!(state, ::StickyPDMP) (SamplingLoopInplace.jl:49-63) and its loop body
+    (StickySamplingLoop.jl:30-164).  `kappa[i]` is the thawing rate of coordinate i.  Quirks kept as they are:
+    the velocity jump after an accepted event sees the full velocity, frozen coordinates included (if_accept!,
+    SamplingLoopInplace.jl:178); thawing adds tt but not the time already spent (ts) to the clock
+    (StickySamplingLoop.jl:160-161); axis crossings are only looked for at the start of an outer step (:52-60)."""
+
+    def __init__(self, sampler: Sampler, kappa, xinit, vinit, tape: Tape):
+        super().__init__(sampler, xinit, vinit, tape)
+        if sampler.cfg.sampler != ZIGZAG:
+            raise ValueError("StickyChain restates StickyZigZag only")
+        self.kappa = np.asarray(kappa, dtype=np.float64)
+        st = self.state
+        st.is_active = np.ones(sampler.dim, dtype=bool)   # PDMPState ctor: trues(d), tt = Inf (Composites.jl:95-99)
+        st.tt = math.inf
+        st.stick_or_thaw_event = False
+
+    def _active_velocity(self):  # SamplingLoopInplace.jl:13-25
+        st = self.state
+        return st.v if st.is_active.all() else np.where(st.is_active, st.v, 0.0)
+
+    def get_event_state(self):  # SamplingLoopInplace.jl:49-63
+        st = self.state
+        st.errored_bound = 0
+        st.rejected = 0
+        st.hitting_horizon = 0
+        st.error_value_ar = np.zeros(5)
+        while not st.accept and not st.stick_or_thaw_event:
+            self.one_step_of_thinning_or_sticking_or_thawing()
+        st.accept = False
+        st.stick_or_thaw_event = False
+        return st
+
+    def one_step_of_thinning_or_sticking_or_thawing(self):  # StickySamplingLoop.jl:30-67
+        st = self.state
+        v_used = self._active_velocity()
+        ub = self.upper_bound_func(st.x, v_used, st.horizon)
+        e = self.tape.randexp()
+        tp, lb = next_event(ub, e)
+        rate_thawing = 0.0
+        for i in range(len(st.is_active)):
+            if not st.is_active[i]:
+                rate_thawing += self.kappa[i]
+        tt = math.inf if rate_thawing == 0 else self.tape.randexp() / rate_thawing
+        st.tp, st.exp_rv, st.lambda_bar, st.upper_bound, st.tt = tp, e, lb, ub, tt
+        event_time = min(tp, st.horizon, tt)
+        xe, _ = self.s.flow(st.x, v_used, event_time)
+        crossed = bool(np.any(st.x * xe < 0))
+        if crossed:
+            self.move_to_axes_and_stick()
+        elif min(tp, tt) > st.horizon:
+            self.move_to_horizon()
+        else:
+            self.moves_until_horizon_or_axes()
+
+    def move_to_axes_and_stick(self):  # StickySamplingLoop.jl:73-107
+        st = self.state
+        t_togo, i = math.inf, -1
+        for j in range(len(st.x)):
+            if st.is_active[j]:
+                dj = st.x[j] * st.v[j]
+                if dj < 0:
+                    tj = -dj
+                    if tj < t_togo:
+                        t_togo, i = tj, j
+        if t_togo == math.inf:
+            raise RuntimeError("erronous t_togo, although no axis is crossed")
+        v_used = self._active_velocity()
+        st.x, _ = self.s.flow(st.x, v_used, t_togo)
+        st.is_active = st.is_active.copy()
+        st.is_active[i] = False
+        st.t += t_togo + st.ts
+        st.ts = 0.0
+        st.stick_or_thaw_event = True
+
+    def move_to_horizon(self):  # SamplingLoopInplace.jl:87-101 (masked branch)
+        st = self.state
+        if st.is_active.all():
+            st.x, st.v = self.s.flow(st.x, st.v, st.horizon)
+        else:
+            st.x, _ = self.s.flow(st.x, self._active_velocity(), st.horizon)
+        st.ts += st.horizon
+        st.hitting_horizon += 1
+        st.horizon = st.horizon * 1.01 if st.adaptive else st.horizon
+
+    def moves_until_horizon_or_axes(self):  # StickySamplingLoop.jl:121-132
+        st = self.state
+        while min(st.tp, st.tt) < st.horizon and not st.accept and not st.stick_or_thaw_event:
+            if st.tp < st.tt:
+                self.ac_step()
+            else:
+                self.thaw_one_coordinate()
+
+    def thaw_one_coordinate(self):  # StickySamplingLoop.jl:138-164
+        st = self.state
+        st.x, _ = self.s.flow(st.x, self._active_velocity(), st.tt)
+        total = 0.0
+        for j in range(len(st.is_active)):
+            if not st.is_active[j]:
+                total += self.kappa[j]
+        u = self.tape.rand() * total
+        acc, i = 0.0, -1
+        for j in range(len(st.is_active)):
+            if not st.is_active[j]:
+                acc += self.kappa[j]
+                if acc >= u:
+                    i = j
+                    break
+        st.is_active = st.is_active.copy()
+        st.is_active[i] = True
+        st.t += st.tt
+        st.ts = 0.0
+        st.stick_or_thaw_event = True
+
+    # --- masked variants of the shared steps (SamplingLoopInplace.jl:113-217) ---
+    def ac_step(self):  # :113-129
+        st = self.state
+        st.n_rate_evals += 1
+        lt = self.s.rate(st.x, self._active_velocity(), st.tp)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ar = float(np.float64(lt) / np.float64(st.lambda_bar))
+        st.lambda_t, st.ar = lt, ar
+        if ar > 1.0:
+            self.erroneous_acceptance_rate()
+        else:
+            self.ac_step_with_proxy()
+
+    def erroneous_acceptance_rate(self):  # :131-151
+        st = self.state
+        horizon = st.horizon / 2
+        ub = self.upper_bound_func(st.x, self._active_velocity(), horizon)
+        e = self.tape.randexp()
+        tp, lb = next_event(ub, e)
+        st.horizon = horizon if st.adaptive else st.horizon
+        st.tp, st.exp_rv, st.lambda_bar, st.upper_bound = tp, e, lb, ub
+        st.errored_bound += 1
+        st.error_value_ar[st.errored_bound % 5] = st.ar
+
+    def ac_step_with_proxy(self):  # :153-168
+        st = self.state
+        accept = self.tape.rand() < st.ar
+        st.accept = accept
+        if accept:
+            self.if_accept()
+        else:
+            self.if_reject()
+        if (not st.accept) and (min(st.tp, st.tt) > st.horizon):
+            self.move_to_horizon2()
+
+    def if_accept(self):  # :170-186
+        st = self.state
+        if st.is_active.all():
+            st.x, st.v = self.s.flow(st.x, st.v, st.tp)
+        else:
+            st.x, _ = self.s.flow(st.x, self._active_velocity(), st.tp)
+        st.v = self.s.velocity_jump(st.x, st.v, self.tape)   # the FULL velocity (quirk, see class docstring)
+        st.t = st.t + st.tp + st.ts
+        st.ts = 0.0
+        st.tp = 0.0
+        st.accept = True
+
+    def move_to_horizon2(self):  # :205-217
+        st = self.state
+        if st.is_active.all():
+            st.x, st.v = self.s.flow(st.x, st.v, st.horizon)
+        else:
+            st.x, _ = self.s.flow(st.x, self._active_velocity(), st.horizon)
+        st.ts += st.horizon
+        st.hitting_horizon += 1
+
+
+def sample_skeleton_sticky(sampler: Sampler, kappa, n_sk, xinit, vinit, tape: Tape):
+    """sample_skeleton for a StickyZigZag sampler (src/sample.jl:253-284 with the StickyPDMP dispatch): every accepted
+    flip, every sticking and every thawing is a skeleton point."""
+    if n_sk <= 0:
+        raise ValueError("n_sk must be positive")
+    ch = StickyChain(sampler, kappa, xinit, vinit, tape)
+    h = StickyHistory(sampler.dim, n_sk)
+    h.record(0, ch.state)
+    for k in range(1, n_sk):
+        h.record(k, ch.get_event_state())
+    h.final_state = ch.state
+    h.tape_pos = list(tape.pos)
+    return h
