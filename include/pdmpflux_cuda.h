@@ -225,7 +225,7 @@ int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_ch
  * of (U(x(t_b)) - U(x(t_{b-1})))^2 / t[end], positions by the linear interpolation of _history_position_linear!
  * (src/diagnostic.jl:23-35) when flow_kind = 0; flow_kind = 1 interpolates with the Boomerang rotation, which is what
  * the online sample_skeleton_with_diagnostic (src/sample.jl:75-236) accumulates through sampler.flow.  U is the value
- * plugin of `pot` (Gaussians and banana; LOGREG / GAUSS_DENSE -> PDMPFLUX_ERR_UNSUPPORTED).  X, V: [C][ld_sk][d],
+ * plugin of `pot` (Gaussians, banana, logistic regression; GAUSS_DENSE -> PDMPFLUX_ERR_UNSUPPORTED).  X, V: [C][ld_sk][d],
  * t: [C][ld_sk]; chain c uses its first ncols[c] columns (ncols == NULL: n_sk for all).  B = 0 -> floor(sqrt(n)) like
  * the reference, B < 0 -> PDMPFLUX_ERR_ARGUMENT (the reference's ArgumentError).  A chain whose t[end] is negative or
  * not finite gets rv = NaN (the binding raises the reference's ArgumentError). */

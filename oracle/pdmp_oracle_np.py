@@ -177,6 +177,10 @@ class LogReg:
         self.y = np.asarray(y, dtype=np.float64)
         self.inv_s2 = 1.0 / (sigma0 * sigma0)
 
+    def value(self, x):
+        z = self.X @ x
+        return float(np.sum(np.logaddexp(0.0, z) - self.y * z) + 0.5 * self.inv_s2 * np.dot(x, x))
+
     @staticmethod
     def _sigmoid(z):
         return 1.0 / (1.0 + np.exp(-z))

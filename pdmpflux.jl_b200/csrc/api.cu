@@ -1102,7 +1102,7 @@ int pdmpflux_rv_diagnostic(pdmpflux_potential_t pot, int flow_kind, int64_t n_sk
         return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
     if (B < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "B must be non-negative");  // diagnostic.jl:49-51
     if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear) or 1 (rotation)");
-    if (pot->kind == PDMPFLUX_LOGREG || pot->kind == PDMPFLUX_GAUSS_DENSE)
+    if (pot->kind == PDMPFLUX_GAUSS_DENSE)
         return fail(PDMPFLUX_ERR_UNSUPPORTED, "no device U(x) plugin for this potential");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: no CPU fallback");

@@ -8,6 +8,7 @@
 //
 // One CTA per chain; a warp per boundary (lanes stride the coordinates: X/V rows are contiguous, so the reads are
 // coalesced), U values parked in a global scratch row, then one block reduction of the squared increments.
+// U plugins: the Gaussians, the banana, and the logistic-regression posterior (a pass over X per boundary).
 #include "common.cuh"
 #include <math_constants.h>
 
@@ -45,6 +46,29 @@ __device__ double potential_value(int kind, const PotParams& pp, int d, const do
     }
 }
 
+// Logistic-regression posterior (BASELINE.json config 4): U(theta) = sum_r [log(1 + e^{z_r}) - y_r z_r] + |theta|^2 / (2 s0^2),
+// z = X theta.  theta (this boundary's position) is staged in the warp's slice of shared memory; lanes stride the rows
+// of X (which stays in L2), log(1 + e^z) in the overflow-free form max(z, 0) + log1p(e^{-|z|}).
+__device__ double logreg_value(const PotParams& pp, int d, const double* __restrict__ x0, const double* __restrict__ v0,
+                               double ca, double cb, int lane, double* theta) {
+    double sq = 0.0;
+    for (int j = lane; j < d; j += 32) {
+        const double xj = x0[j] * ca + v0[j] * cb;
+        theta[j] = xj;
+        sq += xj * xj;
+    }
+    __syncwarp();
+    double acc = 0.0;
+    for (int64_t r = lane; r < pp.n; r += 32) {
+        const double* row = pp.vec + r * d;
+        double z = 0.0;
+        for (int j = 0; j < d; ++j) z = fma(row[j], theta[j], z);
+        acc += fmax(z, 0.0) + log1p(exp(-fabs(z))) - pp.vec2[r] * z;
+    }
+    __syncwarp();
+    return warp_sum(acc) + 0.5 * pp.inv_s2 * warp_sum(sq);
+}
+
 __global__ void __launch_bounds__(256) rv_kernel(int kind, PotParams pp, int flow_kind, int d, int64_t ld_sk, int64_t n_sk,
                                                  const int64_t* __restrict__ ncols, int64_t B_req,
                                                  const double* __restrict__ X, const double* __restrict__ V,
@@ -55,6 +79,7 @@ __global__ void __launch_bounds__(256) rv_kernel(int kind, PotParams pp, int flo
     const int64_t n = ncols ? ncols[c] : n_sk;
     const double* t = T + c * ld_sk;
     __shared__ double red[8];
+    extern __shared__ double theta_smem[];  // LOGREG only: 8 warps x d
     if (n <= 0) { if (threadIdx.x == 0) rv[c] = 0.0; return; }            // diagnostic.jl:40
     const double Tend = t[n - 1];
     if (!(Tend >= 0.0) || Tend == CUDART_INF) { if (threadIdx.x == 0) rv[c] = CUDART_NAN; return; }  // :43-45 (caller raises)
@@ -79,7 +104,10 @@ __global__ void __launch_bounds__(256) rv_kernel(int kind, PotParams pp, int flo
         }
         double ca = 1.0, cb = tau;
         if (flow_kind == 1) sincos(tau, &cb, &ca);
-        const double val = potential_value(kind, pp, d, X + (c * ld_sk + lo) * d, V + (c * ld_sk + lo) * d, ca, cb, lane);
+        const double* xs = X + (c * ld_sk + lo) * d;
+        const double* vs = V + (c * ld_sk + lo) * d;
+        const double val = kind == PDMPFLUX_LOGREG ? logreg_value(pp, d, xs, vs, ca, cb, lane, theta_smem + warp * d)
+                                                   : potential_value(kind, pp, d, xs, vs, ca, cb, lane);
         if (lane == 0) u[b] = val;
     }
     __syncthreads();  // makes this CTA's global writes visible to itself
@@ -103,7 +131,8 @@ __global__ void __launch_bounds__(256) rv_kernel(int kind, PotParams pp, int flo
 cudaError_t launch_rv_diagnostic(int kind, const PotParams& pp, int flow_kind, int d, int64_t ld_sk, int64_t n_sk,
                                  int64_t n_chains, const int64_t* ncols, int64_t B, const double* X, const double* V,
                                  const double* t, double* uval, int64_t ld_u, double* rv, cudaStream_t stream) {
-    rv_kernel<<<(unsigned)n_chains, 256, 0, stream>>>(kind, pp, flow_kind, d, ld_sk, n_sk, ncols, B, X, V, t, uval, ld_u, rv);
+    const size_t smem = kind == PDMPFLUX_LOGREG ? sizeof(double) * 8 * (size_t)d : 0;
+    rv_kernel<<<(unsigned)n_chains, 256, smem, stream>>>(kind, pp, flow_kind, d, ld_sk, n_sk, ncols, B, X, V, t, uval, ld_u, rv);
     return cudaGetLastError();
 }
 

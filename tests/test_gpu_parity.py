@@ -478,8 +478,6 @@ def test_rv_diagnostic_reference_kat_and_errors(p):
     hneg = p.PDMPHistory(X, V, np.array([0.0, 0.5, np.inf]), z, z, zi, np.zeros((5, 3)), zi, zi)
     with pytest.raises(p.ArgumentError):
         p.RV_diagnostic(hneg, p.GaussStd())
-    with pytest.raises(p.UnsupportedError):
-        p.RV_diagnostic(h, p.LogReg(np.ones((4, 1)), np.array([0.0, 1.0, 0.0, 1.0])), B=2)
 
 
 @pytest.mark.parametrize("kind", ["zigzag_banana", "zigzag_readme", "bps_equicorr", "fecmc_std", "boomerang_diag"])
@@ -661,3 +659,19 @@ def test_zero_slices_of_error_columns_stay_on_device(p):
     assert cols_with.any() and not cols_with.all()
     for f in ("X", "V", "t", "horizon", "ar", "error_value_ar", "errored_bound", "rejected", "hitting_horizon"):
         assert getattr(a, f).tobytes() == getattr(b, f).tobytes(), f
+
+
+def test_rv_diagnostic_logistic_regression(p):
+    """RV_diagnostic with the logistic-regression U plugin (a pass over X per block boundary) against the oracle."""
+    import pdmp_oracle_np as onp
+    from oracle_cases import logreg_data
+    n, d, nch, n_sk = 157, 9, 4, 200
+    X, y, s0 = logreg_data(n, d)
+    g = np.random.default_rng(6)
+    s = p.ZigZagAD(d, p.LogReg(X, y, s0), grid_size=6)
+    hb = p.sample_skeleton(s, n_sk, 0.2 * g.standard_normal((nch, d)), np.where(g.random((nch, d)) < 0.5, -1.0, 1.0), seed=8)
+    opot = onp.LogReg(X, y, s0)
+    for B in (0, 23):
+        rv = p.RV_diagnostic(hb, s.potential, B=B)
+        ref = np.array([onp.rv_diagnostic(hb.X[c].T, hb.V[c].T, hb.t[c], opot.value, B=B) for c in range(nch)])
+        assert np.allclose(rv, ref, rtol=1e-9, atol=0), (B, rv, ref)
