@@ -117,6 +117,60 @@ end
 sample_skeleton(s::CuPDMP, n_sk::Int, xinit::Vector{Float64}, vinit::Vector{Float64}; kw...) =
     sample_skeleton(s, n_sk, reshape(xinit, :, 1), reshape(vinit, :, 1); kw...)[1]
 
+"""
+    sample_skeleton(sampler::CuPDMP, T::Float64, xinit, vinit; seed, init_capacity=1024) -> PDMPHistory
+
+Replaces the time-horizon method (src/sample.jl:323-439): the skeleton ends with the point at exactly `t == T`.  The
+number of events is not known in advance: like `_grow_history` (src/Composites.jl:172-191) the capacity doubles until
+the chain fits (`PDMPFLUX_ERR_CAPACITY = -6`; the run is deterministic, so it is simply repeated).
+"""
+function sample_skeleton(s::CuPDMP, T::Float64, xinit::Vector{Float64}, vinit::Vector{Float64};
+                         seed::Union{Int,Nothing}=nothing, verbose::Bool=true, init_capacity::Int=1024)
+    (isfinite(T) && T >= 0) || throw(ArgumentError("T must be finite and non-negative. Current value: $T"))
+    d = length(xinit)
+    (d == s.dim && length(vinit) == d) || throw(DimensionMismatch("xinit and vinit must have the same dimension as pdmp.dim ($(s.dim))"))
+    sd = seed === nothing ? rand(UInt64) : UInt64(seed)
+    cap = max(1, init_capacity)
+    while true
+        X = Matrix{Float64}(undef, d, cap); V = similar(X)
+        t = Vector{Float64}(undef, cap); hz = similar(t); ar = similar(t)
+        eva = Matrix{Float64}(undef, 5, cap)
+        eb = Vector{Int32}(undef, cap); rej = similar(eb); hh = similar(eb)
+        status = zeros(Int32, 1); ncols = zeros(Int64, 1)
+        rc = GC.@preserve X V t hz ar eva eb rej hh status ncols xinit vinit begin
+            h = CHistory(pointer(X), pointer(V), pointer(t), pointer(hz), pointer(ar), pointer(eva), pointer(eb),
+                         pointer(rej), pointer(hh), pointer(status), C_NULL, C_NULL, cap, 0)
+            ccall((:pdmpflux_sample_skeleton_until, LIB), Cint,
+                  (Ptr{Cvoid}, Int64, Float64, Int64, Ptr{Float64}, Ptr{Float64}, UInt64, Int64, Ptr{Cvoid}, Ref{CHistory},
+                   Ptr{Int64}, Ptr{Cvoid}),
+                  s.handle, 1, T, cap, xinit, vinit, sd, 0, C_NULL, Ref(h), ncols, C_NULL)
+        end
+        if rc == -6      # PDMPFLUX_ERR_CAPACITY
+            cap *= 2
+            continue
+        end
+        check(rc)
+        s.state = status
+        n = Int(ncols[1])
+        return PDMPHistory{Float64}(X[:, 1:n], V[:, 1:n], t[1:n], trues(d, n), hz[1:n], ar[1:n], eb[1:n], eva[:, 1:n],
+                                    rej[1:n], hh[1:n])
+    end
+end
+
+"Replaces `PDMPFlux.sample_from_skeleton(sampler, dt::Float64, history)` (src/sample.jl:573-646): samples at j*dt."
+function sample_from_skeleton(s::CuPDMP, dt::Float64, h::PDMPHistory; discard_vt::Bool=true)
+    (dt > 0 && isfinite(dt)) || throw(ArgumentError("dt must be positive. Current value: $dt"))
+    d, n_sk = size(h.X)
+    M = floor(Int, h.t[end] / dt)
+    out = Matrix{Float64}(undef, discard_vt ? d : 2d + 1, M)
+    M == 0 && return out
+    check(ccall((:pdmpflux_sample_from_skeleton_dt, LIB), Cint,
+                (Cint, Cint, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int64, Int32,
+                 Ptr{Float64}, Int32, Ptr{Cvoid}),
+                s.flow_kind, d, n_sk, n_sk, 1, h.X, h.V, h.t, dt, M, discard_vt, out, 0, C_NULL))
+    return out
+end
+
 "Replaces `PDMPFlux.sample_from_skeleton` (src/sample.jl:475-513)."
 function sample_from_skeleton(s::CuPDMP, N::Int, h::PDMPHistory; discard_vt::Bool=true)
     N <= 0 && throw(ArgumentError("N must be positive. Current value: $N"))
