@@ -111,7 +111,7 @@ struct pdmpflux_chains_s {
     int team = 32, n_own = 0, scratch_in_smem = 1, path = 0, vec_elems = 0, dpad = 0;
     size_t smem = 0;
     unsigned grid = 0;
-    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols, m1, m2;
+    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols, m1, m2, wq;
     int moments = 0;
     double t_stop = 0.0;
     int use_t_stop = 0;
@@ -202,7 +202,23 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     if (smem_launch > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "fused moments: shared memory exhausted for this dimension");
     if (s->pot->kind == PDMPFLUX_LOGREG) {
         p.vec32 = 0; p.bulk_rows = 0;
-        e = launch_logreg_zigzag(p, ch->grid, ch->smem, stream);
+        // One CTA per SM (384 threads, 168 registers): with more CTAs of four chains than SMs, the first wave starts on
+        // chains 0 .. 4 grid - 1 and every warp pulls its next chain from a work queue when its own is done.
+        unsigned grid = ch->grid;
+        p.work_counter = nullptr; p.work_start = 0;
+        if (n_events > 0 && ch->wq.p) {
+            static int n_sm = 0;
+            if (n_sm == 0) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+            }
+            grid = std::min<unsigned>(grid, (unsigned)n_sm);
+            p.work_counter = ch->wq.as<int64_t>();
+            p.work_start = (int64_t)grid * logreg_chains_per_block();
+            CUDA_TRY(cudaMemsetAsync(ch->wq.p, 0, sizeof(int64_t), stream));
+        }
+        e = launch_logreg_zigzag(p, grid, ch->smem, stream);
     } else
     switch (s->kind) {
     case PDMPFLUX_ZIGZAG: e = launch_skeleton_zigzag(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
@@ -510,6 +526,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
         const char* off = getenv("PDMPFLUX_LOGREG_NO_ZW_CACHE");
         if (!(off && off[0] == '1') && zw_bytes <= ((size_t)32 << 30) && ch->scratch.alloc(zw_bytes) != cudaSuccess)
             (void)cudaGetLastError();  // out of memory: run without the cache
+        CUDA_TRY(ch->wq.alloc(sizeof(int64_t)));  // work-queue counter of the persistent launch
     }
     if (ch->smem > 227 * 1024) return fail(PDMPFLUX_ERR_UNSUPPORTED, "dimension too large for the shared-memory state layout");
     CUDA_TRY(ch->x.alloc(sizeof(double) * d * n_chains));

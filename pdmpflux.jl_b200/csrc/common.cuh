@@ -46,6 +46,9 @@ struct KernelParams {
     int32_t* status;   // [C]
     int64_t* counters; // [C][2]
     int64_t* ncols;    // [C] history columns recorded so far (time-horizon variant)
+    // logistic-regression kernel: chains beyond the first gridDim.x * 4 are pulled from a work queue (logreg.cu)
+    int64_t* work_counter;  // device counter, zeroed before the launch (nullptr: no queue)
+    int64_t work_start;     // index of the first queued chain
     // fused moments (no reference equivalent): running time integrals of x_i and x_i^2 per chain,
     // accumulated segment by segment inside the flows, so moments / ESS need no stored skeleton
     int accumulate_moments;

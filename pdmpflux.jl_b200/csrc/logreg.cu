@@ -95,6 +95,7 @@ struct LrSched {
     // pending move x = x0 + pdt v0 followed by the flip of coordinate pm (whose velocity was pvm); mode 0 = recompute
     int mode[kLrChains], pm[kLrChains];
     double pdt[kLrChains], pvm[kLrChains];
+    long long chain_id[kLrChains];  // the chain each consumer warp currently runs (chains are pulled from a work queue)
 };
 // mbarriers: full_x[s] (TMA landed), empty_x[s] (consumers done with the tile), full_rs[r] (residual tile written),
 // empty_rs[r] (consumers done with it)
@@ -167,19 +168,21 @@ __device__ void lr_produce(const KernelParams& p, double* sm, const LrShared& L,
     // (z, w) = (X x, X v) of a chain change between two of its requests only by a straight move and at most one flip:
     // z += dt w, w -= 2 v_m X[:, m].  When every chain asking in this pass has valid cached rows (global memory,
     // [chain][tile][row][2], streamed with evict-first hints so that X keeps the L2) the 100-MMA z/w product of the
-    // tile is skipped and each producer warp updates its own chain's rows in registers; any chain without a valid
-    // cache (first request of a launch, periodic exact refresh) makes the pass recompute -- and re-cache -- all of them.
+    // tile is skipped and each producer warp updates its own chain's rows in registers.  A chain without a valid cache
+    // (its first request of a launch, the periodic exact refresh) makes the pass run the product, but only such chains
+    // take its result: a chain's numbers never depend on which other chains happen to share its CTA.
     bool use_dmma = p.scratch == nullptr;
 #pragma unroll
     for (int c = 0; c < kLrChains; ++c) use_dmma |= (S->nt[c] > 0 && S->mode[c] == 0);
     const int my_nt = S->nt[pw];
     double2* cache = nullptr;
     if (p.scratch != nullptr && my_nt > 0)
-        cache = reinterpret_cast<double2*>(p.scratch) + (((int64_t)blockIdx.x * kLrChains + pw) * ntiles) * kLrRows + lane;
+        cache = reinterpret_cast<double2*>(p.scratch) + ((int64_t)S->chain_id[pw] * ntiles) * kLrRows + lane;
     const double pdt = S->pdt[pw], pvm2 = 2.0 * S->pvm[pw];
     const int pm = S->pm[pw];
+    const bool my_cached = cache != nullptr && S->mode[pw] == 1;  // this warp's chain updates its cached rows
     double2 zw_next = make_double2(0.0, 0.0);
-    if (!use_dmma && cache != nullptr && pg < ntiles) zw_next = __ldcs(cache + (int64_t)pg * kLrRows);
+    if (my_cached && pg < ntiles) zw_next = __ldcs(cache + (int64_t)pg * kLrRows);
     for (int64_t tile = pg; tile < ntiles; tile += 2) {
         const LrRing r = lr_ring(gbase + (uint32_t)tile, L.xstages);
         const int rows = (int)min((int64_t)kLrRows, n - tile * kLrRows);
@@ -189,15 +192,14 @@ __device__ void lr_produce(const KernelParams& p, double* sm, const LrShared& L,
         const double* ys = sm + L.ybuf + r.xs * kLrRows;
         double* zwb = sm + L.zw + (pg * 2 + (int)((tile >> 1) & 1)) * (kLrRows * 8);
         double z = 0.0, w = 0.0;  // this lane's row of this warp's chain
-        if (!use_dmma) {
-            if (cache != nullptr) {
-                z = zw_next.x; w = zw_next.y;
-                if (tile + 2 < ntiles) zw_next = __ldcs(cache + (tile + 2) * kLrRows);  // next own tile, one iteration ahead
-                z = fma(pdt, w, z);
-                if (pm >= 0) w = fma(-pvm2, Xs[lane * d + pm], w);
-                if (pdt != 0.0 || pm >= 0) __stcs(cache + tile * kLrRows, make_double2(z, w));
-            }
-        } else {
+        if (my_cached) {
+            z = zw_next.x; w = zw_next.y;
+            if (tile + 2 < ntiles) zw_next = __ldcs(cache + (tile + 2) * kLrRows);  // next own tile, one iteration ahead
+            z = fma(pdt, w, z);
+            if (pm >= 0) w = fma(-pvm2, Xs[lane * d + pm], w);
+            if (pdt != 0.0 || pm >= 0) __stcs(cache + tile * kLrRows, make_double2(z, w));
+        }
+        if (use_dmma) {
         // ---- (z, w) of the four chains for the tile: DMMA with B = [x1 v1 .. x4 v4] (k x 8); 8 rows per warp ----
         {
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: halves the dependent MMA chain
@@ -214,8 +216,10 @@ __device__ void lr_produce(const KernelParams& p, double* sm, const LrShared& L,
             zr[1] = c1 + e1;
         }
         group_barrier(1 + pg, 128);
-        z = zwb[lane * 8 + 2 * pw]; w = zwb[lane * 8 + 2 * pw + 1];
-        if (cache != nullptr) __stcs(cache + tile * kLrRows, make_double2(z, w));
+        if (!my_cached) {
+            z = zwb[lane * 8 + 2 * pw]; w = zwb[lane * 8 + 2 * pw + 1];
+            if (cache != nullptr) __stcs(cache + tile * kLrRows, make_double2(z, w));
+        }
         }
         mbar_wait(&bar[kBarEmptyR + r.rs], r.rpar ^ 1u);  // consumers are done with the tile that used this slot
         // ---- residual columns: warp c evaluates chain c's requested times, lane = row of the tile ----
@@ -376,9 +380,11 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
     const int dp = (d + 7) / 8 * 8;
     const double inv_s2 = p.pot.inv_s2;
     LrSched* S = reinterpret_cast<LrSched*>(sm + L.sched);
-    const int64_t c_raw = (int64_t)blockIdx.x * kLrChains + w;  // warp w runs chain c
-    const bool valid = wgroup == 0 && c_raw < p.n_chains;
-    const int64_t c = valid ? c_raw : 0;
+    // Consumer warp w starts with chain blockIdx.x * 4 + w and pulls further chains from a global work queue as soon as
+    // its chain has finished this launch's events (persistent CTAs: no CTA waits for the slowest of four fixed chains).
+    const int64_t c_raw = (int64_t)blockIdx.x * kLrChains + w;
+    bool valid = wgroup == 0 && c_raw < p.n_chains;
+    int64_t c = valid ? c_raw : 0;
 
     // ---- shared state: xv[k][8] holds (x, v) of chain w in columns (2w, 2w+1); it is also the z/w B operand ----
     for (int e = tid; e < (dp + 4) * 8; e += kLrThreads) sm[L.xv + e] = 0.0;
@@ -389,6 +395,7 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
             sm[L.xv + i * 8 + 2 * w] = p.sx[c * d + i];
             sm[L.xv + i * 8 + 2 * w + 1] = p.sv[c * d + i];
         }
+    if (wgroup == 0 && lane == 0) S->chain_id[w] = valid ? (long long)c : -1;
     fence_async_smem();  // order these generic-proxy writes before the TMA (async-proxy) writes into the same buffers
     if (tid == 0) {
         uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
     int status = valid ? p.status[c] : 0;
     int64_t n_builds = p.counters[2 * c], n_rates = p.counters[2 * c + 1];
     DrawKey key;
-    const uint64_t gchain = (uint64_t)(p.chain_offset + c);
+    uint64_t gchain = (uint64_t)(p.chain_offset + c);
     key.k0 = (uint32_t)p.seed; key.k1 = (uint32_t)(p.seed >> 32);
     key.chain_lo = (uint32_t)gchain; key.chain_hi8 = (uint32_t)(gchain >> 32) << 8;
     key.event = 0;
@@ -523,7 +530,60 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
     enum { REQ_NONE = 0, REQ_BOUND = 1, REQ_RATE = 2 };
     unsigned round = 0;
 
+    // ---- work queue: write a finished chain's PDMPState back, take over the next chain ----
+    auto store_chain = [&]() {
+        for (int i = lane; i < d; i += 32) {
+            p.sx[c * d + i] = xr(i);
+            p.sv[c * d + i] = vr(i);
+        }
+        if (lane == 0) {
+            p.st[c] = t; p.shorizon[c] = horizon; p.sar[c] = ar; p.status[c] = status;
+            p.counters[2 * c] = n_builds; p.counters[2 * c + 1] = n_rates;
+            p.tape_pos[3 * c] = pE; p.tape_pos[3 * c + 1] = pU;
+            p.ncols[c] += ev;
+        }
+    };
+    auto load_chain = [&](int64_t cc) {
+        valid = cc < p.n_chains;
+        c = valid ? cc : 0;
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) {
+            xr(i) = valid ? p.sx[c * d + i] : 0.0;
+            vr(i) = valid ? p.sv[c * d + i] : 0.0;
+        }
+        if (lane == 0) S->chain_id[w] = valid ? (long long)c : -1;
+        __syncwarp();
+        t = p.st[c]; horizon = p.shorizon[c]; ar = p.sar[c];
+        status = valid ? p.status[c] : 0;
+        n_builds = p.counters[2 * c]; n_rates = p.counters[2 * c + 1];
+        gchain = (uint64_t)(p.chain_offset + c);
+        key.chain_lo = (uint32_t)gchain; key.chain_hi8 = (uint32_t)(gchain >> 32) << 8;
+        key.event = (uint32_t)(p.event0 + 1);
+        sE = sU = 0;
+        pE = p.tape_pos[3 * c]; pU = p.tape_pos[3 * c + 1];
+        tE = p.tE + c * p.nE; tU = p.tU + c * p.nU;
+        exhausted = false;
+        eb = rej = hh = 0;
+        for (int k = 0; k < 5; ++k) eva[k] = 0.0;
+        ev = 0; steps = 0;
+        ts = tp = lambda_bar = exp_rv = hbound = 0.0;
+        need_build = true; half = false;
+        cache_valid = false; served = 0; pend_m = -1; pend_dt = 0.0;
+        if (p.use_t_stop && status == 0 && !(t < p.t_stop)) status = PDMPFLUX_CHAIN_DONE;
+        live = valid && status == 0;
+    };
+
     while (true) {
+        // ---- 0. a chain that is done with this launch hands its warp to the next chain in the queue ----
+        if (p.work_counter != nullptr)
+            while (valid && !live) {
+                store_chain();
+                long long next = 0;
+                if (lane == 0) next = p.work_start + (long long)atomicAdd(reinterpret_cast<unsigned long long*>(p.work_counter), 1ull);
+                next = __shfl_sync(0xffffffffu, next, 0);
+                load_chain(next);
+            }
+
         // ---- 1. every chain posts its request ----
         int req = REQ_NONE;
         if (live) {
@@ -721,17 +781,7 @@ __global__ void __launch_bounds__(kLrThreads, 1) logreg_zigzag_kernel(const __gr
         __syncthreads();  // accumulators consumed before the next pass reuses the rings
     }
 
-    if (!valid) return;
-    for (int i = lane; i < d; i += 32) {
-        p.sx[c * d + i] = xr(i);
-        p.sv[c * d + i] = vr(i);
-    }
-    if (lane == 0) {
-        p.st[c] = t; p.shorizon[c] = horizon; p.sar[c] = ar; p.status[c] = status;
-        p.counters[2 * c] = n_builds; p.counters[2 * c + 1] = n_rates;
-        p.tape_pos[3 * c] = pE; p.tape_pos[3 * c + 1] = pU;
-        p.ncols[c] += ev;
-    }
+    if (valid) store_chain();  // (without a work queue: the chain this warp started with)
 }
 
 template <int NA, bool SPLIT>

@@ -675,3 +675,28 @@ def test_rv_diagnostic_logistic_regression(p):
         rv = p.RV_diagnostic(hb, s.potential, B=B)
         ref = np.array([onp.rv_diagnostic(hb.X[c].T, hb.V[c].T, hb.t[c], opot.value, B=B) for c in range(nch)])
         assert np.allclose(rv, ref, rtol=1e-9, atol=0), (B, rv, ref)
+
+
+def test_logreg_work_queue_matches_static_assignment(p):
+    """With more chains than 4 x SMs the logistic-regression kernel runs persistent CTAs whose warps pull chains from
+    a work queue (logreg.cu).  Which warp ran a chain must not matter: a 1500-chain run equals the same chains run in
+    shards small enough for the static assignment, bit for bit, including a second launch (resume) and the
+    time-horizon variant with its ragged column counts."""
+    from oracle_cases import logreg_data
+    n, d, nch, n_sk = 96, 5, 1500, 9
+    X, y, s0 = logreg_data(n, d)
+    g = np.random.default_rng(13)
+    x0 = 0.3 * g.standard_normal((nch, d)); v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0)
+    s = p.ZigZagAD(d, p.LogReg(X, y, s0), grid_size=4)
+    big = p.sample_skeleton(s, n_sk, x0, v0, seed=77)
+    for lo in (0, 500, 1000):
+        part = p.sample_skeleton(s, n_sk, x0[lo:lo + 500], v0[lo:lo + 500], seed=77, chain_offset=lo)
+        for f in ("X", "V", "t", "horizon", "ar", "rejected", "hitting_horizon", "errored_bound"):
+            assert np.array_equal(getattr(big, f)[lo:lo + 500], getattr(part, f)), (lo, f)
+    assert (big.status == 0).all() and np.all(np.diff(big.t, axis=1) > 0)
+    T = float(np.median(big.t[:, -1]))
+    hs = p.sample_skeleton(s, T, x0, v0, seed=77)
+    hp = p.sample_skeleton(s, T, x0[700:1000], v0[700:1000], seed=77, chain_offset=700)
+    assert len({h.t.shape[0] for h in hs}) > 1
+    for a, b in zip(hs[700:1000], hp):
+        assert a.t.shape == b.t.shape and np.array_equal(a.X, b.X) and a.t[-1] == T
