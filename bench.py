@@ -42,7 +42,7 @@ CONFIGS = {
                 oracle=(3, 0, None, dict(tmax=1.0, refresh_rate=0.1, deriv_mode=1))),
 }
 DEFAULT_CHAINS = {"c1": 65536, "c2": 4096, "c3": 16384, "c4": 4096, "c5f": 8192, "c5b": 8192}
-DEFAULT_EVENTS = {"c1": 500, "c2": 1000, "c3": 300, "c4": 2, "c5f": 40, "c5b": 40}
+DEFAULT_EVENTS = {"c1": 500, "c2": 1000, "c3": 300, "c4": 8, "c5f": 40, "c5b": 40}
 
 
 def logreg_data(n, d, seed=2024, sigma0=10.0):
