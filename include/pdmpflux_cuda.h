@@ -49,11 +49,11 @@ typedef enum pdmpflux_sampler_kind {
  *   BANANA               -                      test/test_config.jl:33-36
  *   BANANA_README_SCALAR -                      README.md:62-65 (scalar "gradient" broadcast to all coords)
  *   LOGREG               n, sigma0, X[n*d] row-major, y[n]
- *   GAUSS_DENSE          P[d*d] (symmetric precision, row-major)
+ * (A dense-precision Gaussian is not offered: the only "slanted" Gaussian BASELINE names is GAUSS_EQUICORR.)
  */
 typedef enum pdmpflux_potential_kind {
     PDMPFLUX_GAUSS_STD = 0, PDMPFLUX_GAUSS_DIAG = 1, PDMPFLUX_GAUSS_EQUICORR = 2, PDMPFLUX_BANANA = 3,
-    PDMPFLUX_BANANA_README_SCALAR = 4, PDMPFLUX_LOGREG = 5, PDMPFLUX_GAUSS_DENSE = 6
+    PDMPFLUX_BANANA_README_SCALAR = 4, PDMPFLUX_LOGREG = 5
 } pdmpflux_potential_kind;
 
 /* How d/dt of the rate is obtained on the time grid: JVP = analytic (what AD_backend="ForwardDiff" computes,
@@ -138,6 +138,12 @@ int pdmpflux_potential_destroy(pdmpflux_potential_t pot);
 int pdmpflux_sampler_create(int sampler_kind, int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg,
                             pdmpflux_sampler_t* out);
 int pdmpflux_sampler_destroy(pdmpflux_sampler_t s);
+/* Ownership / threading of a sampler handle: the host-buffer pipeline of pdmpflux_sample_skeleton* caches its device
+ * slabs, pinned staging buffers and copy stream in the handle (they only grow; one large call keeps up to ~10 GiB of
+ * device memory until the handle is destroyed), so a handle must not be used by two host threads at once -- create one
+ * sampler per thread (handles are cheap; the potential may be shared).  release_workspace frees the cached buffers
+ * (synchronises the device); the next host-buffer call allocates them again. */
+int pdmpflux_sampler_release_workspace(pdmpflux_sampler_t s);
 /* the config after constructor rewrites */
 int pdmpflux_sampler_get_config(pdmpflux_sampler_t s, pdmpflux_config* out);
 
@@ -172,7 +178,10 @@ int pdmpflux_sample_skeleton_until(pdmpflux_sampler_t s, int64_t n_chains, doubl
                                    int64_t* n_cols_out, void* cuda_stream);
 
 /* Streaming form of the same loop: device-resident PDMPState array (the analogue of `sampler.state`,
- * src/sample.jl:281) that can be advanced in slices; lets skeletons larger than HBM stream to the host. */
+ * src/sample.jl:281) that can be advanced in slices; lets skeletons larger than HBM stream to the host.
+ * Stream ordering: chains_create / set_state / enable_moments / get_* synchronise the device themselves (device
+ * inputs produced on any stream are complete before they are read, and the set-up is complete before the call
+ * returns), so chains_advance / chains_record may run on any stream, including cudaStreamNonBlocking ones. */
 int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double* xinit, const double* vinit,
                            int32_t init_on_device, uint64_t seed, int64_t chain_offset,
                            const pdmpflux_tape* tape_or_null, pdmpflux_chains_t* out);
@@ -225,7 +234,7 @@ int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_ch
  * of (U(x(t_b)) - U(x(t_{b-1})))^2 / t[end], positions by the linear interpolation of _history_position_linear!
  * (src/diagnostic.jl:23-35) when flow_kind = 0; flow_kind = 1 interpolates with the Boomerang rotation, which is what
  * the online sample_skeleton_with_diagnostic (src/sample.jl:75-236) accumulates through sampler.flow.  U is the value
- * plugin of `pot` (Gaussians, banana, logistic regression; GAUSS_DENSE -> PDMPFLUX_ERR_UNSUPPORTED).  X, V: [C][ld_sk][d],
+ * plugin of `pot` (Gaussians, banana, logistic regression).  X, V: [C][ld_sk][d],
  * t: [C][ld_sk]; chain c uses its first ncols[c] columns (ncols == NULL: n_sk for all).  B = 0 -> floor(sqrt(n)) like
  * the reference, B < 0 -> PDMPFLUX_ERR_ARGUMENT (the reference's ArgumentError).  A chain whose t[end] is negative or
  * not finite gets rv = NaN (the binding raises the reference's ArgumentError). */

@@ -76,6 +76,7 @@ SIGNATURES = {
     "pdmpflux_potential_destroy": (C.c_int, [C.c_void_p]),
     "pdmpflux_sampler_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "pdmpflux_sampler_destroy": (C.c_int, [C.c_void_p]),
+    "pdmpflux_sampler_release_workspace": (C.c_int, [C.c_void_p]),
     "pdmpflux_sampler_get_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
     "pdmpflux_sample_skeleton": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint64,
                                            C.c_int64, C.POINTER(Tape), C.POINTER(History), C.c_void_p]),

@@ -124,15 +124,23 @@ struct pdmpflux_chains_s {
 
 namespace {
 
-int pick_team(int d, int64_t n_chains) {
+// Team widths built: 1, 8, 32 for everything; 4 only for the register-resident Zig-Zag x Brent kernels (launch.cuh).
+int pick_team(int d, int64_t n_chains, bool zz_brent_fast) {
     if (const char* e = std::getenv("PDMPFLUX_TEAM")) {
-        const int t = std::atoi(e);
-        if (t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32) return t;
+        const int t = std::atoi(e);  // only the team widths launch_for_sampler instantiates
+        if (t == 1 || t == 8 || t == 32) return t;
+        if (t == 4 && zz_brent_fast && d <= 64) return t;
+#ifdef PDMPFLUX_EXTRA_TEAM
+        if (t == PDMPFLUX_EXTRA_TEAM) return t;
+#endif
     }
     // Measured on B200 (profiles/): thread-per-chain wins for small d once there are enough chains to occupy the
     // SMs; 8 lanes per chain win for d up to a few hundred (fewer shuffle stages than a full warp, 4 chains share a
     // warp's instruction stream); a warp per chain beyond that (and whenever the shared-memory state would not fit).
     if (d <= 16) return n_chains >= 8192 ? 1 : 8;
+    // Zig-Zag x Brent is a serial recurrence of ~40 rate evaluations per bound whose scalar part every lane of the
+    // team repeats: 4 lanes per chain (<= 16 coordinates per lane, line model in registers) halve that redundancy.
+    if (zz_brent_fast && d <= 64) return 4;
     if (d <= 256) return 8;
     return 32;
 }
@@ -423,9 +431,6 @@ int pdmpflux_potential_create(int kind, int dim, const double* params, int64_t n
         pot->pp.n = n;
         pot->pp.inv_s2 = 1.0 / (s0 * s0);
     } break;
-    case PDMPFLUX_GAUSS_DENSE:
-        rc = fail(PDMPFLUX_ERR_UNSUPPORTED, "potential kind not available on the device path yet (no CPU fallback)");
-        break;
     default: rc = fail(PDMPFLUX_ERR_ARGUMENT, "unknown potential kind " + std::to_string(kind));
     }
     if (rc != PDMPFLUX_OK) { delete pot; return rc; }
@@ -464,6 +469,13 @@ int pdmpflux_sampler_create(int kind, int dim, pdmpflux_potential_t pot, const p
     return PDMPFLUX_OK;
 }
 int pdmpflux_sampler_destroy(pdmpflux_sampler_t s) { delete s; return PDMPFLUX_OK; }
+int pdmpflux_sampler_release_workspace(pdmpflux_sampler_t s) {
+    if (!s) return fail(PDMPFLUX_ERR_ARGUMENT, "sampler is NULL");
+    CUDA_TRY(cudaDeviceSynchronize());
+    s->ws.~Workspace();
+    new (&s->ws) Workspace();
+    return PDMPFLUX_OK;
+}
 int pdmpflux_sampler_get_config(pdmpflux_sampler_t s, pdmpflux_config* out) {
     if (!s || !out) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
     *out = s->cfg;
@@ -485,7 +497,9 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     ch->s = s; ch->n_chains = n_chains; ch->chain_offset = chain_offset; ch->seed = seed;
     const int d = s->dim;
     const bool logreg = s->pot->kind == PDMPFLUX_LOGREG;
-    ch->team = pick_team(d, n_chains);
+    ch->path = select_path(s->kind, s->pot->kind, s->cfg.grid_size, s->cfg.vectorized_bound, s->cfg.deriv_mode);
+    if (const char* e = std::getenv("PDMPFLUX_FORCE_GENERIC")) { if (std::atoi(e)) ch->path = kPathGeneric; }
+    ch->team = pick_team(d, n_chains, s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && !logreg);
     // widen the team until x and v (per-thread-owned shared-memory columns) fit next to a second block
     while (ch->team < 32 && 4 * (size_t)((d + ch->team - 1) / ch->team) * kBlockThreads * sizeof(double) > 100 * 1024)
         ch->team = ch->team < 8 ? 8 : 32;
@@ -499,9 +513,8 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
         ch->vec_elems = cpb * ch->dpad;
     }
     const size_t vec_bytes = (size_t)ch->vec_elems * sizeof(double);
-    ch->path = select_path(s->kind, s->pot->kind, s->cfg.grid_size, s->cfg.vectorized_bound, s->cfg.deriv_mode);
-    if (const char* e = std::getenv("PDMPFLUX_FORCE_GENERIC")) { if (std::atoi(e)) ch->path = kPathGeneric; }
-    const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent) ? 4 : 2;
+    const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent &&
+                         brent_reg_nw(s->kind, ch->path, ch->team, ch->n_own) == 0) ? 4 : 2;
     ch->smem = nvec * vec_bytes;
     if (s->kind == PDMPFLUX_FECMC) {
         if ((nvec + 3) * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = (nvec + 3) * vec_bytes; }
@@ -538,6 +551,10 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     CUDA_TRY(ch->status.alloc(sizeof(int32_t) * n_chains));
     CUDA_TRY(ch->counters.alloc(sizeof(int64_t) * 2 * n_chains));
     CUDA_TRY(ch->ncols.alloc(sizeof(int64_t) * n_chains));
+    // Stream ordering: the set-up below runs on the legacy default stream, the kernels later run on the caller's stream
+    // (possibly cudaStreamNonBlocking).  Device inputs may still be in flight on the caller's stream, so wait for the
+    // device first; the stream is drained again before returning, so every later launch sees initialised state.
+    if (init_on_device || (tape && tape->on_device)) CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemset(ch->ncols.p, 0, sizeof(int64_t) * n_chains));
     const cudaMemcpyKind k = init_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CUDA_TRY(cudaMemcpy(ch->x.p, xinit, sizeof(double) * d * n_chains, k));
@@ -566,6 +583,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
             ch->dE = ch->tE.as<double>(); ch->dU = ch->tU.as<double>(); ch->dN = ch->tN.as<double>();
         }
     }
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));  // set-up complete before any launch on any stream
     guard.c = nullptr;
     *out = ch;
     return PDMPFLUX_OK;
@@ -576,8 +594,11 @@ int pdmpflux_chains_set_state(pdmpflux_chains_t ch, const double* t, const doubl
     if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
     if (event0 < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "event0 must be >= 0");
     const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    // earlier launches of these chains (any stream) and the producer of device inputs must be done; see chains_create
+    if (t || horizon) CUDA_TRY(cudaDeviceSynchronize());
     if (t) CUDA_TRY(cudaMemcpy(ch->t.p, t, sizeof(double) * ch->n_chains, k));
     if (horizon) CUDA_TRY(cudaMemcpy(ch->horizon.p, horizon, sizeof(double) * ch->n_chains, k));
+    if (t || horizon) CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
     ch->event0 = event0;
     return PDMPFLUX_OK;
 }
@@ -586,6 +607,7 @@ int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double
     if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
     const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const size_t nd = sizeof(double) * ch->s->dim * ch->n_chains;
+    CUDA_TRY(cudaDeviceSynchronize());  // launches on a non-blocking stream are not ordered before legacy-stream copies
     if (x) CUDA_TRY(cudaMemcpy(x, ch->x.p, nd, k));
     if (v) CUDA_TRY(cudaMemcpy(v, ch->v.p, nd, k));
     if (t) CUDA_TRY(cudaMemcpy(t, ch->t.p, sizeof(double) * ch->n_chains, k));
@@ -600,6 +622,7 @@ int pdmpflux_chains_enable_moments(pdmpflux_chains_t ch) {
     const size_t nd = sizeof(double) * ch->s->dim * ch->n_chains;
     CUDA_TRY(ch->m1.alloc(nd)); CUDA_TRY(ch->m2.alloc(nd));
     CUDA_TRY(cudaMemset(ch->m1.p, 0, nd)); CUDA_TRY(cudaMemset(ch->m2.p, 0, nd));
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));  // zeroed before the next launch on the caller's stream
     ch->moments = 1;
     return PDMPFLUX_OK;
 }
@@ -608,6 +631,7 @@ int pdmpflux_chains_get_moments(pdmpflux_chains_t ch, double* m1, double* m2, in
     if (!ch || !ch->moments) return fail(PDMPFLUX_ERR_ARGUMENT, "moments are not enabled on these chains");
     const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const size_t nd = sizeof(double) * ch->s->dim * ch->n_chains;
+    CUDA_TRY(cudaDeviceSynchronize());
     if (m1) CUDA_TRY(cudaMemcpy(m1, ch->m1.p, nd, k));
     if (m2) CUDA_TRY(cudaMemcpy(m2, ch->m2.p, nd, k));
     return PDMPFLUX_OK;
@@ -623,6 +647,7 @@ int pdmpflux_chains_set_stop_time(pdmpflux_chains_t ch, double T) {
 
 int pdmpflux_chains_get_ncols(pdmpflux_chains_t ch, int64_t* ncols) {
     if (!ch || !ncols) return fail(PDMPFLUX_ERR_ARGUMENT, "NULL argument");
+    CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(ncols, ch->ncols.p, sizeof(int64_t) * ch->n_chains, cudaMemcpyDeviceToHost));
     return PDMPFLUX_OK;
 }
@@ -646,6 +671,7 @@ int pdmpflux_chains_record(pdmpflux_chains_t ch, const pdmpflux_history* h, int6
 int pdmpflux_chains_status(pdmpflux_chains_t ch, int32_t* status, int64_t* tape_pos, int64_t* counters) {
     if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
     std::vector<int32_t> st((size_t)ch->n_chains);
+    CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(st.data(), ch->status.p, sizeof(int32_t) * ch->n_chains, cudaMemcpyDeviceToHost));
     if (status) std::memcpy(status, st.data(), sizeof(int32_t) * ch->n_chains);
     if (tape_pos) CUDA_TRY(cudaMemcpy(tape_pos, ch->tape_pos.p, sizeof(int64_t) * 3 * ch->n_chains, cudaMemcpyDeviceToHost));
@@ -1119,8 +1145,6 @@ int pdmpflux_rv_diagnostic(pdmpflux_potential_t pot, int flow_kind, int64_t n_sk
         return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
     if (B < 0) return fail(PDMPFLUX_ERR_ARGUMENT, "B must be non-negative");  // diagnostic.jl:49-51
     if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear) or 1 (rotation)");
-    if (pot->kind == PDMPFLUX_GAUSS_DENSE)
-        return fail(PDMPFLUX_ERR_UNSUPPORTED, "no device U(x) plugin for this potential");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: no CPU fallback");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -54,10 +54,16 @@ extern __shared__ __align__(128) double g_smem[];
 // Results differ from the generic path (and the oracle) only by floating-point reassociation (~1e-16 relative).
 enum { kPathGeneric = 0, kPathFastBrent = 1, kPathFastGrid = 2 };
 
-template <int TEAM, int SAMPLER, int POT, int PATH>
+// NW > 0 (Zig-Zag + kPathFastBrent only): compile-time capacity of the owned-coordinate loops; the line model
+// (A_j, B_j) of the owned coordinates then lives in registers (slots >= n_own hold A = B = 0) and the ~40 rate
+// evaluations of a Brent bound touch neither shared memory nor any loop counter.
+template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
 struct Chain {
     using P = Pot<POT>;
     static constexpr bool kFast = (PATH != kPathGeneric);
+    static constexpr bool kRegLine = (NW > 0);
+    static constexpr int NWW = NW > 0 ? NW : 1;
+    static_assert(NW == 0 || (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent), "NW is a Zig-Zag x Brent option");
     static constexpr int NS = P::kSpecial;
     static constexpr int K = P::K;
     static constexpr int KK = K > 0 ? K : 1;
@@ -79,6 +85,7 @@ struct Chain {
     double Lx[KK], Lv[KK];  // functionals of the current (x, v)
     // fast-path line model of the current (x, v)
     // (ZigZag + Brent keeps the per-owned-coordinate A_j, B_j in shared memory: AS(j), BS(j))
+    double ra[NWW], rb[NWW];  // NW > 0: A_j, B_j of the owned coordinates (registers: only indexed by unrolled loops)
     double la, lb;          // BPS/FECMC: a = sum A_i, b = sum B_i over the affine coordinates
     double pxx, pxv, pvv;   // Boomerang: <Px,x>, <Px,v>, <Pv,v>
 
@@ -160,8 +167,9 @@ struct Chain {
                 return;
             }
         }
-        z0 = rand_normal_at(coord(j0));
-        z1 = rand_normal_at(coord(j0 + 1));
+        // tape mode: lanes that do not own the coordinate must not read it (it may lie beyond the chain's tape)
+        z0 = owns(j0) ? rand_normal_at(coord(j0)) : 0.0;
+        z1 = owns(j0 + 1) ? rand_normal_at(coord(j0 + 1)) : 0.0;
     }
     // v_j <- N(0,1) for every owned coordinate (BPS / Boomerang refresh); returns the lane's partial sum of squares
     __device__ double refresh_velocity_normals() {
@@ -311,7 +319,19 @@ struct Chain {
             team_sum_n<TEAM, 3>(r3, mask);
             pxx = r3[0]; pxv = r3[1]; pvv = r3[2];
         } else if constexpr (kZZ) {
-            if constexpr (PATH == kPathFastBrent) {
+            if constexpr (kRegLine) {
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {
+                    double A = 0.0, B = 0.0;  // A = B = 0 contributes max(0, 0) = 0 for unowned / special / padding slots
+                    if (j < nown && owns(j) && coord(j) >= NS) {
+                        const double vi = VS(j);
+                        double g, hv;
+                        P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
+                        A = g * vi; B = hv * vi;
+                    }
+                    ra[j] = A; rb[j] = B;
+                }
+            } else if constexpr (PATH == kPathFastBrent) {
                 for (int j = 0; j < nown; ++j) {
                     double A = 0.0, B = 0.0;  // A = B = 0 contributes max(0, 0) = 0 for unowned / special slots
                     if (owns(j) && coord(j) >= NS) {
@@ -371,6 +391,24 @@ struct Chain {
             double y, dy;
             line_scalar(tt, y, dy);
             return (y > 0.0 ? y : 0.0) + extra_rate();
+        } else if constexpr (kRegLine) {
+            // max(0, y) = (y + |y|) / 2 exactly in binary floating point; four accumulators, everything in registers
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const double y = fma(tt, rb[j], ra[j]);
+                acc[j & 3] += y + fabs(y);
+            }
+            double sp_ = 0.0;  // special coordinates: independent of the reduction, evaluated while the shuffles fly
+            if constexpr (NS > 0) {
+                double ys[NS], dys[NS];
+                special_rates(tt, ys, dys);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) sp_ += ys[k] + fabs(ys[k]);
+                sp_ *= 0.5;
+            }
+            const double s = team_sum<TEAM>((acc[0] + acc[1]) + (acc[2] + acc[3]), mask);
+            return fma(0.5, s, sp_);
         } else if constexpr (kZZ && PATH == kPathFastBrent) {
             // max(0, y) = (y + |y|) / 2 exactly in binary floating point: one DADD (|.| is an operand modifier)
             // instead of a compare and two selects; the halving is applied once to the sum.
@@ -770,44 +808,70 @@ struct Chain {
     }
 
     // upper_bound_constant, UpperBound.jl:18-36: Optim.jl Brent on t -> -rate(t) over [0, h]
+    //
+    // The recurrence is Optim's (restated in SURVEY.md Appendix B); it is written here so that
+    //   * every rounding is the reference's: Julia does not contract a*b+c, so the few places where nvcc would fuse
+    //     (tol, the parabola numerator, the first abscissa) use __dmul_rn / __dadd_rn, which are never contracted --
+    //     with bit-identical rate values the iterates are bit-identical to a CPU evaluation of the same recurrence;
+    //   * the bookkeeping at the end of an iteration (bracket, best three points) is a fixed set of selects and the
+    //     compound conditions are evaluated without short-circuit branches: lanes of a warp belong to different chains,
+    //     so both sides of those tiny branches would be executed anyway, plus the divergence bookkeeping
+    //     (BSSY / BSYNC / re-convergence) in the hottest loop of the Brent configurations;
+    //   * the parabolic step itself (an IEEE division: 124 cycles of latency on B200, measured) stays behind a real
+    //     branch: for the piecewise-linear Zig-Zag rates the maximum sits at an end of [0, h], the parabola through
+    //     three collinear points is degenerate and Brent takes golden-section steps only (BASELINE config C2: not one
+    //     parabolic step in 2.4e4 iterations), so the warps skip the division altogether.
     __device__ void build_bound_brent(double h) {
         const double golden = 0.3819660112501051;  // (3 - sqrt(5)) / 2
         double lo = 0.0, hi = h;
-        double x = lo + golden * (hi - lo);
+        double x = __dadd_rn(lo, __dmul_rn(golden, __dadd_rn(hi, -lo)));
         double fx = -rate_unsigned(x);
         double stp = 0.0, old_step = 0.0, w = x, vv = x, fw = fx, fv = fx;
-        for (int it = 0; it < 1000;) {
-            double pp = 0.0, q = 0.0;
-            const double tol = kSqrtEps * fabs(x) + kEps;
-            const double mid = (hi + lo) / 2;
-            if (fabs(x - mid) <= 2 * tol - (hi - lo) / 2) break;
-            ++it;
-            if (fabs(old_step) > tol) {
-                const double r = (x - w) * (fx - fv);
-                q = (x - vv) * (fx - fw);
-                pp = (x - vv) * q - (x - w) * r;
-                q = 2 * (q - r);
-                if (q > 0) pp = -pp; else q = -q;
+        for (int it = 0; it < 1000; ++it) {
+            const double tol = __dadd_rn(__dmul_rn(kSqrtEps, fabs(x)), kEps);
+            const double tol2 = tol + tol;
+            const double mid = (hi + lo) * 0.5;                      // (hi + lo) / 2
+            if (fabs(x - mid) <= fma(hi - lo, -0.5, tol2)) break;    // 2 tol - (hi - lo) / 2: the halving is exact
+            // parabola through (x, fx), (w, fw), (v, fv); only used when |old_step| > tol
+            const double xw = x - w, xv = x - vv;
+            const double r = xw * (fx - fv);
+            double q = xv * (fx - fw);
+            double pp = __dadd_rn(__dmul_rn(xv, q), -__dmul_rn(xw, r));
+            q = q - r;
+            q = q + q;                                               // 2 (q - r)
+            pp = (q > 0.0) ? -pp : pp;
+            q = fabs(q);                                             // `if q > 0: p = -p else: q = -q`
+            const double hx = hi - x, xl = x - lo;
+            const bool use_para = (int)(fabs(old_step) > tol) & (int)(fabs(pp) < fabs(q * old_step * 0.5)) &
+                                  (int)(pp < q * hx) & (int)(pp < q * xl);
+            // golden-section step
+            const double og = (x < mid) ? hx : -xl;                  // hi - x : lo - x
+            double new_old = og, new_stp = golden * og;
+            if (use_para) {                                          // parabolic step
+                double sp = pp / q;
+                const double xt = x + sp;
+                const bool near_end = (int)((xt - lo) < tol2) | (int)((hi - xt) < tol2);
+                sp = near_end ? ((x < mid) ? tol : -tol) : sp;
+                new_old = stp; new_stp = sp;
             }
-            if (fabs(pp) < fabs(q * old_step / 2) && pp < q * (hi - x) && pp < q * (x - lo)) {
-                old_step = stp;
-                stp = pp / q;
-                const double xt = x + stp;
-                if ((xt - lo) < 2 * tol || (hi - xt) < 2 * tol) stp = (x < mid) ? tol : -tol;
-            } else {
-                old_step = (x < mid) ? hi - x : lo - x;
-                stp = golden * old_step;
-            }
-            const double u = (fabs(stp) >= tol) ? x + stp : x + ((stp > 0) ? tol : -tol);
+            old_step = new_old; stp = new_stp;
+            const double u = x + ((fabs(stp) >= tol) ? stp : ((stp > 0.0) ? tol : -tol));
             const double fu = -rate_unsigned(u);
-            if (fu < fx) {
-                if (u < x) hi = x; else lo = x;
-                vv = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
-            } else {
-                if (u < x) lo = u; else hi = u;
-                if (fu <= fw || w == x) { vv = w; fv = fw; w = u; fw = fu; }
-                else if (fu <= fv || vv == x || vv == w) { vv = u; fv = fu; }
-            }
+            // bookkeeping (all conditions on the values before the update)
+            const bool better = fu < fx, left = u < x;
+            const bool c1 = (int)(fu <= fw) | (int)(w == x);
+            const bool c2 = (int)(fu <= fv) | (int)(vv == x) | (int)(vv == w);
+            const double nbk = better ? x : u;                       // new end of the bracket ...
+            const bool set_hi = (better == left);                    // ... better: (u < x ? hi : lo) = x; else: (u < x ? lo : hi) = u
+            hi = set_hi ? nbk : hi;
+            lo = set_hi ? lo : nbk;
+            const bool v_w = better | c1, v_u = !v_w & c2;
+            vv = v_w ? w : (v_u ? u : vv);
+            fv = v_w ? fw : (v_u ? fu : fv);
+            w = better ? x : (c1 ? u : w);
+            fw = better ? fx : (c1 ? fu : fw);
+            x = better ? u : x;
+            fx = better ? fu : fx;
         }
         BOX(0) = -fx + 0.0;  // init_state passes no refresh here (AbstractPDMP.jl:122-125)
         CUM(0) = 0.0; CUM(1) = BOX(0) * (h - 0.0);
@@ -1119,31 +1183,55 @@ struct Chain {
 #pragma unroll
         for (int k = 0; k < KK; ++k) Lxn[k] = Lx[k] + Lv[k] * tt;
         const double uS = rand_uniform() * S;
-        double carry = 0.0;
-        int m = d - 1;
-        bool found = false;
-        for (int j = 0; j < nown; ++j) {
-            double lj = 0.0;
-            if (owns(j)) {
+        if constexpr (TEAM == 1) {
+            double cum = 0.0;
+            int m = d - 1;
+            bool found = false;
+            for (int j = 0; j < nown; ++j) {
                 const double vi = VS(j);
                 const double xn = XS(j) + vi * tt;
                 XS(j) = xn;
-                const double y = P::grad(p.pot, coord(j), xn, Lxn) * vi;
-                lj = (y > 0.0 ? y : 0.0);
+                const double y = P::grad(p.pot, j, xn, Lxn) * vi;
+                cum += (y > 0.0 ? y : 0.0);
+                if (!found && cum > uS) { m = j; found = true; }
             }
-            const double incl = team_scan_incl<TEAM>(lj, mask, tl) + carry;
-            const bool hit = !found && owns(j) && (incl > uS);
-            int first = -1;
-            if constexpr (TEAM == 1) first = hit ? 0 : -1;
-            else {
-                unsigned b = __ballot_sync(mask, hit) & mask;
-                b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
-                first = b ? (__ffs(b) - 1) : -1;
+            VS(m) = -VS(m);
+        } else {
+            // The categorical scan runs over the coordinates in order.  With the strided ownership of the other passes
+            // that is one team-wide scan per owned row (n_own serial scans); here the team instead splits the chain's
+            // contiguous shared-memory row into TEAM blocks of n_own consecutive coordinates: a serial pass inside the
+            // lane, ONE scan over the lanes' block totals, and a short search inside the block that holds the index.
+            __syncwarp(mask);  // x / v written under the strided ownership are visible to the whole team
+            const int cbx = off_x - tl, cbv = off_v - tl;  // element offset of the chain's coordinate 0
+            const int i0 = tl * nown, i1 = min(d, i0 + nown);
+            double tot = 0.0;
+            for (int i = i0; i < i1; ++i) {
+                const double vi = g_smem[cbv + i];
+                const double xn = g_smem[cbx + i] + vi * tt;
+                g_smem[cbx + i] = xn;
+                const double y = P::grad(p.pot, i, xn, Lxn) * vi;
+                tot += (y > 0.0 ? y : 0.0);
             }
-            if (first >= 0) { m = first + TEAM * j; found = true; }
-            carry = team_bcast<TEAM>(incl, TEAM - 1, mask);
+            const double incl = team_scan_incl<TEAM>(tot, mask, tl);
+            double excl = __shfl_up_sync(mask, incl, 1, TEAM);
+            if (tl == 0) excl = 0.0;
+            unsigned b = __ballot_sync(mask, (i0 < i1) && (incl > uS)) & mask;
+            b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
+            const int first = b ? (__ffs(b) - 1) : -1;
+            if (first < 0) {  // rounding left the total below u S: the reference's scan ends on the last index
+                if (tl == (d - 1) / nown) g_smem[cbv + d - 1] = -g_smem[cbv + d - 1];
+            } else if (tl == first) {
+                double cum = excl;
+                int m = i1 - 1;
+                for (int i = i0; i < i1; ++i) {
+                    const double y = P::grad(p.pot, i, g_smem[cbx + i], Lxn) * g_smem[cbv + i];
+                    cum += (y > 0.0 ? y : 0.0);
+                    if (cum > uS) { m = i; break; }
+                }
+                g_smem[cbv + m] = -g_smem[cbv + m];
+            }
+            __syncwarp(mask);
         }
-        if (m % TEAM == tl) { const int j = m / TEAM; VS(j) = -VS(j); }
     }
 
     __device__ void velocity_jump() {
@@ -1455,7 +1543,7 @@ struct Chain {
 
 // One launch advances every chain by p.n_events accepted events (or just records the current state when
 // n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
-template <int TEAM, int SAMPLER, int POT, int PATH>
+template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
 __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PATH == kPathFastBrent ? 2 : 4)) skeleton_kernel(const __grid_constant__ KernelParams p) {
     constexpr int CPB = kBlockThreads / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
@@ -1463,7 +1551,7 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
     const bool valid = c_raw < p.n_chains;  // out-of-range lanes stay (warp-wide votes) but never touch memory
     const int64_t c = valid ? c_raw : 0;
 
-    Chain<TEAM, SAMPLER, POT, PATH> ch(p);
+    Chain<TEAM, SAMPLER, POT, PATH, NW> ch(p);
     ch.tl = threadIdx.x % TEAM;
     ch.mask = team_mask<TEAM>();
     ch.d = p.d;
@@ -1476,7 +1564,7 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
     ch.off_v = vec + toff;
     int used = 2;
     ch.off_a = ch.off_b = 0;
-    if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent) {
+    if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent && NW == 0) {
         ch.off_a = 2 * vec + toff;
         ch.off_b = 3 * vec + toff;
         used = 4;

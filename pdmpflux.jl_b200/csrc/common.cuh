@@ -16,7 +16,7 @@ constexpr double kEps = 2.220446049250313e-16;
 
 // Device-side potential parameters (owned by pdmpflux_potential_s).
 struct PotParams {
-    const double* vec;   // GAUSS_DIAG: p[d]; GAUSS_DENSE: P[d*d]; LOGREG: X[n*d]
+    const double* vec;   // GAUSS_DIAG: p[d]; LOGREG: X[n*d]
     const double* vec2;  // LOGREG: y[n]
     double alpha, beta;  // GAUSS_EQUICORR
     double inv_s2;       // LOGREG prior precision

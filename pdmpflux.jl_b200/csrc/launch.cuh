@@ -4,14 +4,22 @@
 
 namespace pdmpflux {
 
-template <int TEAM, int SAMPLER, int POT, int PATH>
+// Zig-Zag + Brent: capacity of the register-resident line model (0: the shared-memory A/B arrays are used).
+// Mirrors the instantiations below; api.cu sizes the shared memory with it.
+inline int brent_reg_nw(int sampler, int path, int team, int n_own) {
+    if (sampler != PDMPFLUX_ZIGZAG || path != kPathFastBrent) return 0;
+    if (team != 4 && team != 8) return 0;
+    return n_own <= 8 ? 8 : (n_own <= 16 ? 16 : 0);
+}
+
+template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
 cudaError_t launch_one(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
     // combinations without a fast path fall back to the generic kernel (same results, more passes)
     constexpr bool ok = PATH == kPathGeneric ||
                         (Pot<POT>::kAffine && !(SAMPLER == PDMPFLUX_BOOMERANG && Pot<POT>::kSpecial > 0));
     if constexpr (!ok) return cudaErrorInvalidValue;
     else {
-        auto kern = skeleton_kernel<TEAM, SAMPLER, POT, PATH>;
+        auto kern = skeleton_kernel<TEAM, SAMPLER, POT, PATH, NW>;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -23,11 +31,28 @@ cudaError_t launch_one(const KernelParams& p, unsigned grid, size_t smem, cudaSt
 
 template <int TEAM, int SAMPLER, int POT>
 cudaError_t launch_for_pot(int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
-    switch (path) {
-    case kPathGeneric: return launch_one<TEAM, SAMPLER, POT, kPathGeneric>(p, grid, smem, stream);
-    case kPathFastBrent: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent>(p, grid, smem, stream);
-    case kPathFastGrid: return launch_one<TEAM, SAMPLER, POT, kPathFastGrid>(p, grid, smem, stream);
-    default: return cudaErrorInvalidValue;
+    if constexpr (TEAM == 4) {  // only built for the register-resident Zig-Zag x Brent kernels
+        if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && Pot<POT>::kAffine) {
+            switch (brent_reg_nw(SAMPLER, path, TEAM, p.n_own)) {
+            case 8: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 8>(p, grid, smem, stream);
+            case 16: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 16>(p, grid, smem, stream);
+            }
+        }
+        return cudaErrorInvalidValue;
+    } else {
+        switch (path) {
+        case kPathGeneric: return launch_one<TEAM, SAMPLER, POT, kPathGeneric>(p, grid, smem, stream);
+        case kPathFastBrent:
+            if constexpr (TEAM == 8 && SAMPLER == PDMPFLUX_ZIGZAG && Pot<POT>::kAffine) {
+                switch (brent_reg_nw(SAMPLER, path, TEAM, p.n_own)) {
+                case 8: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 8>(p, grid, smem, stream);
+                case 16: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 16>(p, grid, smem, stream);
+                }
+            }
+            return launch_one<TEAM, SAMPLER, POT, kPathFastBrent>(p, grid, smem, stream);
+        case kPathFastGrid: return launch_one<TEAM, SAMPLER, POT, kPathFastGrid>(p, grid, smem, stream);
+        default: return cudaErrorInvalidValue;
+        }
     }
 }
 
@@ -49,6 +74,9 @@ cudaError_t launch_for_sampler(int team, int pot, int path, const KernelParams& 
                                cudaStream_t stream) {
     switch (team) {
     case 1: return launch_for_team<1, SAMPLER>(pot, path, p, grid, smem, stream);
+    case 4:
+        if constexpr (SAMPLER == PDMPFLUX_ZIGZAG) return launch_for_team<4, SAMPLER>(pot, path, p, grid, smem, stream);
+        else return cudaErrorInvalidValue;
 #ifdef PDMPFLUX_EXTRA_TEAM
     case PDMPFLUX_EXTRA_TEAM: return launch_for_team<PDMPFLUX_EXTRA_TEAM, SAMPLER>(pot, path, p, grid, smem, stream);
 #endif

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 
-GAUSS_STD, GAUSS_DIAG, GAUSS_EQUICORR, BANANA, BANANA_README_SCALAR, LOGREG, GAUSS_DENSE = range(7)
+GAUSS_STD, GAUSS_DIAG, GAUSS_EQUICORR, BANANA, BANANA_README_SCALAR, LOGREG = range(6)
 
 
 class Potential:
