@@ -857,21 +857,25 @@ struct Chain {
             old_step = new_old; stp = new_stp;
             const double u = x + ((fabs(stp) >= tol) ? stp : ((stp > 0.0) ? tol : -tol));
             const double fu = -rate_unsigned(u);
-            // bookkeeping (all conditions on the values before the update)
-            const bool better = fu < fx, left = u < x;
-            const bool c1 = (int)(fu <= fw) | (int)(w == x);
-            const bool c2 = (int)(fu <= fv) | (int)(vv == x) | (int)(vv == w);
-            const double nbk = better ? x : u;                       // new end of the bracket ...
-            const bool set_hi = (better == left);                    // ... better: (u < x ? hi : lo) = x; else: (u < x ? lo : hi) = u
-            hi = set_hi ? nbk : hi;
-            lo = set_hi ? lo : nbk;
-            const bool v_w = better | c1, v_u = !v_w & c2;
-            vv = v_w ? w : (v_u ? u : vv);
-            fv = v_w ? fw : (v_u ? fu : fv);
-            w = better ? x : (c1 ? u : w);
-            fw = better ? fx : (c1 ? fu : fw);
-            x = better ? u : x;
-            fx = better ? fu : fx;
+            // bookkeeping.  A new best point shifts (x, w, v) <- (u, x, w): plain register moves behind a branch that is
+            // uniform whenever the chains of the warp agree (always, on the monotone rates of the Zig-Zag
+            // configurations); the other outcomes are a fixed set of selects on the values before the update.
+            const bool left = u < x;
+            if (fu < fx) {
+                hi = left ? x : hi;
+                lo = left ? lo : x;
+                vv = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+            } else {
+                const bool c1 = (int)(fu <= fw) | (int)(w == x);
+                const bool c2 = (int)(fu <= fv) | (int)(vv == x) | (int)(vv == w);
+                lo = left ? u : lo;
+                hi = left ? hi : u;
+                const bool v_u = !c1 & c2;
+                vv = c1 ? w : (v_u ? u : vv);
+                fv = c1 ? fw : (v_u ? fu : fv);
+                w = c1 ? u : w;
+                fw = c1 ? fu : fw;
+            }
         }
         BOX(0) = -fx + 0.0;  // init_state passes no refresh here (AbstractPDMP.jl:122-125)
         CUM(0) = 0.0; CUM(1) = BOX(0) * (h - 0.0);

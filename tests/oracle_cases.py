@@ -2,7 +2,7 @@
 import numpy as np
 
 ZIGZAG, BPS, FECMC, BOOMERANG = 0, 1, 2, 3
-GAUSS_STD, GAUSS_DIAG, GAUSS_EQUICORR, BANANA, BANANA_README, LOGREG, GAUSS_DENSE = range(7)
+GAUSS_STD, GAUSS_DIAG, GAUSS_EQUICORR, BANANA, BANANA_README, LOGREG = range(6)
 
 # name, sampler, potential, pot_params, dim, config kwargs, n_sk
 CASES = [
@@ -32,6 +32,8 @@ CASES = [
     ("boom_banana_jvp", BOOMERANG, BANANA, None, 4, dict(tmax=1.0, refresh_rate=0.1), 1000),
     ("boom_diag_brent", BOOMERANG, GAUSS_DIAG, "linspace", 6, dict(tmax=1.0, refresh_rate=0.1, grid_size=0), 500),
     ("boom_equi64", BOOMERANG, GAUSS_EQUICORR, [0.3], 64, dict(tmax=1.0, refresh_rate=0.3), 500),
+    # BASELINE.json config 5b at full dimension: Boomerang d = 1000, finite-difference bound, every event a 1000-normal refresh
+    ("boom1000_fd", BOOMERANG, GAUSS_STD, None, 1000, dict(tmax=1.0, refresh_rate=0.1, deriv_mode=1), 120),
     # Bayesian logistic regression (BASELINE.json config 4 in miniature): n rows, prior N(0, 10^2 I)
     ("zz_logreg5_n40", ZIGZAG, LOGREG, "logreg:40", 5, dict(grid_size=6), 300),
     ("zz_logreg100_n300", ZIGZAG, LOGREG, "logreg:300", 100, dict(grid_size=10), 120),
@@ -79,9 +81,13 @@ def case_inputs(name, sampler, d, n_sk, n_chains=1, seed=0):
 
 
 def tier_tolerance(kw, base=1e-10):
-    """Parity tiers (DESIGN.md): analytic-derivative grid bounds are held to `base` (the north_star's 1e-10);
-    Brent (grid_size=0) and sqrt(eps) finite differences amplify last-bit summation-order differences by up
-    to 1/sqrt(eps) ~ 7e7, so their one-step tolerance is 1e-6."""
-    if kw.get("grid_size", 10) == 0 or kw.get("deriv_mode", 0) == 1:
+    """Parity tiers.  Everything with an analytic derivative -- grid bounds AND the constant
+    (Brent) bound -- is held to `base`, the north_star's 1e-10: the Brent recurrence is evaluated without
+    multiply-add contraction, i.e. with the reference's roundings, and the achieved one-step errors are <= 4e-14
+    (profiles/r2_parity_errors.json).  Only the sqrt(eps) finite-difference derivative mode keeps a looser tier:
+    dividing O(1e-16) summation-order differences by h = sqrt(eps) leaves ~1e-8 in the derivative (measured worst
+    case 1.6e-8, zz_banana5_grid_fd; the two CPU restatements differ by the same amount), so it is held to 1e-6 and
+    documented as a deviation from the 1e-10 target."""
+    if kw.get("deriv_mode", 0) == 1:
         return 1e-6
     return base

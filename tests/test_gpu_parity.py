@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 
 import oracle_c as oc
+from conftest import record_parity_error
 from oracle_cases import CASES, case_inputs, pot_params, tier_tolerance
 
 pytestmark = pytest.mark.gpu
@@ -65,12 +66,14 @@ def set_team(team):
 
 
 @pytest.mark.parametrize("generic", [0, 1], ids=["auto", "generic"])
-@pytest.mark.parametrize("team", [1, 8, 32])
+@pytest.mark.parametrize("team", [1, 4, 8, 32])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_one_step_parity(p, case, team, generic):
     """`auto` runs the path the library picks (affine fast paths where they exist); `generic` forces the
     per-node generic kernel on the same case, so both implementations are held to the oracle."""
     name, sampler, pk, pp, d, kw, n_sk = case
+    if team == 4 and not (sampler == 0 and kw.get("grid_size", 10) == 0 and pk in (0, 1, 2, 3) and not generic):
+        pytest.skip("teams of 4 are built for the register-resident Zig-Zag x Brent kernels only")
     if generic and team != 8:
         pytest.skip("generic path is exercised at one team width")
     if team == 1 and d > 100:
@@ -109,6 +112,8 @@ def test_one_step_parity(p, case, team, generic):
     et = (np.abs((h.t[:, 1] - h.t[:, 0]) - dt_o) / dt_o).max()
     eh = (np.abs(h.horizon[:, 1] - r.horizon[0, 1:]) / r.horizon[0, 1:]).max()
     ea = np.abs(h.ar[:, 1] - r.ar[0, 1:]).max()
+    record_parity_error(f"one_step/{name}/team{team}/{'generic' if generic else 'auto'}", x=ex, v=ev, t=et, horizon=eh,
+                        ar=ea, tol=tol)
     assert max(ex, ev, et, eh, ea) < tol, dict(x=ex, v=ev, t=et, horizon=eh, ar=ea)
     assert np.array_equal(np.sign(h.V[:, 1]), np.sign(r.V[0, 1:]))
     assert np.array_equal(h.rejected[:, 1], r.rejected[0, 1:])
@@ -125,6 +130,9 @@ FREE_RUNNING = [
     ("zz_gauss10_unsigned", 0, 0, None, 10, dict(signed_bound=False), 3001),
     ("zz_diag70", 0, 1, "linspace", 70, dict(), 3001),
     ("zz_equicorr33_nonadaptive", 0, 2, [0.5], 33, dict(grid_size=5, adaptive=False, tmax=0.3), 3001),
+    # BASELINE.json config 3 at full size: BPS on the slanted Gaussian d = 100 (reflections + refreshes; the two CPU
+    # restatements stay within 5e-15 of each other over 1200 events, so the dynamics do not amplify rounding)
+    ("C3_bps_equi100_free", 1, 2, [0.9], 100, dict(tmax=1.0, refresh_rate=0.1), 3001),
 ]
 
 
@@ -134,6 +142,8 @@ def test_free_running_parity(p, case, team):
     """north_star: with injected draws, event times / positions / velocities match the Float64 reference path to
     1e-10 relative for the first 10^4 events, velocity signs bit-exact."""
     name, sampler, pk, pp, d, kw, n_sk = case
+    if team == 1 and d > 70:
+        pytest.skip("thread-per-chain is for small d")
     pp = pot_params(pp, d)
     nch = 3
     x0, v0, (E, U, N) = case_inputs(name, sampler, d, n_sk, n_chains=nch)
@@ -145,10 +155,17 @@ def test_free_running_parity(p, case, team):
         h = p.sample_skeleton(s, n_sk, x0, v0, tape=(E, U, N))
     finally:
         set_team(None)
+    worst = 0.0
     for c in range(nch):
-        assert relerr(h.X[c], r.X[c]) < 1e-10 and relerr(h.t[c], r.t[c]) < 1e-10
-        assert relerr(h.horizon[c], r.horizon[c]) < 1e-10 and relerr(h.ar[c], r.ar[c]) < 1e-10
-        assert np.array_equal(h.V[c], r.V[c])  # ZigZag velocities are +-1: bit-exact
+        e = max(relerr(h.X[c], r.X[c]), relerr(h.t[c], r.t[c]), relerr(h.horizon[c], r.horizon[c]), relerr(h.ar[c], r.ar[c]))
+        if sampler == 0:
+            assert np.array_equal(h.V[c], r.V[c])  # ZigZag velocities are +-1: bit-exact
+        else:
+            e = max(e, relerr(h.V[c], r.V[c]))
+            assert np.array_equal(np.sign(h.V[c]), np.sign(r.V[c]))
+        worst = max(worst, e)
+    record_parity_error(f"free_running/{name}/team{team}", max_rel=worst, events=n_sk - 1, tol=1e-10)
+    assert worst < 1e-10, worst
     assert np.array_equal(h.rejected, r.rejected) and np.array_equal(h.hitting_horizon, r.hitting_horizon)
     assert np.array_equal(h.errored_bound, r.errored_bound) and np.array_equal(h.tape_pos, r.tape_used)
     assert np.array_equal(h.counters, r.counters)
