@@ -230,6 +230,26 @@ int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_ch
                               const double* X, const double* V, const double* t, double* m1, double* m2,
                               double* T, int32_t on_device, void* cuda_stream);
 
+/* Cross-chain sufficient statistics of the per-chain time integrals (one fused kernel; SURVEY.md 8d/8e -- the
+ * reference has no ESS estimator): with m_c = m1[c] / T[c] and s_c = m2[c] / T[c] (T == NULL: already time averages),
+ * sums[0][i] = sum_c m_c[i], sums[1][i] = sum_c m_c[i]^2, sums[2][i] = sum_c s_c[i], sums[3][i] = n_chains.
+ * Summation order is fixed (bitwise reproducible).  Pooled mean / variance and the cross-chain ESS follow from the
+ * sums after they have been added over ranks: ESS_i = C Var_pi(x_i) / Var_c(m_c[i]). */
+int pdmpflux_moments_reduce(int dim, int64_t n_chains, const double* m1, const double* m2, const double* T,
+                            double* sums /* [4][dim] */, int32_t on_device, void* cuda_stream);
+
+/* The only collective of the path: sum the moment statistics over the GPUs of a job (NCCL over NVLink).  The library
+ * owns the communicator; the host only moves the 128-byte unique id from rank 0 to the other ranks (MPI / sockets /
+ * torch.distributed -- any transport).  NCCL is bound at run time (libnccl.so.2); without it comm_create with
+ * n_ranks > 1 returns PDMPFLUX_ERR_UNSUPPORTED.  n_ranks == 1 needs no NCCL and allreduce is a no-op. */
+#define PDMPFLUX_COMM_ID_BYTES 128
+typedef struct pdmpflux_comm_s* pdmpflux_comm_t;
+int pdmpflux_comm_unique_id(void* id_out, size_t bytes);           /* rank 0: ncclGetUniqueId */
+int pdmpflux_comm_create(const void* unique_id, int n_ranks, int rank, pdmpflux_comm_t* out); /* after set_device */
+int pdmpflux_comm_destroy(pdmpflux_comm_t comm);
+/* in-place sum over ranks of `n` doubles in device memory, enqueued on cuda_stream */
+int pdmpflux_moments_allreduce(pdmpflux_comm_t comm, double* device_sums, int64_t n, void* cuda_stream);
+
 /* replaces RV_diagnostic(history, U; B) (src/diagnostic.jl:37-75) for a batch of skeletons: rv[c] = sum over B blocks
  * of (U(x(t_b)) - U(x(t_{b-1})))^2 / t[end], positions by the linear interpolation of _history_position_linear!
  * (src/diagnostic.jl:23-35) when flow_kind = 0; flow_kind = 1 interpolates with the Boomerang rotation, which is what

@@ -60,6 +60,10 @@ struct DevBuf {  // RAII device allocation
 
 }  // namespace
 
+// used by the other translation units (reduce.cu)
+int pdmpflux_fail_(int code, const std::string& msg) { return fail(code, msg); }
+void pdmpflux_count_launch_() { g_launches.fetch_add(1); }
+
 struct pdmpflux_potential_s {
     int kind = 0, dim = 0;
     PotParams pp{};
@@ -140,7 +144,10 @@ int pick_team(int d, int64_t n_chains, bool zz_brent_fast) {
     if (d <= 16) return n_chains >= 8192 ? 1 : 8;
     // Zig-Zag x Brent is a serial recurrence of ~40 rate evaluations per bound whose scalar part every lane of the
     // team repeats: 4 lanes per chain (<= 16 coordinates per lane, line model in registers) halve that redundancy.
-    if (zz_brent_fast && d <= 64) return 4;
+    // Measured (B200, banana d = 50): with enough chains to give every scheduler several warps the kernel is
+    // issue bound and teams of 4 win (3.6e8 vs 2.3e8 events/s at 65536 chains); at 4096 chains a team of 4 leaves
+    // one latency-bound warp per scheduler and teams of 8 (two warps per scheduler) win (1.9e8 vs 1.7e8).
+    if (zz_brent_fast && d <= 64 && n_chains >= 16384) return 4;
     if (d <= 256) return 8;
     return 32;
 }

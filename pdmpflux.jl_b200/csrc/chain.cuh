@@ -79,6 +79,7 @@ struct Chain {
     double* sc1;
     double* sc2;
     int tl, d, nown;
+    int nfull;               // owned slots j < nfull belong to a coordinate on every lane; slot nfull only where tl < d - TEAM * nfull
     unsigned mask;
     int64_t chain;
 
@@ -206,6 +207,14 @@ struct Chain {
         else return tl + TEAM * j < d;
     }
     __device__ __forceinline__ int coord(int j) const { return tl + TEAM * j; }
+    // f(j) for every owned slot: an unpredicated main loop over the slots every lane owns, then the ragged last slot
+    // (U = unroll factor of the main loop: 4 for light bodies, 1 for bodies that draw normals)
+    template <int U = 4, class F>
+    __device__ __forceinline__ void for_owned(F&& f) const {
+#pragma unroll U
+        for (int j = 0; j < nfull; ++j) f(j);
+        if (tl < d - TEAM * nfull) f(nfull);
+    }
 
     // functionals of the current x and v (one fused multi-value reduction)
     __device__ void compute_functionals() {
@@ -213,11 +222,10 @@ struct Chain {
             double acc[2 * KK];
 #pragma unroll
             for (int k = 0; k < 2 * KK; ++k) acc[k] = 0.0;
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) {
-                    P::accum(p.pot, coord(j), XS(j), acc);
-                    P::accum(p.pot, coord(j), VS(j), acc + KK);
-                }
+            for_owned([&](int j) {
+                P::accum(p.pot, coord(j), XS(j), acc);
+                P::accum(p.pot, coord(j), VS(j), acc + KK);
+            });
             team_sum_n<TEAM, 2 * KK>(acc, mask);
 #pragma unroll
             for (int k = 0; k < KK; ++k) { Lx[k] = acc[k]; Lv[k] = acc[KK + k]; }
@@ -253,31 +261,29 @@ struct Chain {
     // closed-form int_0^tt x_i(s) ds and int_0^tt x_i(s)^2 ds along the flow from the current (x, v); tt may be
     // negative (time-horizon variant stepping back to T), which subtracts the overshoot
     __device__ void accumulate_segment(double tt, const Flow& f) {
-        for (int j = 0; j < nown; ++j)
-            if (owns(j)) {
-                const double x = XS(j), v = VS(j);
-                if constexpr (kRot) {  // x cos s + v sin s  (f.a = cos tt, f.b = sin tt)
-                    const double s2t = 2.0 * f.b * f.a;
-                    M1S(j) += x * f.b + v * (1.0 - f.a);
-                    M2S(j) += x * x * (0.5 * tt + 0.25 * s2t) + v * v * (0.5 * tt - 0.25 * s2t) + x * v * f.b * f.b;
-                } else {
-                    M1S(j) += tt * (x + 0.5 * v * tt);
-                    M2S(j) += tt * (x * x + tt * (x * v + v * v * tt * (1.0 / 3.0)));
-                }
+        for_owned([&](int j) {
+            const double x = XS(j), v = VS(j);
+            if constexpr (kRot) {  // x cos s + v sin s  (f.a = cos tt, f.b = sin tt)
+                const double s2t = 2.0 * f.b * f.a;
+                M1S(j) += x * f.b + v * (1.0 - f.a);
+                M2S(j) += x * x * (0.5 * tt + 0.25 * s2t) + v * v * (0.5 * tt - 0.25 * s2t) + x * v * f.b * f.b;
+            } else {
+                M1S(j) += tt * (x + 0.5 * v * tt);
+                M2S(j) += tt * (x * x + tt * (x * v + v * v * tt * (1.0 / 3.0)));
             }
+        });
     }
 
     __device__ void flow_inplace(double tt) {
         wait_row_stores();  // x / v are about to change: the TMA engine must have read the previous row
         const Flow f = flow_coef(tt);
         if (p.accumulate_moments) accumulate_segment(tt, f);
-        for (int j = 0; j < nown; ++j)
-            if (owns(j)) {
-                double xt, vt;
-                flow_point(f, XS(j), VS(j), xt, vt);
-                XS(j) = xt;
-                if constexpr (kRot) VS(j) = vt;
-            }
+        for_owned([&](int j) {
+            double xt, vt;
+            flow_point(f, XS(j), VS(j), xt, vt);
+            XS(j) = xt;
+            if constexpr (kRot) VS(j) = vt;
+        });
     }
 
     __device__ __forceinline__ double extra_rate() const {
@@ -309,13 +315,12 @@ struct Chain {
         if constexpr (!kFast) return;
         else if constexpr (kRot) {
             double r3[3] = {0.0, 0.0, 0.0};
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) {
-                    const double xi = XS(j), vi = VS(j);
-                    double g, hv;
-                    P::eval(p.pot, coord(j), xi, vi, Lx, Lv, g, hv);
-                    r3[0] += g * xi; r3[1] += g * vi; r3[2] += hv * vi;
-                }
+            for_owned([&](int j) {
+                const double xi = XS(j), vi = VS(j);
+                double g, hv;
+                P::eval(p.pot, coord(j), xi, vi, Lx, Lv, g, hv);
+                r3[0] += g * xi; r3[1] += g * vi; r3[2] += hv * vi;
+            });
             team_sum_n<TEAM, 3>(r3, mask);
             pxx = r3[0]; pxv = r3[1]; pvv = r3[2];
         } else if constexpr (kZZ) {
@@ -345,13 +350,14 @@ struct Chain {
             }
         } else {  // BPS / FECMC
             double r2[2] = {0.0, 0.0};
-            for (int j = 0; j < nown; ++j)
-                if (owns(j) && coord(j) >= NS) {
+            for_owned([&](int j) {
+                if (NS == 0 || coord(j) >= NS) {
                     const double vi = VS(j);
                     double g, hv;
                     P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
                     r2[0] += g * vi; r2[1] += hv * vi;
                 }
+            });
             team_sum_n<TEAM, 2>(r2, mask);
             la = r2[0]; lb = r2[1];
         }
@@ -949,12 +955,11 @@ struct Chain {
 
     __device__ void jump_bps() {  // BouncyParticleSamplers.jl:50-74
         double r2[2] = {0.0, 0.0};
-        for (int j = 0; j < nown; ++j)
-            if (owns(j)) {
-                const double g = P::grad(p.pot, coord(j), XS(j), Lx);
-                r2[0] += g * VS(j);
-                r2[1] += g * g;
-            }
+        for_owned([&](int j) {
+            const double g = P::grad(p.pot, coord(j), XS(j), Lx);
+            r2[0] += g * VS(j);
+            r2[1] += g * g;
+        });
         team_sum_n<TEAM, 2>(r2, mask);
         const double gv = r2[0], gg = r2[1];
         const double bounce = (gv > 0.0 ? gv : 0.0);
@@ -963,17 +968,15 @@ struct Chain {
         if (u < prob) {
             if (gg == 0) return;
             const double scale = 2 * gv / gg;
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) {
-                    const double g = P::grad(p.pot, coord(j), XS(j), Lx);
-                    VS(j) = VS(j) - scale * g;
-                }
+            for_owned([&](int j) {
+                const double g = P::grad(p.pot, coord(j), XS(j), Lx);
+                VS(j) = VS(j) - scale * g;
+            });
         } else {
             double nn = refresh_velocity_normals();
             if (!p.gaussian_velocity) {
                 nn = 1.0 / sqrt(team_sum<TEAM>(nn, mask));
-                for (int j = 0; j < nown; ++j)
-                    if (owns(j)) VS(j) = VS(j) * nn;
+                for_owned([&](int j) { VS(j) = VS(j) * nn; });
             }
         }
     }
@@ -981,12 +984,11 @@ struct Chain {
     __device__ void jump_boomerang() {  // BoomerangSamplers.jl:49-67
         // QUIRK: the jump uses grad U(x) - x although the rates use grad U (BoomerangSamplers.jl:38-46 vs :51-52)
         double r2[2] = {0.0, 0.0};
-        for (int j = 0; j < nown; ++j)
-            if (owns(j)) {
-                const double g = P::grad(p.pot, coord(j), XS(j), Lx) - XS(j);
-                r2[0] += g * VS(j);
-                r2[1] += g * g;
-            }
+        for_owned([&](int j) {
+            const double g = P::grad(p.pot, coord(j), XS(j), Lx) - XS(j);
+            r2[0] += g * VS(j);
+            r2[1] += g * g;
+        });
         team_sum_n<TEAM, 2>(r2, mask);
         const double gv = r2[0];
         const double bounce = (gv > 0.0 ? gv : 0.0);
@@ -994,28 +996,119 @@ struct Chain {
         const double u = rand_uniform();
         if (u < prob) {
             const double ing = 1.0 / sqrt(r2[1]);
-            double ve = 0.0;
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) {
-                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) * ing;
-                    ve += VS(j) * e;
-                }
-            ve = team_sum<TEAM>(ve, mask);
-            for (int j = 0; j < nown; ++j)
-                if (owns(j)) {
-                    const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) * ing;
-                    VS(j) = VS(j) - 2 * ve * e;
-                }
+            // <v, e> = <v, g> / |g| (r2[0] is already reduced)
+            const double ve = r2[0] * ing;
+            for_owned([&](int j) {
+                const double e = (P::grad(p.pot, coord(j), XS(j), Lx) - XS(j)) * ing;
+                VS(j) = VS(j) - 2 * ve * e;
+            });
         } else {  // QUIRK: refresh draws from the global RNG in the reference (:65); on a tape it is the N stream
             refresh_velocity_normals();
         }
     }
 
-    __device__ void jump_fecmc() {  // ForwardEventChainMonteCarlo.jl:132-218 (+ :60-88, :105-113)
+    // ForwardEventChainMonteCarlo.jl:132-218 (+ :60-88, :105-113), fused.
+    //
+    // The reference builds the new velocity through a chain of d-vectors (n, v_o, g1, g2, e1, e2, v_rot, proposal: seven
+    // passes over three scratch vectors).  Every one of them lies in span{v, n, z1, z2} (z1, z2 the two rows of the
+    // randn(2, d) draw), so the result is  v' = c_v v + c_1 z1 + c_2 z2 + c_n n  with coefficients that depend only on
+    // eight inner products.  Here: one pass for |g|^2, <v, g>, |v|^2; one pass that draws z1, z2 and accumulates the
+    // eight products; scalar Gram-Schmidt algebra; one pass that writes v'.  z1, z2 are the only vectors kept between
+    // passes (two scratch vectors, written once and read once).  Differences from the literal sequence are
+    // reassociation only (~1e-15 relative; parity is held at 1e-10).  The degenerate case |v_o| ~ 0 (a redraw of v_o,
+    // probability ~0) takes the literal multi-pass path below.
+    __device__ void jump_fecmc() {
         const double sf = p.speed_factor;
         const double u = rand_uniform();
         double rho = -sqrt(1 - pow(u, 2.0 / (d - 1)));
         if (sf != 1.0) rho = sf * rho;
+        double r3[3] = {0.0, 0.0, 0.0};
+        for_owned([&](int j) {
+            const double g = P::grad(p.pot, coord(j), XS(j), Lx), vj = VS(j);
+            r3[0] += g * g; r3[1] += vj * g; r3[2] += vj * vj;
+        });
+        team_sum_n<TEAM, 3>(r3, mask);
+        const double ng = sqrt(r3[0]);
+        const double inv_ng = ng == 0 ? 0.0 : 1.0 / ng;   // n = g / |g| (zero vector if the norm is 0)
+        const double vn = r3[1] * inv_ng;                  // <v, n>
+        const double nn = ng == 0 ? 0.0 : 1.0;             // <n, n>
+        double nvo = r3[2] - vn * vn * nn;                 // |v - <v,n> n|^2
+        if (!(nvo > 1e-3 * r3[2])) {                       // cancellation (or the degenerate redraw): literal path
+            jump_fecmc_literal(rho);
+            return;
+        }
+        const double u2 = rand_uniform();
+        const double rad = (sf != 1.0) ? sqrt(sf * sf - rho * rho) : sqrt(1 - rho * rho);
+        if (u2 >= p.mix_p) {  // keep the direction of v_o: v' = v_o / |v_o| sqrt(1 - rho^2) + rho n
+            const double sc_ = rad / sqrt(nvo);
+            const double cn = (rho - sc_ * vn) * inv_ng;
+            for_owned([&](int j) { VS(j) = fma(sc_, VS(j), cn * P::grad(p.pot, coord(j), XS(j), Lx)); });
+            return;
+        }
+        double* __restrict__ z1s = sc0;
+        double* __restrict__ z2s = sc1;
+        if (p.switch_) {  // _orthogonal_switch; randn(key, 2, dim) is column-major: g1[i] = N[2i], g2[i] = N[2i+1]
+            normals_reserve(2 * (int64_t)d);
+            double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for_owned<1>([&](int j) {
+                double z1, z2;
+                rand_normal_two_at(coord(j), z1, z2);
+                z1s[j * kStr] = z1; z2s[j * kStr] = z2;
+                const double n = P::grad(p.pot, coord(j), XS(j), Lx) * inv_ng;
+                const double vo = fma(-vn, n, VS(j));
+                a[0] += z1 * n; a[1] += z2 * n; a[2] += z1 * z1; a[3] += z2 * z2; a[4] += z1 * z2;
+                a[5] += vo * z1; a[6] += vo * z2; a[7] += vo * vo;
+            });
+            normals_advance(2 * (int64_t)d);
+            team_sum_n<TEAM, 8>(a, mask);
+            nvo = a[7];
+            // Gram-Schmidt on (g1, g2) = (z1 - a0 n, z2 - a1 n):  e1 = g1 / N1,  e2 = (g2 - b e1) / N2
+            const double N1 = sqrt(a[2] - a[0] * a[0] * nn);
+            const double b = (a[4] - a[0] * a[1] * nn) / N1;
+            const double N2 = sqrt(a[3] - a[1] * a[1] * nn - b * b);
+            const double c1 = a[5] / N1;               // <v_o, e1>   (<v_o, n> = 0)
+            const double c2 = (a[6] - b * c1) / N2;    // <v_o, e2>
+            double p1 = c2, p2 = c1;                   // swap of the (e1, e2) components
+            if (p.ran_p) {
+                const double th = rand_uniform() * 2 * 3.14159265358979323846;
+                double st, ct;
+                sincos(th, &st, &ct);
+                p1 = ct * c1 + st * c2; p2 = st * c1 - ct * c2;
+            }
+            // proposal = v_o + q1 e1 + q2 e2
+            const double q1 = p1 - c1, q2 = p2 - c2;
+            const double vop = nvo + q1 * c1 + q2 * c2;                              // <v_o, proposal>
+            const double pp2 = nvo + 2.0 * (q1 * c1 + q2 * c2) + q1 * q1 + q2 * q2;  // |proposal|^2
+            double sgn = 1.0;
+            if (p.positive) sgn = (vop > 0) ? 1.0 : ((vop < 0) ? -1.0 : vop);        // sign(0) = 0, sign(NaN) = NaN
+            const double sc_ = sgn * rad / sqrt(pp2 * (sgn * sgn));                  // sign(0) = 0 -> NaN as in the reference
+            const double gam = q2 / N2, bet = (q1 - gam * b) / N1;
+            const double cz1 = sc_ * bet, cz2 = sc_ * gam;
+            const double cn = (rho - sc_ * (bet * a[0] + gam * a[1]) - sc_ * vn) * inv_ng;
+            for_owned([&](int j) {
+                const double g = P::grad(p.pot, coord(j), XS(j), Lx);
+                VS(j) = fma(sc_, VS(j), fma(cz1, z1s[j * kStr], fma(cz2, z2s[j * kStr], cn * g)));
+            });
+        } else {  // _full_refresh: w = z / |z|, proposal = w - <w, n> n, v' = proposal rad / |proposal| + rho n
+            normals_reserve(d);
+            double a[2] = {0.0, 0.0};
+            for_owned<1>([&](int j) {
+                const double z = rand_normal_at(coord(j));
+                z1s[j * kStr] = z;
+                a[0] += z * (P::grad(p.pot, coord(j), XS(j), Lx) * inv_ng);
+                a[1] += z * z;
+            });
+            normals_advance(d);
+            team_sum_n<TEAM, 2>(a, mask);
+            const double k = rad / sqrt(a[1] - a[0] * a[0] * nn);
+            const double cn = (rho - k * a[0]) * inv_ng;
+            for_owned([&](int j) { VS(j) = fma(k, z1s[j * kStr], cn * P::grad(p.pot, coord(j), XS(j), Lx)); });
+        }
+    }
+
+    // the reference's sequence of vector operations, pass by pass (used for the degenerate / ill-conditioned case)
+    __device__ void jump_fecmc_literal(double rho) {
+        const double sf = p.speed_factor;
         double* __restrict__ vo = sc0;
         // n = grad U(x) / |grad U(x)| (zero vector if the norm is 0)
         double r2[2] = {0.0, 0.0};
@@ -1547,8 +1640,11 @@ struct Chain {
 
 // One launch advances every chain by p.n_events accepted events (or just records the current state when
 // n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
+#ifndef PDMPFLUX_MINBLOCKS_GRID
+#define PDMPFLUX_MINBLOCKS_GRID 4
+#endif
 template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
-__global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PATH == kPathFastBrent ? 2 : 4)) skeleton_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PATH == kPathFastBrent ? 2 : (TEAM == 32 ? 3 : PDMPFLUX_MINBLOCKS_GRID))) skeleton_kernel(const __grid_constant__ KernelParams p) {
     constexpr int CPB = kBlockThreads / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
     const int64_t c_raw = (int64_t)blockIdx.x * CPB + c_local;
@@ -1560,6 +1656,7 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
     ch.mask = team_mask<TEAM>();
     ch.d = p.d;
     ch.nown = p.n_own;
+    ch.nfull = p.d / TEAM;
     ch.chain = c;
     // shared-memory state vectors: [x | v | (A | B) | (scratch x3) | (row carry)]
     const int vec = p.vec_elems;
@@ -1605,11 +1702,10 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
         }
     }
     // load PDMPState
-    for (int j = 0; j < ch.nown; ++j)
-        if (ch.owns(j)) {
-            g_smem[ch.off_x + j * ch.kStr] = p.sx[c * p.d + ch.coord(j)];
-            g_smem[ch.off_v + j * ch.kStr] = p.sv[c * p.d + ch.coord(j)];
-        }
+    ch.for_owned([&](int j) {
+        g_smem[ch.off_x + j * ch.kStr] = p.sx[c * p.d + ch.coord(j)];
+        g_smem[ch.off_v + j * ch.kStr] = p.sv[c * p.d + ch.coord(j)];
+    });
     ch.t = p.st[c];
     ch.horizon = p.shorizon[c];
     ch.ar = p.sar[c];

@@ -91,3 +91,38 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle_c" not in src and "pdmp_oracle" not in src and "libpdmp_oracle" not in src, f
+
+
+def test_reduction_entry_points_without_gpu(p):
+    """pdmpflux_moments_reduce / pdmpflux_comm_* / pdmpflux_moments_allreduce (kernel K5): argument
+    validation, the single-rank communicator (needs neither NCCL nor a GPU) and the no-fallback rule."""
+    from pdmpflux_b200 import _lib
+    lib = p.lib()
+    h = C.c_void_p()
+    with pytest.raises(p.ArgumentError):
+        _lib.check(lib.pdmpflux_comm_create(None, 0, 0, C.byref(h)))
+    with pytest.raises(p.ArgumentError):
+        _lib.check(lib.pdmpflux_comm_create(None, 2, 2, C.byref(h)))
+    with pytest.raises(p.ArgumentError):
+        _lib.check(lib.pdmpflux_comm_create(None, 2, 0, C.byref(h)))       # more than one rank needs the unique id
+    _lib.check(lib.pdmpflux_comm_create(None, 1, 0, C.byref(h)))            # one rank: no NCCL involved
+    buf = np.arange(8, dtype=np.float64)
+    _lib.check(lib.pdmpflux_moments_allreduce(h, buf.ctypes.data, 8, None))  # no-op on a single rank
+    assert np.array_equal(buf, np.arange(8.0))
+    with pytest.raises(p.ArgumentError):
+        _lib.check(lib.pdmpflux_moments_allreduce(h, None, 8, None))
+    _lib.check(lib.pdmpflux_comm_destroy(h))
+    with pytest.raises(p.ArgumentError):
+        _lib.check(lib.pdmpflux_comm_unique_id(None, 128))
+    m = np.ones((4, 3)); out = np.zeros((4, 3))
+    with pytest.raises(p.ArgumentError):
+        _lib.check(lib.pdmpflux_moments_reduce(0, 4, m.ctypes.data, m.ctypes.data, None, out.ctypes.data, 0, None))
+    n = C.c_int(-1)
+    lib.pdmpflux_device_count(C.byref(n))
+    if n.value <= 0:
+        with pytest.raises(p.CudaError, match="no CPU fallback|CUDA"):
+            _lib.check(lib.pdmpflux_moments_reduce(3, 4, m.ctypes.data, m.ctypes.data, None, out.ctypes.data, 0, None))
+    # the python wrapper builds a single-rank communicator when torch.distributed is not initialised
+    c = p.dist.Comm()
+    assert (c.rank, c.world) == (0, 1)
+    c.close()
