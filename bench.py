@@ -4,13 +4,20 @@
 Workload (BASELINE.json configs[1], "C2"): ZigZag, banana potential d=50 with the manual gradient,
 grid_size=0 (constant bound via Brent), 4096 chains per GPU, Philox draws, full PDMPHistory columns stored.
 One "step" = every chain advanced by --events accepted events (one launch of the skeleton kernel), followed
-by the closed-form moment kernel and (N > 1) one NCCL all-reduce of the moment sums.
+by the closed-form moment kernel, pdmpflux_moments_reduce and (N > 1) pdmpflux_moments_allreduce (NCCL, in the library).
 
   value  events/s, whole job, state and outputs resident in HBM (CUDA events, max over ranks)
   e2e    events/s through pdmpflux_sample_skeleton with HOST (pinned) buffers: H2D of the initial states and
-         D2H of the full history inside the timed region
-  roofline  algorithmic bytes (16 d + 76 per event: X, V, t, horizon, ar, error_value_ar, 3 int32 counters)
-         / skeleton-kernel time vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+         D2H of the full history inside the timed region (median, mean and max of individually timed calls)
+  e2e_moments_only  the same metric end to end with fused in-kernel moments and no stored skeleton (only the
+         initial states and 4 x d moment sums cross PCIe)
+  roofline  the governing roofline north_star names: algorithmic bytes (16 d + 76 per event: X, V, t, horizon, ar,
+         error_value_ar, 3 int32 counters) / skeleton-kernel time vs the measured HBM copy bandwidth
+         (MEASURED_PEAKS.json); for --config c4 algorithmic FP64 flops vs the DMMA peak measured in this run
+         (tools/fp64_peaks.cu, reported under roofline_fp64).  roofline.issue: fraction of the instruction-issue ceiling
+         (what actually bounds the HBM-named kernels), from the ncu instruction count of this build (profiles/traffic.json,
+         refused when its source stamp does not match the sources)
+  strong_scaling  BASELINE config 5 (FECMC / Boomerang d = 1000): 65536 chains in total sharded over the N ranks
   cpu_baseline  the C restatement of the reference (oracle/, OpenMP, one chain per thread) on the host cores
 `--impl reference` times that CPU restatement alone (Julia, hence the reference itself, is not installed).
 """
@@ -72,7 +79,47 @@ def make_sampler(p, name):
     raise SystemExit(f"unknown config {name}")
 
 
-FP64_PEAK_TFLOPS = 37.0  # measured FP64 tensor (DMMA) throughput, scratch/dmma_peak.cu; plain DFMA measures 33.4 (scratch/fp64_peak.cu)
+FP64_PEAK_FALLBACK = 37.0  # TFLOP/s DMMA, earlier measurement on this pool (profiles/r2_fp64_peaks.json); used only when
+                           # tools/fp64_peaks cannot run
+
+
+def source_stamp():
+    """sha256 over the kernel sources: ncu-derived numbers in profiles/traffic.json are only quoted for the build they
+    were measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "pdmpflux.jl_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_profile(name):
+    """(dram traffic per launch, warp instructions per event) from the committed ncu capture of THIS build, else Nones."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        return None, None, "profiles/traffic.json missing"
+    if t.get("_source_stamp") != source_stamp():
+        return None, None, "profiles/traffic.json was measured on another build (stamp %s != %s): not quoted" % (
+            t.get("_source_stamp"), source_stamp())
+    e = t.get(name) or {}
+    return e.get("dram_bytes_per_launch"), e.get("warp_inst_per_event"), "ncu --set full capture of this build (profiles/)"
+
+
+def fp64_peaks():
+    """FP64 tensor (DMMA) and vector (DFMA) throughput of this GPU, measured now by tools/fp64_peaks (a few 10 ms)."""
+    exe = os.path.join(ROOT, "tools", "fp64_peaks")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        r = json.loads(out)
+        if "dmma_tflops" in r:
+            r["source"] = "measured in this run (tools/fp64_peaks.cu)"
+            return r
+    except (OSError, ValueError, IndexError, subprocess.SubprocessError):
+        pass
+    return {"dmma_tflops": FP64_PEAK_FALLBACK, "dfma_tflops": 33.4, "source": "fallback: earlier measurement on this pool"}
 
 
 def pin_to_gpu_numa_node(index):
@@ -203,6 +250,68 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def alloc_history(torch, dev, nch, n_ev, d):
+    f64 = torch.float64
+    return dict(X=torch.empty((nch, n_ev, d), dtype=f64, device=dev), V=torch.empty((nch, n_ev, d), dtype=f64, device=dev),
+                t=torch.empty((nch, n_ev), dtype=f64, device=dev), horizon=torch.empty((nch, n_ev), dtype=f64, device=dev),
+                ar=torch.empty((nch, n_ev), dtype=f64, device=dev),
+                error_value_ar=torch.empty((nch, n_ev, 5), dtype=f64, device=dev),
+                errored_bound=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
+                rejected=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
+                hitting_horizon=torch.empty((nch, n_ev), dtype=torch.int32, device=dev))
+
+
+def init_states(torch, dev, name, nch):
+    cfgd = CONFIGS[name]; d = cfgd["d"]
+    x0 = torch.full((nch, d), cfgd["x0"], dtype=torch.float64, device=dev)
+    v0 = torch.ones((nch, d), dtype=torch.float64, device=dev) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+    return x0, v0
+
+
+C4_ROWS, C4_GRID = 100000, 10
+
+
+def c4_flops(d, builds, rates, n_chain_launches):
+    """FP64 work of the logistic-regression kernel.  algorithmic: 2nd(2 + 2G) per bound build (z = Xx, w = Xv and the
+    d x 2G product), 2nd(2 + 1) per rate evaluation.  executed: the same minus the z / w products the (z, w) cache
+    skips (a chain recomputes them on its first request of a launch and on every 64th request)."""
+    nd2 = 2.0 * C4_ROWS * d
+    alg = nd2 * ((2 + 2 * C4_GRID) * builds + 3 * rates)
+    zw_done = n_chain_launches + (builds + rates) / 64.0
+    exe = nd2 * (2 * C4_GRID * builds + rates) + 2 * nd2 * zw_done
+    return alg, exe
+
+
+def roofline_block(name, nch, n_ev, kern_s, builds, rates, n_chain_launches, hbm_peak, peak_src, fp64, clock_mhz):
+    """The governing roofline north_star names for the workload (HBM skeleton writes; FP64 DMMA for C4), from the
+    kernel's CUDA-event time in THIS run, plus what actually limits it (instruction issue) where that is not the roofline."""
+    d = CONFIGS[name]["d"]
+    traffic, inst_per_event, prof_note = measured_profile(name)
+    events = nch * n_ev
+    if name == "c4":
+        alg, exe = c4_flops(d, builds, rates, n_chain_launches)
+        peak = float(fp64["dmma_tflops"])
+        return {"bound": "fp64", "achieved": alg / kern_s / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": alg / kern_s / 1e12 / peak,
+                "executed": exe / kern_s / 1e12, "executed_frac": exe / kern_s / 1e12 / peak, "traffic": traffic,
+                "kernel": "logreg_zigzag_kernel", "kernel_ms": kern_s * 1e3, "flop_per_event": alg / events,
+                "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64), " + fp64["source"], "dfma_peak_tflops": fp64.get("dfma_tflops"),
+                "note": "achieved counts the algorithmic flops (incl. the z/w products the (z, w) cache skips); executed "
+                        "counts the DMMA work actually issued", "profile": prof_note}
+    achieved = events * bytes_per_event(d) / kern_s / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+         "kernel": "skeleton_kernel", "kernel_ms": kern_s * 1e3, "bytes_per_event": bytes_per_event(d), "peak_source": peak_src,
+         "profile": prof_note}
+    if inst_per_event and clock_mhz:
+        # every instruction of these kernels (FP64 arithmetic, selects, moves) issues at one per two cycles per scheduler
+        # (tools/lat_probe.cu): the issue ceiling is 4 schedulers x 148 SMs x clock / 2 warp instructions per second
+        ceiling = 4 * 148 * clock_mhz * 1e6 / 2.0
+        r["issue"] = {"warp_inst_per_event": inst_per_event, "warp_inst_per_s": inst_per_event * events / kern_s,
+                      "ceiling_warp_inst_per_s": ceiling, "frac": inst_per_event * events / kern_s / ceiling,
+                      "note": "the kernel is bound by FP64 / ALU instruction issue, not by HBM: fraction of the measured "
+                              "issue ceiling (one warp instruction per 2 cycles per scheduler)"}
+    return r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +343,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    comm = p.dist.Comm(dev)          # the library's own NCCL communicator (unique id carried by torch.distributed)
 
     name = args.config
     cfgd = CONFIGS[name]
@@ -242,20 +352,14 @@ def main():
     n_ev = args.events or DEFAULT_EVENTS[name]
     sampler = make_sampler(p, name)
     f64 = torch.float64
-    x0 = torch.full((nch, d), cfgd["x0"], dtype=f64, device=dev)
-    v0 = torch.ones((nch, d), dtype=f64, device=dev) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+    x0, v0 = init_states(torch, dev, name, nch)
     chain_offset, _ = p.dist.shard(nch * world, rank, world)      # weak scaling: nch chains on every rank
     chains = p.DeviceChains(sampler, x0, v0, seed=2024, chain_offset=chain_offset)
-    bufs = dict(X=torch.empty((nch, n_ev, d), dtype=f64, device=dev), V=torch.empty((nch, n_ev, d), dtype=f64, device=dev),
-                t=torch.empty((nch, n_ev), dtype=f64, device=dev), horizon=torch.empty((nch, n_ev), dtype=f64, device=dev),
-                ar=torch.empty((nch, n_ev), dtype=f64, device=dev),
-                error_value_ar=torch.empty((nch, n_ev, 5), dtype=f64, device=dev),
-                errored_bound=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
-                rejected=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
-                hitting_horizon=torch.empty((nch, n_ev), dtype=torch.int32, device=dev))
+    bufs = alloc_history(torch, dev, nch, n_ev, d)
     view = p.device_history_view(n_ev, **bufs)
     m1 = torch.empty((nch, d), dtype=f64, device=dev); m2 = torch.empty((nch, d), dtype=f64, device=dev)
     Tl = torch.empty((nch,), dtype=f64, device=dev)
+    sums = torch.empty((4, d), dtype=f64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     lib = p.lib()
     from pdmpflux_b200 import _lib as L
@@ -270,8 +374,8 @@ def main():
         L.check(lib.pdmpflux_skeleton_moments(sampler.flow_kind, d, n_ev, nch, 0, bufs["X"].data_ptr(),
                                               bufs["V"].data_ptr(), bufs["t"].data_ptr(), m1.data_ptr(), m2.data_ptr(),
                                               Tl.data_ptr(), 1, stream))
-        sums = p.dist.moment_sums(m1 / Tl[:, None], m2 / Tl[:, None])   # 4 x d sufficient statistics
-        p.dist.all_reduce_sums(sums)                                # the only collective: final moment reduction
+        p.dist.moment_sums_device(m1, m2, Tl, sums, stream)         # pdmpflux_moments_reduce: 4 x d sufficient statistics
+        comm.all_reduce(sums, stream)                               # pdmpflux_moments_allreduce: the only collective
         if timed:
             kern_ms.append((k0, k1))
         return sums
@@ -279,6 +383,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(False)
     torch.cuda.synchronize()
+    _, _, cnt0 = chains.status()
     if world > 1:
         dist.barrier()
     launches0 = lib.pdmpflux_launch_count()
@@ -289,7 +394,7 @@ def main():
     w0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        sums = step(True)
+        step(True)
     e1.record()
     torch.cuda.synchronize()
     w1 = time.time()
@@ -307,7 +412,9 @@ def main():
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern, op=dist.ReduceOp.MAX)
     elapsed = float(elapsed); kern = float(kern)
-    chains.status()  # raises if any chain stopped
+    _, _, cnt1 = chains.status()  # raises if any chain stopped
+    builds = float((cnt1[:, 0] - cnt0[:, 0]).sum()) / args.steps
+    rates = float((cnt1[:, 1] - cnt0[:, 1]).sum()) / args.steps
     total_chains = nch * world
     events_per_step = total_chains * n_ev
     value = events_per_step * args.steps / elapsed
@@ -321,57 +428,66 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = nch * n_ev * bytes_per_event(d) / kern / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
-    except (OSError, ValueError):
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "skeleton_kernel", "kernel_ms": kern * 1e3,
-                "bytes_per_event": bytes_per_event(d),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s"}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s"
+    chains.close()
+    del bufs, view
+    torch.cuda.empty_cache()
+    fp64 = fp64_peaks() if (rank == 0) else {"dmma_tflops": FP64_PEAK_FALLBACK, "source": "fallback"}
+    roofline = roofline_block(name, nch, n_ev, kern, builds, rates, nch, hbm_peak, peak_src, fp64, clk.get("sm_mhz"))
 
     line = {"metric": "skeleton events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name}: {cfgd['desc']}", "chains_per_gpu": nch, "events_per_chain_per_step": n_ev,
                        "draws": "philox4x32-10 keyed (seed=2024, chain, event)", "stored": "full PDMPHistory row",
-                       "l2": "outputs per step (%.2f GB) exceed the 126 MB L2" % (nch * n_ev * bytes_per_event(d) / 1e9)},
+                       "l2": ("outputs per step (%.2f GB) exceed the 126 MB L2" % (nch * n_ev * bytes_per_event(d) / 1e9)) if name != "c4"
+                             else "the (z, w) cache streamed per step (1.6 MB per chain, 6.6 GB) exceeds the 126 MB L2; X (80 MB) is meant to stay in it",
+                       "parity": "unpinned against Julia (no Julia in the image): parity is against the CPU restatement in oracle/"},
             "ess_per_s": ess_per_s, "ess_definition": "min over coordinates of C * Var_pi(x_i) / Var_c(chain time-average of x_i), per step window",
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "host_cpus": numa_cpus,
-            "per_rank_kernel_ms": per_rank_kernel_ms}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "roofline_fp64": fp64, "host_cpus": numa_cpus,
+            "per_rank_kernel_ms": per_rank_kernel_ms, "source_stamp": source_stamp()}
 
-    chains.close()
-    del bufs, view
-    torch.cuda.empty_cache()
+    # strong scaling (BASELINE.json config 5): 65536 chains in total, sharded over the ranks of this job
+    line["strong_scaling"] = strong_scaling(p, torch, dist, rank, world, dev)
+
     if not args.no_e2e:
         # every rank runs its shard through the host-buffer call at the same time (they share the host's memory
         # system and CPUs); the slowest rank's time counts
         if world > 1:
             # CPUs this rank may use for rebuilding the V rows: an equal share of the CPUs local to its GPU
-            local = sorted(os.sched_getaffinity(0))
+            local_cpus = sorted(os.sched_getaffinity(0))
             sharing = [None] * world
-            dist.all_gather_object(sharing, local)
-            peers = sum(1 for other in sharing if other == local)
-            os.environ["PDMPFLUX_HOST_THREADS"] = str(max(1, min(16, len(local) // max(peers, 1))))
+            dist.all_gather_object(sharing, local_cpus)
+            peers = sum(1 for other in sharing if other == local_cpus)
+            os.environ["PDMPFLUX_HOST_THREADS"] = str(max(1, min(16, len(local_cpus) // max(peers, 1))))
             # (one rank alone needs >= 12 threads to beat the plain copy of the V rows -- the library's own default -- but
             # with several ranks the host's ingest bandwidth saturates (plain copy: 75 ms per step at 1 rank, 97 at 2,
             # 211 at 4), so moving half the bytes wins even with few threads per rank)
             os.environ["PDMPFLUX_VBITS"] = "1"
             dist.barrier()
         res = e2e(p, sampler, name, nch, n_ev, world, dev)
+        mom = e2e_moments(p, sampler, name, nch, n_ev, dev)
         if world > 1:
-            worst = torch.tensor([res["ms_per_step"]], dtype=f64, device=dev)
+            worst = torch.tensor([res["ms_per_step"], mom["ms_per_step"] or 0.0], dtype=f64, device=dev)
             dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-            res["ms_per_step"] = float(worst)
-            res["value"] = world * nch * n_ev / (float(worst) * 1e-3)
-            res["h2d_bytes_per_step"] *= world; res["d2h_bytes_per_step"] *= world; res["history_bytes_per_step"] *= world
-            res["timing"] += "; all %d ranks concurrently, max over ranks" % world
+            res["ms_per_step"] = float(worst[0])
+            res["value"] = world * nch * n_ev / (float(worst[0]) * 1e-3)
+            if mom["value"] is not None:
+                mom["ms_per_step"] = float(worst[1])
+                mom["value"] = world * nch * n_ev / (float(worst[1]) * 1e-3)
+            for r_ in (res, mom):
+                r_["h2d_bytes_per_step"] *= world; r_["d2h_bytes_per_step"] *= world
+                r_["timing"] += "; all %d ranks concurrently, max over ranks" % world
+            res["history_bytes_per_step"] *= world
+        gbs = res["d2h_bytes_per_step"] / (res["ms_per_step"] * 1e-3) / 1e9
+        res["d2h_gbs"] = gbs
+        res["limiter"] = ("host ingest of the full history: %.1f GB/s device-to-host into one host's DRAM (all ranks together)" % gbs
+                          if gbs > 15.0 else "the kernel (the history is small next to the compute)")
         line["e2e"] = res
+        line["e2e_moments_only"] = mom
     if rank == 0 and world == 1 and not args.no_extra:
-        line["extra_workloads"] = extra_workloads(p, name, peak)
+        line["extra_workloads"] = extra_workloads(p, name, hbm_peak, peak_src, fp64, clk.get("sm_mhz"))
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -379,57 +495,89 @@ def main():
         line["cpu_baseline"] = cpu_baseline(name)[0]
     if rank == 0:
         print(json.dumps(line))
+    comm.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def extra_workloads(p, main, peak):
+def timed_launches(p, torch, name, nch, n_ev, dev, chain_offset=0, reps=3):
+    """Kernel time (CUDA events, best of `reps` after a warm-up launch) of one advance() of n_ev events per chain with the
+    full history stored; returns (seconds, builds, rates) with the counters of one launch."""
+    d = CONFIGS[name]["d"]
+    s = make_sampler(p, name)
+    x0, v0 = init_states(torch, dev, name, nch)
+    ch = p.DeviceChains(s, x0, v0, seed=2024, chain_offset=chain_offset)
+    bufs = alloc_history(torch, dev, nch, n_ev, d)
+    view = p.device_history_view(n_ev, **bufs)
+    st = torch.cuda.current_stream().cuda_stream
+    ch.advance(n_ev, view, 0, st)
+    torch.cuda.synchronize()
+    _, _, c0 = ch.status()
+    best = float("inf")
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); ch.advance(n_ev, view, 0, st); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    _, _, c1 = ch.status(); ch.close()
+    del bufs, view, ch
+    torch.cuda.empty_cache()
+    return best, float((c1[:, 0] - c0[:, 0]).sum()) / reps, float((c1[:, 1] - c0[:, 1]).sum()) / reps
+
+
+def strong_scaling(p, torch, dist, rank, world, dev):
+    """BASELINE.json config 5: ForwardECMC / Boomerang, Gaussian d = 1000, 65536 chains IN TOTAL sharded over the ranks
+    (fixed total work: strong scaling).  Device-timed kernel, slowest rank counts; the driver's N = 1, 2, 4, 8 runs give
+    the curve."""
+    out = {"scaling": "strong", "chains_total": 65536, "events_per_chain": 20}
+    for name in ("c5f", "c5b"):
+        off, cnt = p.dist.shard(65536, rank, world)
+        sec, _, _ = timed_launches(p, torch, name, cnt, 20, dev, chain_offset=off, reps=2)
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        per_rank = [sec * 1e3]
+        if world > 1:
+            g = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            per_rank = [float(x) * 1e3 for x in g]
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t)
+        out[name] = {"workload": CONFIGS[name]["desc"], "events_per_s": 65536 * 20 / sec, "ms": sec * 1e3,
+                     "per_rank_kernel_ms": per_rank, "chains_per_rank": cnt,
+                     "hbm_gbs_per_gpu": cnt * 20 * bytes_per_event(1000) / sec / 1e9}
+    return out
+
+
+def extra_workloads(p, main, hbm_peak, peak_src, fp64, clock_mhz):
     """Short device-resident runs (kernel time by CUDA events, best of 3 after a warm-up launch) of the other
-    BASELINE.json configurations and of the headline config at 65536 chains; same byte accounting."""
+    BASELINE.json configurations and of the headline config at 65536 chains; same roofline accounting as the main line."""
     import torch
     out = {}
     todo = [(n, DEFAULT_CHAINS[n], DEFAULT_EVENTS[n]) for n in ("c1", "c2", "c3", "c4", "c5f", "c5b") if n != main]
-    todo.append((main, 65536, 100))
+    todo.append((main, 65536, 100 if main != "c4" else 2))
     dev = torch.device("cuda")
-    f64 = torch.float64
     for name, nch, n_ev in todo:
-        cfgd = CONFIGS[name]; d = cfgd["d"]
-        s = make_sampler(p, name)
-        x0 = torch.full((nch, d), cfgd["x0"], dtype=f64, device=dev)
-        v0 = torch.ones((nch, d), dtype=f64, device=dev) / (d ** 0.5 if cfgd["unit_v"] else 1.0)
-        ch = p.DeviceChains(s, x0, v0, seed=2024)
-        bufs = dict(X=torch.empty((nch, n_ev, d), dtype=f64, device=dev), V=torch.empty((nch, n_ev, d), dtype=f64, device=dev),
-                    t=torch.empty((nch, n_ev), dtype=f64, device=dev), horizon=torch.empty((nch, n_ev), dtype=f64, device=dev),
-                    ar=torch.empty((nch, n_ev), dtype=f64, device=dev),
-                    error_value_ar=torch.empty((nch, n_ev, 5), dtype=f64, device=dev),
-                    errored_bound=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
-                    rejected=torch.empty((nch, n_ev), dtype=torch.int32, device=dev),
-                    hitting_horizon=torch.empty((nch, n_ev), dtype=torch.int32, device=dev))
-        view = p.device_history_view(n_ev, **bufs)
-        st = torch.cuda.current_stream().cuda_stream
-        ch.advance(n_ev, view, 0, st)
-        best = float("inf")
-        for _ in range(3):
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(); ch.advance(n_ev, view, 0, st); b.record(); torch.cuda.synchronize()
-            best = min(best, a.elapsed_time(b) * 1e-3)
-        _, _, cnt = ch.status(); ch.close()
-        gbs = nch * n_ev * bytes_per_event(d) / best / 1e9
-        out[f"{name}@{nch}"] = {"workload": cfgd["desc"], "chains": nch, "events_per_chain": n_ev,
-                                "events_per_s": nch * n_ev / best, "hbm_gbs": gbs, "hbm_frac": gbs / peak,
-                                "bytes_per_event": bytes_per_event(d), "ms": best * 1e3}
-        if name == "c4":
-            # governing roofline is FP64 (north_star: DMMA): 2nd(2+2G) flop per bound build (z, w and the d x 2G product),
-            # 2nd(2+1) per rate evaluation; counts come from the kernel's own counters (4 launches of n_ev events)
-            n_rows, G = 100000, 10
-            builds, rates = cnt[:, 0].sum() / 4.0, cnt[:, 1].sum() / 4.0
-            flop = 2.0 * n_rows * d * ((2 + 2 * G) * builds + 3 * rates)
-            out[f"{name}@{nch}"].update({"fp64_tflops": flop / best / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
-                                         "fp64_frac": flop / best / 1e12 / FP64_PEAK_TFLOPS,
-                                         "fp64_peak_source": "scratch/dmma_peak.cu DMMA microbenchmark on this pool's B200 (MEASURED_PEAKS.json has no FP64 entry)"})
-        del bufs, view, ch
-        torch.cuda.empty_cache()
+        if name == "c4" and nch > 8192:
+            continue
+        best, builds, rates = timed_launches(p, torch, name, nch, n_ev, dev)
+        rl = roofline_block(name, nch, n_ev, best, builds, rates, nch, hbm_peak, peak_src, fp64, clock_mhz)
+        e = {"workload": CONFIGS[name]["desc"], "chains": nch, "events_per_chain": n_ev, "events_per_s": nch * n_ev / best,
+             "ms": best * 1e3, "roofline": rl}
+        if rl["bound"] == "hbm":
+            e.update({"hbm_gbs": rl["achieved"], "hbm_frac": rl["frac"], "bytes_per_event": rl["bytes_per_event"]})
+        else:
+            e.update({"fp64_tflops": rl["achieved"], "fp64_frac": rl["frac"], "fp64_executed_frac": rl["executed_frac"],
+                      "fp64_peak_tflops": rl["peak"]})
+        out[f"{name}@{nch}"] = e
     return out
+
+
+def _pinned(lib, L, shape, dtype):
+    import ctypes as C
+    import numpy as np
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    L.check(lib.pdmpflux_host_alloc(C.byref(ptr), n))
+    buf = (C.c_char * n).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
 
 
 def e2e(p, sampler, name, nch, n_ev, world, dev):
@@ -443,21 +591,13 @@ def e2e(p, sampler, name, nch, n_ev, world, dev):
     cfgd = CONFIGS[name]
     d = cfgd["d"]
     n_sk = n_ev + 1
-
-    def pinned(shape, dtype):
-        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        ptr = C.c_void_p()
-        L.check(lib.pdmpflux_host_alloc(C.byref(ptr), n))
-        buf = (C.c_char * n).from_address(ptr.value)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
-
     arrs, ptrs = {}, []
     for f, shape, dt in (("X", (nch, n_sk, d), np.float64), ("V", (nch, n_sk, d), np.float64), ("t", (nch, n_sk), np.float64),
                          ("horizon", (nch, n_sk), np.float64), ("ar", (nch, n_sk), np.float64),
                          ("error_value_ar", (nch, n_sk, 5), np.float64), ("errored_bound", (nch, n_sk), np.int32),
                          ("rejected", (nch, n_sk), np.int32), ("hitting_horizon", (nch, n_sk), np.int32),
                          ("x0", (nch, d), np.float64), ("v0", (nch, d), np.float64)):
-        arrs[f], ptr = pinned(shape, dt)
+        arrs[f], ptr = _pinned(lib, L, shape, dt)
         ptrs.append(ptr)
     arrs["x0"][:] = cfgd["x0"]
     arrs["v0"][:] = 1.0 / (d ** 0.5 if cfgd["unit_v"] else 1.0)
@@ -474,8 +614,8 @@ def e2e(p, sampler, name, nch, n_ev, world, dev):
     for w in range(4):  # warm-up calls: slab allocation, lazy module loading, PCIe / copy-engine ramp
         call(100 + w)
     torch.cuda.synchronize()
-    # Each call is timed on its own and the median is reported: on these shared hosts the PCIe / host-memory leg is
-    # occasionally 10-20x slower for a single call (other tenants), which a mean over 3 calls would inherit.
+    # Each call is timed on its own; the median is the headline (on these shared hosts the PCIe / host-memory leg is
+    # occasionally 10-20x slower for a single call), mean and max are reported beside it.
     reps, times = 7, []
     for i in range(reps):
         t0 = time.perf_counter()
@@ -487,13 +627,61 @@ def e2e(p, sampler, name, nch, n_ev, world, dev):
     ok = bool(np.isfinite(arrs["t"][:, -1]).all())
     for ptr in ptrs:
         lib.pdmpflux_host_free(ptr)
+    lib.pdmpflux_sampler_release_workspace(sampler._handle)
     h2d, d2h = C.c_int64(0), C.c_int64(0)
     lib.pdmpflux_last_transfer_bytes(C.byref(h2d), C.byref(d2h))   # counted by the library from the copies it issued
     return {"value": nch * n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": int(h2d.value),
             "d2h_bytes_per_step": int(d2h.value), "history_bytes_per_step": nch * n_sk * bytes_per_event(d),
-            "ms_per_step": dt * 1e3, "finite": ok,
-            "timing": "median of %d individually timed calls (min %.1f ms, max %.1f ms)" % (reps, times[0] * 1e3, times[-1] * 1e3),
-            "call": "pdmpflux_sample_skeleton (host buffers, pinned)"}
+            "ms_per_step": dt * 1e3, "ms_mean": 1e3 * sum(times) / reps, "ms_min": times[0] * 1e3, "ms_max": times[-1] * 1e3,
+            "finite": ok, "timing": "median of %d individually timed calls" % reps,
+            "call": "pdmpflux_sample_skeleton (host buffers, pinned): the reference's sample_skeleton with the full PDMPHistory returned to the host"}
+
+
+def e2e_moments(p, sampler, name, nch, n_ev, dev):
+    """End to end in moments-only mode: initial states from pinned host memory, the chains advance with fused in-kernel
+    moments and NO stored skeleton (pdmpflux_chains_enable_moments, NULL history), the 4 x d sufficient statistics are
+    reduced on the device and read back.  Nothing else crosses PCIe: this is the path that scales with the GPUs."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from pdmpflux_b200 import _lib as L
+    lib = p.lib()
+    cfgd = CONFIGS[name]; d = cfgd["d"]
+    if name == "c4":
+        return {"value": None, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_step": None,
+                "timing": "", "call": "fused moments are not available for the logistic-regression kernel"}
+    x0, px = _pinned(lib, L, (nch, d), np.float64); v0, pv = _pinned(lib, L, (nch, d), np.float64)
+    sums_h, ps = _pinned(lib, L, (4, d), np.float64)
+    x0[:] = cfgd["x0"]; v0[:] = 1.0 / (d ** 0.5 if cfgd["unit_v"] else 1.0)
+    f64 = torch.float64
+    m1 = torch.empty((nch, d), dtype=f64, device=dev); m2 = torch.empty_like(m1)
+    T = torch.empty((nch,), dtype=f64, device=dev); sums = torch.empty((4, d), dtype=f64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def call(seed):
+        ch = p.DeviceChains(sampler, x0, v0, seed=seed)            # H2D of the initial states
+        ch.enable_moments()
+        ch.advance(n_ev, None, 0, stream)
+        L.check(lib.pdmpflux_chains_get_moments(ch._h, m1.data_ptr(), m2.data_ptr(), 1))
+        L.check(lib.pdmpflux_chains_get_state(ch._h, None, None, T.data_ptr(), None, 1))
+        p.dist.moment_sums_device(m1, m2, T, sums, stream)         # pdmpflux_moments_reduce
+        torch.cuda.synchronize()
+        sums_h[:] = sums.cpu().numpy()                              # D2H of the result
+        ch.status(); ch.close()
+
+    for w in range(2):
+        call(50 + w)
+    reps, times = 5, []
+    for i in range(reps):
+        t0 = time.perf_counter(); call(7 + i); times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = times[len(times) // 2]
+    for ptr in (px, pv, ps):
+        lib.pdmpflux_host_free(ptr)
+    return {"value": nch * n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": 2 * 8 * d * nch, "d2h_bytes_per_step": 4 * 8 * d,
+            "ms_per_step": dt * 1e3, "ms_mean": 1e3 * sum(times) / reps, "ms_max": times[-1] * 1e3,
+            "finite": bool(np.isfinite(sums_h).all()), "timing": "median of %d individually timed calls" % reps,
+            "call": "pdmpflux_chains_create + enable_moments + chains_advance(NULL history) + moments_reduce, host (pinned) initial states in, 4 x d moment sums out"}
 
 
 if __name__ == "__main__":
