@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDMPFLUX_VERSION 100 /* 0.1.0 */
+#define PDMPFLUX_VERSION 200 /* 0.2.0: pdmpflux_history gained is_active (appended), Sticky Zig-Zag, reductions */
 
 typedef enum pdmpflux_error {
     PDMPFLUX_OK = 0,
@@ -39,7 +39,9 @@ typedef enum pdmpflux_error {
 
 /* src/Samplers/{ZigZagSamplers,BouncyParticleSamplers,ForwardEventChainMonteCarlo,BoomerangSamplers}.jl */
 typedef enum pdmpflux_sampler_kind {
-    PDMPFLUX_ZIGZAG = 0, PDMPFLUX_BPS = 1, PDMPFLUX_FECMC = 2, PDMPFLUX_BOOMERANG = 3
+    PDMPFLUX_ZIGZAG = 0, PDMPFLUX_BPS = 1, PDMPFLUX_FECMC = 2, PDMPFLUX_BOOMERANG = 3,
+    PDMPFLUX_STICKY_ZIGZAG = 4 /* src/Samplers/StickyZigZagSamplers.jl + src/StickySamplingLoop.jl; create it with
+                                  pdmpflux_sampler_create_sticky (it needs the thawing rates kappa) */
 } pdmpflux_sampler_kind;
 
 /* Device potential plugins (replace the Julia closure `grad U`).  params layout:
@@ -102,7 +104,9 @@ typedef struct pdmpflux_tape {
 } pdmpflux_tape;
 
 /* Output columns of PDMPHistory (Composites.jl:138-149), chain-major; any pointer may be NULL (not stored).
- * is_active is not materialised: it is all-true for the non-sticky samplers on this path. */
+ * is_active (the BitMatrix of Composites.jl:143, written by record! :254-258) is stored as one byte per coordinate and
+ * only by the Sticky Zig-Zag sampler; for the other samplers it is all-true and is left untouched (build trues(d, n)
+ * host-side). */
 typedef struct pdmpflux_history {
     double* X;               /* [C][n_cols][d] */
     double* V;               /* [C][n_cols][d] */
@@ -117,7 +121,8 @@ typedef struct pdmpflux_history {
     int64_t* tape_pos;       /* [C][3] draws consumed from (E,U,N) (tape mode) */
     int64_t* counters;       /* [C][2] (bound builds, rate evaluations) -- instrumentation */
     int64_t n_cols;          /* leading dimension (columns per chain slab) */
-    int32_t on_device;       /* all pointers above are device pointers */
+    int32_t on_device;       /* all pointers above and below are device pointers */
+    uint8_t* is_active;      /* [C][n_cols][d] 0 / 1, Sticky Zig-Zag only (NULL: not stored) */
 } pdmpflux_history;
 
 typedef struct pdmpflux_potential_s* pdmpflux_potential_t;
@@ -137,6 +142,12 @@ int pdmpflux_potential_destroy(pdmpflux_potential_t pot);
 /* replaces ZigZag(dim, grad U; kw...) / BPS / ForwardECMC / Boomerang constructors */
 int pdmpflux_sampler_create(int sampler_kind, int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg,
                             pdmpflux_sampler_t* out);
+/* replaces StickyZigZag(dim, grad U, kappa; kw...) (StickyZigZagSamplers.jl:60-111): Zig-Zag closures plus the
+ * thawing rates kappa[dim] (prior inclusion).  Runs on the generic (per-node) path; sample_skeleton* then produce the
+ * sticky skeleton (flips, stickings and thawings are all skeleton points, with the is_active column).  The
+ * time-horizon variant is not available for it (PDMPFLUX_ERR_UNSUPPORTED). */
+int pdmpflux_sampler_create_sticky(int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg, const double* kappa,
+                                   pdmpflux_sampler_t* out);
 int pdmpflux_sampler_destroy(pdmpflux_sampler_t s);
 /* Ownership / threading of a sampler handle: the host-buffer pipeline of pdmpflux_sample_skeleton* caches its device
  * slabs, pinned staging buffers and copy stream in the handle (they only grow; one large call keeps up to ~10 GiB of
@@ -220,6 +231,12 @@ int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t 
  * j = 1..n_out with n_out = floor(t[end]/dt) computed by the caller; and, with n_sk < ld_sk, the (N, dt) method
  * (src/sample.jl:649-682) that only uses the first n_sk columns of slabs whose leading dimension is ld_sk.
  * All chains must share n_out (pass chains one at a time for ragged skeletons). */
+/* replaces sample_from_skeleton(sampler::StickyPDMP, N, history) (src/sample.jl:516-561): the reconstructed velocity of
+ * a frozen coordinate is zero.  is_active: [C][n_sk][d] bytes as written by the sticky skeleton (NULL: all active). */
+int pdmpflux_sample_from_skeleton_sticky(int dim, int64_t n_sk, int64_t n_chains, const double* X, const double* V,
+                                         const double* t, const uint8_t* is_active, int64_t N, int32_t discard_vt,
+                                         double* out, int32_t on_device, void* cuda_stream);
+
 int pdmpflux_sample_from_skeleton_dt(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int64_t n_chains,
                                      const double* X, const double* V, const double* t, double dt, int64_t n_out,
                                      int32_t discard_vt, double* out, int32_t on_device, void* cuda_stream);

@@ -63,7 +63,7 @@ class History(C.Structure):
                 ("ar", C.c_void_p), ("error_value_ar", C.c_void_p), ("errored_bound", C.c_void_p),
                 ("rejected", C.c_void_p), ("hitting_horizon", C.c_void_p), ("status", C.c_void_p),
                 ("tape_pos", C.c_void_p), ("counters", C.c_void_p), ("n_cols", C.c_int64),
-                ("on_device", C.c_int32)]
+                ("on_device", C.c_int32), ("is_active", C.c_void_p)]
 
 
 # every symbol include/pdmpflux_cuda.h declares: (restype, argtypes)
@@ -75,6 +75,7 @@ SIGNATURES = {
     "pdmpflux_potential_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "pdmpflux_potential_destroy": (C.c_int, [C.c_void_p]),
     "pdmpflux_sampler_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "pdmpflux_sampler_create_sticky": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(Config), C.c_void_p, C.POINTER(C.c_void_p)]),
     "pdmpflux_sampler_destroy": (C.c_int, [C.c_void_p]),
     "pdmpflux_sampler_release_workspace": (C.c_int, [C.c_void_p]),
     "pdmpflux_sampler_get_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
@@ -100,6 +101,8 @@ SIGNATURES = {
     "pdmpflux_chains_destroy": (C.c_int, [C.c_void_p]),
     "pdmpflux_sample_from_skeleton": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdmpflux_sample_from_skeleton_sticky": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                       C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "pdmpflux_sample_from_skeleton_dt": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                                    C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int32, C.c_void_p,
                                                    C.c_int32, C.c_void_p]),
@@ -141,7 +144,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             f = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             f.restype, f.argtypes = res, args
-        if l.pdmpflux_version() < 100:
+        if l.pdmpflux_version() < 200:
             raise ImportError("libpdmpflux_cuda.so is older than this binding")
         _lib = l
     return _lib

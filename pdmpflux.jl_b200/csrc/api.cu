@@ -105,6 +105,7 @@ struct pdmpflux_sampler_s {
     int kind = 0, dim = 0;
     pdmpflux_config cfg{};
     pdmpflux_potential_s* pot = nullptr;
+    DevBuf kappa;  // Sticky Zig-Zag: thawing rates [dim]
     Workspace ws;
 };
 
@@ -115,7 +116,7 @@ struct pdmpflux_chains_s {
     int team = 32, n_own = 0, scratch_in_smem = 1, path = 0, vec_elems = 0, dpad = 0;
     size_t smem = 0;
     unsigned grid = 0;
-    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols, m1, m2, wq;
+    DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols, m1, m2, wq, act;
     int moments = 0;
     double t_stop = 0.0;
     int use_t_stop = 0;
@@ -189,6 +190,7 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
         if (rows) { p.X = rows->X; p.V = rows->V; p.ld_rows = rows->ld; p.col0_rows = rows->col0; }
     }
     p.col0 = col0;
+    p.kappa = s->kappa.as<double>(); p.sact = ch->act.as<uint8_t>(); p.ACT = h ? h->is_active : nullptr;
     p.scratch = ch->scratch.as<double>(); p.scratch_in_smem = ch->scratch_in_smem; p.n_own = ch->n_own;
     p.vec_elems = ch->vec_elems; p.dpad = ch->dpad;
     if (h) {
@@ -240,6 +242,7 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     case PDMPFLUX_BPS: e = launch_skeleton_bps(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
     case PDMPFLUX_FECMC: e = launch_skeleton_fecmc(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
     case PDMPFLUX_BOOMERANG: e = launch_skeleton_boomerang(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
+    case PDMPFLUX_STICKY_ZIGZAG: e = launch_skeleton_sticky(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
     default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("skeleton kernel launch: ") + cudaGetErrorString(e));
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(256) pack_signs_kernel(const double* __restric
 __global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64_t n_sk, int64_t ld_sk, int64_t N,
                                                      int discard_vt, double dt_fixed, const double* __restrict__ X,
                                                      const double* __restrict__ V, const double* __restrict__ T,
-                                                     double* __restrict__ out) {
+                                                     const uint8_t* __restrict__ act, double* __restrict__ out) {
     const int64_t c = blockIdx.x;  // chains on grid.x (up to 2^31 - 1), output elements grid-strided over grid.y
     const double* t = T + c * ld_sk;
     const double dt = dt_fixed > 0.0 ? dt_fixed : t[n_sk - 1] / (double)N;
@@ -309,7 +312,8 @@ __global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64
         if (a == 2 * d) r = tm;
         else {
             const int b = a < d ? a : a - d;
-            const double xi = x0[b], vi = v0[b];
+            // Sticky samplers (src/sample.jl:516-561): the reconstructed velocity of a frozen coordinate is zero
+            const double xi = x0[b], vi = (act && !act[(c * ld_sk + lo) * d + b]) ? 0.0 : v0[b];
             if (flow_kind == 1) {
                 double s, co;
                 sincos(tau, &s, &co);
@@ -355,7 +359,7 @@ int normalise_config(int kind, int dim, pdmpflux_config& c) {
     // constructor rewrites: ZigZagSamplers.jl:73-78, BouncyParticleSamplers.jl:29-37,
     // ForwardEventChainMonteCarlo.jl:306-323, BoomerangSamplers.jl:27-36
     if (c.tmax == 0.0) { c.tmax = 1.0; c.adaptive = 1; }
-    if (kind == PDMPFLUX_ZIGZAG) {
+    if (kind == PDMPFLUX_ZIGZAG || kind == PDMPFLUX_STICKY_ZIGZAG) {
         if (c.signed_bound && !c.vectorized_bound) c.signed_bound = 0;
     } else c.vectorized_bound = 0;
     if (kind == PDMPFLUX_FECMC) {
@@ -446,11 +450,27 @@ int pdmpflux_potential_create(int kind, int dim, const double* params, int64_t n
 }
 int pdmpflux_potential_destroy(pdmpflux_potential_t pot) { delete pot; return PDMPFLUX_OK; }
 
+static int sampler_create_impl(int kind, int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg, const double* kappa,
+                               pdmpflux_sampler_t* out);
+
 int pdmpflux_sampler_create(int kind, int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg, pdmpflux_sampler_t* out) {
+    if (kind == PDMPFLUX_STICKY_ZIGZAG)
+        return fail(PDMPFLUX_ERR_ARGUMENT, "StickyZigZag needs the thawing rates kappa: use pdmpflux_sampler_create_sticky");
+    return sampler_create_impl(kind, dim, pot, cfg, nullptr, out);
+}
+
+int pdmpflux_sampler_create_sticky(int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg, const double* kappa,
+                                   pdmpflux_sampler_t* out) {
+    if (!kappa) return fail(PDMPFLUX_ERR_ARGUMENT, "kappa is NULL");
+    return sampler_create_impl(PDMPFLUX_STICKY_ZIGZAG, dim, pot, cfg, kappa, out);
+}
+
+static int sampler_create_impl(int kind, int dim, pdmpflux_potential_t pot, const pdmpflux_config* cfg, const double* kappa,
+                               pdmpflux_sampler_t* out) {
     if (!out) return fail(PDMPFLUX_ERR_ARGUMENT, "out is NULL");
     *out = nullptr;
     if (!pot || !cfg) return fail(PDMPFLUX_ERR_ARGUMENT, "potential / config is NULL");
-    if (kind < PDMPFLUX_ZIGZAG || kind > PDMPFLUX_BOOMERANG)
+    if (kind < PDMPFLUX_ZIGZAG || kind > PDMPFLUX_STICKY_ZIGZAG)
         return fail(PDMPFLUX_ERR_UNSUPPORTED, "sampler kind outside the device path (Sticky/SpeedUp/RHMC are not ported; no CPU fallback)");
     if (dim <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "dimension dim must be positive. Current value: " + std::to_string(dim));
     if (dim != pot->dim) return fail(PDMPFLUX_ERR_DIMENSION_MISMATCH, "potential dim " + std::to_string(pot->dim) + " != sampler dim " + std::to_string(dim));
@@ -463,6 +483,15 @@ int pdmpflux_sampler_create(int kind, int dim, pdmpflux_potential_t pot, const p
     auto s = new pdmpflux_sampler_s();
     s->kind = kind; s->dim = dim; s->cfg = *cfg; s->pot = pot;
     normalise_config(kind, dim, s->cfg);
+    if (kind == PDMPFLUX_STICKY_ZIGZAG) {
+        for (int i = 0; i < dim; ++i)
+            if (!(kappa[i] >= 0.0) || !std::isfinite(kappa[i])) { delete s; return fail(PDMPFLUX_ERR_ARGUMENT, "kappa must be finite and non-negative"); }
+        if (s->kappa.alloc(sizeof(double) * dim) != cudaSuccess ||
+            cudaMemcpy(s->kappa.p, kappa, sizeof(double) * dim, cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete s;
+            return fail(PDMPFLUX_ERR_CUDA, "kappa upload failed (is a CUDA device present?)");
+        }
+    }
     if (pot->kind == PDMPFLUX_LOGREG) {
         const pdmpflux_config& c = s->cfg;
         if (kind != PDMPFLUX_ZIGZAG || !c.vectorized_bound || c.grid_size < 2 || c.grid_size > 12 ||
@@ -522,7 +551,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     const size_t vec_bytes = (size_t)ch->vec_elems * sizeof(double);
     const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent &&
                          brent_reg_nw(s->kind, ch->path, ch->team, ch->n_own) == 0) ? 4 : 2;
-    ch->smem = nvec * vec_bytes;
+    ch->smem = (nvec + (s->kind == PDMPFLUX_STICKY_ZIGZAG ? 1 : 0)) * vec_bytes;
     if (s->kind == PDMPFLUX_FECMC) {
         if ((nvec + 3) * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = (nvec + 3) * vec_bytes; }
         else {
@@ -563,6 +592,10 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     // device first; the stream is drained again before returning, so every later launch sees initialised state.
     if (init_on_device || (tape && tape->on_device)) CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemset(ch->ncols.p, 0, sizeof(int64_t) * n_chains));
+    if (s->kind == PDMPFLUX_STICKY_ZIGZAG) {  // PDMPState ctor: is_active = trues(d) (Composites.jl:95-99)
+        CUDA_TRY(ch->act.alloc((size_t)d * n_chains));
+        CUDA_TRY(cudaMemset(ch->act.p, 1, (size_t)d * n_chains));
+    }
     const cudaMemcpyKind k = init_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CUDA_TRY(cudaMemcpy(ch->x.p, xinit, sizeof(double) * d * n_chains, k));
     CUDA_TRY(cudaMemcpy(ch->v.p, vinit, sizeof(double) * d * n_chains, k));
@@ -740,6 +773,8 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         if (rc != PDMPFLUX_OK) return rc;
     }
     if (t_stop) {
+        if (s->kind == PDMPFLUX_STICKY_ZIGZAG)
+            return fail(PDMPFLUX_ERR_UNSUPPORTED, "the time-horizon sample_skeleton is not available for StickyZigZag on the device path (no CPU fallback)");
         rc = pdmpflux_chains_set_stop_time(ch, *t_stop);
         if (rc != PDMPFLUX_OK) return rc;
     }
@@ -772,6 +807,42 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
         if (hist->tape_pos) CUDA_TRY(cudaMemcpy(hist->tape_pos, ch->tape_pos.p, sizeof(int64_t) * 3 * n_chains, cudaMemcpyDeviceToDevice));
         if (hist->counters) CUDA_TRY(cudaMemcpy(hist->counters, ch->counters.p, sizeof(int64_t) * 2 * n_chains, cudaMemcpyDeviceToDevice));
         return finish(pdmpflux_chains_status(ch, nullptr, nullptr, nullptr));
+    }
+
+    if (s->kind == PDMPFLUX_STICKY_ZIGZAG) {
+        // Sticky Zig-Zag with host buffers: the whole history is produced in device memory and copied once (this is the
+        // row after the hot path; the sliced, overlapped pipeline below serves the four samplers of the hot path).
+        const size_t nc = (size_t)n_chains * n_sk;
+        DevBuf dX, dV, dt, dh, da, de, deb, drj, dhh, dact;
+        pdmpflux_history hv{};
+        hv.n_cols = n_sk; hv.on_device = 1;
+        auto want = [&](DevBuf& b, const void* host, size_t bytes) -> void* {
+            if (!host) return nullptr;
+            return b.alloc(bytes) == cudaSuccess ? b.p : nullptr;
+        };
+        hv.X = (double*)want(dX, hist->X, nc * d * 8); hv.V = (double*)want(dV, hist->V, nc * d * 8);
+        hv.t = (double*)want(dt, hist->t, nc * 8); hv.horizon = (double*)want(dh, hist->horizon, nc * 8);
+        hv.ar = (double*)want(da, hist->ar, nc * 8); hv.error_value_ar = (double*)want(de, hist->error_value_ar, nc * 40);
+        hv.errored_bound = (int32_t*)want(deb, hist->errored_bound, nc * 4); hv.rejected = (int32_t*)want(drj, hist->rejected, nc * 4);
+        hv.hitting_horizon = (int32_t*)want(dhh, hist->hitting_horizon, nc * 4);
+        hv.is_active = (uint8_t*)want(dact, hist->is_active, nc * d);
+        if ((hist->X && !hv.X) || (hist->V && !hv.V) || (hist->t && !hv.t) || (hist->is_active && !hv.is_active))
+            return fail(PDMPFLUX_ERR_CUDA, "device allocation for the sticky history failed");
+        rc = pdmpflux_chains_record(ch, &hv, 0, stream);
+        if (rc == PDMPFLUX_OK && n_sk > 1) rc = pdmpflux_chains_advance(ch, n_sk - 1, &hv, 1, stream);
+        if (rc != PDMPFLUX_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        auto back = [&](void* host, const void* dev, size_t elem) -> cudaError_t {
+            if (!host) return cudaSuccess;
+            return cudaMemcpy2D(host, (size_t)hist->n_cols * elem, dev, (size_t)n_sk * elem, (size_t)n_sk * elem, (size_t)n_chains,
+                                cudaMemcpyDeviceToHost);
+        };
+        CUDA_TRY(back(hist->X, hv.X, 8 * (size_t)d)); CUDA_TRY(back(hist->V, hv.V, 8 * (size_t)d));
+        CUDA_TRY(back(hist->t, hv.t, 8)); CUDA_TRY(back(hist->horizon, hv.horizon, 8)); CUDA_TRY(back(hist->ar, hv.ar, 8));
+        CUDA_TRY(back(hist->error_value_ar, hv.error_value_ar, 40)); CUDA_TRY(back(hist->errored_bound, hv.errored_bound, 4));
+        CUDA_TRY(back(hist->rejected, hv.rejected, 4)); CUDA_TRY(back(hist->hitting_horizon, hv.hitting_horizon, 4));
+        CUDA_TRY(back(hist->is_active, hv.is_active, (size_t)d));
+        return pdmpflux_chains_status(ch, hist->status, hist->tape_pos, hist->counters);
     }
 
     // ---- host-buffer path: slices of columns, two device slabs, D2H of slice i overlaps the kernel of slice i+1
@@ -1060,7 +1131,14 @@ static int run_skeleton(pdmpflux_sampler_t s, int64_t n_chains, int64_t n_sk, co
 
 static int interp_impl(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int64_t n_chains, const double* X,
                        const double* V, const double* t, int64_t N, double dt_fixed, int32_t discard_vt, double* out,
-                       int32_t on_device, void* stream_);
+                       int32_t on_device, void* stream_, const uint8_t* act = nullptr);
+
+int pdmpflux_sample_from_skeleton_sticky(int dim, int64_t n_sk, int64_t n_chains, const double* X, const double* V,
+                                         const double* t, const uint8_t* is_active, int64_t N, int32_t discard_vt,
+                                         double* out, int32_t on_device, void* stream_) {
+    if (N <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "N must be positive. Current value: " + std::to_string(N));
+    return interp_impl(0, dim, n_sk, n_sk, n_chains, X, V, t, N, 0.0, discard_vt, out, on_device, stream_, is_active);
+}
 
 int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, const double* X,
                                   const double* V, const double* t, int64_t N, int32_t discard_vt, double* out,
@@ -1079,18 +1157,24 @@ int pdmpflux_sample_from_skeleton_dt(int flow_kind, int dim, int64_t n_sk, int64
 
 static int interp_impl(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int64_t n_chains, const double* X,
                        const double* V, const double* t, int64_t N, double dt_fixed, int32_t discard_vt, double* out,
-                       int32_t on_device, void* stream_) {
+                       int32_t on_device, void* stream_, const uint8_t* act) {
     if (!X || !V || !t || !out || dim <= 0 || n_sk <= 0 || n_chains <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
     if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear) or 1 (rotation)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int ld = discard_vt ? dim : 2 * dim + 1;
-    DevBuf dX, dV, dt, dout;
+    DevBuf dX, dV, dt, dout, dact;
     const double *pX = X, *pV = V, *pt = t;
+    const uint8_t* pact = act;
     double* po = out;
     if (!on_device) {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PDMPFLUX_ERR_CUDA, "no CUDA device: no CPU fallback");
         const size_t nx = sizeof(double) * dim * ld_sk * n_chains;
+        if (act) {
+            CUDA_TRY(dact.alloc((size_t)dim * ld_sk * n_chains));
+            CUDA_TRY(cudaMemcpyAsync(dact.p, act, (size_t)dim * ld_sk * n_chains, cudaMemcpyHostToDevice, stream));
+            pact = dact.as<uint8_t>();
+        }
         CUDA_TRY(dX.alloc(nx)); CUDA_TRY(dV.alloc(nx)); CUDA_TRY(dt.alloc(sizeof(double) * ld_sk * n_chains));
         CUDA_TRY(dout.alloc(sizeof(double) * ld * N * n_chains));
         CUDA_TRY(cudaMemcpyAsync(dX.p, X, nx, cudaMemcpyHostToDevice, stream));
@@ -1100,7 +1184,7 @@ static int interp_impl(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int6
     }
     const int64_t total = N * (int64_t)ld;
     dim3 grid((unsigned)n_chains, (unsigned)std::min<int64_t>((total + 255) / 256, 65535));
-    interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, ld_sk, N, discard_vt, dt_fixed, pX, pV, pt, po);
+    interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, ld_sk, N, discard_vt, dt_fixed, pX, pV, pt, pact, po);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     if (!on_device) {

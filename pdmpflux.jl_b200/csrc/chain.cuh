@@ -36,6 +36,10 @@ extern __shared__ __align__(128) double g_smem[];
 #define BS(j) g_smem[off_b + (j) * kStr]
 #define M1S(j) g_smem[off_m1 + (j) * kStr]
 #define M2S(j) g_smem[off_m2 + (j) * kStr]
+// Sticky Zig-Zag: 1.0 / 0.0 activity flag per coordinate; VU = the velocity the flow, the rates and the bounds see
+// (`_active_velocity`, SamplingLoopInplace.jl:13-25: frozen coordinates move with velocity zero)
+#define ACS(j) g_smem[off_ac + (j) * kStr]
+#define VU(j) (kSticky ? VS(j) * ACS(j) : VS(j))
 #define BOX(k) g_smem[off_box + (k) * kBStr]
 #define CUM(k) g_smem[off_cum + (k) * kBStr]
 
@@ -68,11 +72,15 @@ struct Chain {
     static constexpr int K = P::K;
     static constexpr int KK = K > 0 ? K : 1;
     static constexpr bool kRot = (SAMPLER == PDMPFLUX_BOOMERANG);
-    static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG);
+    static constexpr bool kSticky = (SAMPLER == PDMPFLUX_STICKY_ZIGZAG);
+    static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG) || kSticky;   // StickyZigZagSamplers.jl:69-101: same closures
+    static_assert(!kSticky || PATH == kPathGeneric, "Sticky Zig-Zag runs on the generic path");
     static constexpr int kStr = (TEAM == 1) ? kBlockThreads : TEAM;  // stride between a thread's owned elements
     static constexpr int kBStr = (TEAM == 1) ? kBlockThreads : 1;    // stride between a chain's box / cum entries
 
     const KernelParams& p;
+    int off_ac;                      // Sticky Zig-Zag: is_active flags of the owned coordinates (1.0 / 0.0)
+    double tt;                       // Sticky Zig-Zag: time to thaw (StickySamplingLoop.jl:43)
     int off_m1, off_m2;              // fused-moment accumulators (owned columns, only when p.accumulate_moments)
     int off_x, off_v, off_a, off_b;  // element offsets into g_smem of this thread's owned columns of x, v, A, B
     double* sc0; // scratch owned vectors (FECMC)
@@ -224,7 +232,7 @@ struct Chain {
             for (int k = 0; k < 2 * KK; ++k) acc[k] = 0.0;
             for_owned([&](int j) {
                 P::accum(p.pot, coord(j), XS(j), acc);
-                P::accum(p.pot, coord(j), VS(j), acc + KK);
+                P::accum(p.pot, coord(j), VU(j), acc + KK);
             });
             team_sum_n<TEAM, 2 * KK>(acc, mask);
 #pragma unroll
@@ -262,7 +270,7 @@ struct Chain {
     // negative (time-horizon variant stepping back to T), which subtracts the overshoot
     __device__ void accumulate_segment(double tt, const Flow& f) {
         for_owned([&](int j) {
-            const double x = XS(j), v = VS(j);
+            const double x = XS(j), v = VU(j);
             if constexpr (kRot) {  // x cos s + v sin s  (f.a = cos tt, f.b = sin tt)
                 const double s2t = 2.0 * f.b * f.a;
                 M1S(j) += x * f.b + v * (1.0 - f.a);
@@ -280,7 +288,7 @@ struct Chain {
         if (p.accumulate_moments) accumulate_segment(tt, f);
         for_owned([&](int j) {
             double xt, vt;
-            flow_point(f, XS(j), VS(j), xt, vt);
+            flow_point(f, XS(j), VU(j), xt, vt);
             XS(j) = xt;
             if constexpr (kRot) VS(j) = vt;
         });
@@ -448,7 +456,7 @@ struct Chain {
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     double xt, vt;
-                    flow_point(f, XS(j), VS(j), xt, vt);
+                    flow_point(f, XS(j), VU(j), xt, vt);
                     const double y = P::grad(p.pot, coord(j), xt, Lxt) * vt;
                     if constexpr (kZZ) s += (y > 0.0 ? y : 0.0);
                     else s += y;
@@ -624,7 +632,7 @@ struct Chain {
             for (int j = 0; j < nown; ++j)
                 if (owns(j)) {
                     const int i = coord(j);
-                    const double xi = XS(j), vi = VS(j);
+                    const double xi = XS(j), vi = VU(j);
                     double vl, gl;
                     vect_node(i, xi, vi, tn[0], h, vl, gl);
 #pragma unroll
@@ -660,7 +668,7 @@ struct Chain {
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
                 const int i = coord(j);
-                const double xi = XS(j), vi = VS(j);
+                const double xi = XS(j), vi = VU(j);
 #pragma unroll
                 for (int u = 0; u < kChunk; ++u)
                     if (u < n) {
@@ -1334,7 +1342,8 @@ struct Chain {
     __device__ void velocity_jump() {
         // functionals of the moved x (v's are refreshed by the next compute_functionals before a bound build)
         compute_functionals();
-        if constexpr (SAMPLER == PDMPFLUX_ZIGZAG) jump_zigzag();
+        if constexpr (kZZ) jump_zigzag();   // Sticky: the jump sees the FULL velocity, frozen coordinates included
+                                            // (QUIRK: if_accept! passes state.v, SamplingLoopInplace.jl:178)
         else if constexpr (SAMPLER == PDMPFLUX_BPS) jump_bps();
         else if constexpr (SAMPLER == PDMPFLUX_FECMC) jump_fecmc();
         else jump_boomerang();
@@ -1430,7 +1439,7 @@ struct Chain {
                             status = PDMPFLUX_CHAIN_DONE;
                             live = false;
                         } else {
-                        if constexpr (kZZ) accept_zigzag(tp, lt);
+                        if constexpr (kZZ && !kSticky) accept_zigzag(tp, lt);
                         else {
                             flow_inplace(tp);
                             velocity_jump();
@@ -1466,6 +1475,160 @@ struct Chain {
                     }
                 }
             }
+        }
+        return ev;
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // Sticky Zig-Zag: get_event_state!(state, ::StickyPDMP) (SamplingLoopInplace.jl:49-63) and its loop body
+    // (StickySamplingLoop.jl:30-164), with the masked variants of the shared steps (SamplingLoopInplace.jl:87-217).
+    // Every accepted flip, every sticking and every thawing is a skeleton point.  Written with the reference's own
+    // nesting (this is the row after the hot path: parity first).  Quirks kept: the velocity jump after an accepted
+    // event sees the full velocity, frozen coordinates included; thawing adds tt but not the time already spent in
+    // horizon moves (ts) to the clock (:160-161); axis crossings are only looked for at the start of an outer step
+    // (:52-60) and the time to the axis is -x_j v_j (|v_j| = 1 is assumed, :81-83).
+    // ------------------------------------------------------------------------------------------------
+    __device__ double frozen_rate() {  // sum of kappa_i over the frozen coordinates (StickySamplingLoop.jl:37-42, :143-148)
+        double r = 0.0;
+        for_owned([&](int j) { if (ACS(j) == 0.0) r += __ldg(p.kappa + coord(j)); });
+        return team_sum<TEAM>(r, mask);
+    }
+
+    __device__ void sticky_move_to_axes_and_stick() {  // StickySamplingLoop.jl:73-107
+        double best = CUDART_INF;
+        int bi = 0x7fffffff;
+        for_owned([&](int j) {
+            if (ACS(j) != 0.0) {
+                const double dj = XS(j) * VS(j);
+                if (dj < 0 && -dj < best) { best = -dj; bi = coord(j); }   // per lane in increasing coordinate order
+            }
+        });
+        if constexpr (TEAM > 1) {  // lexicographic minimum of (time, coordinate): the reference keeps the first minimum
+#pragma unroll
+            for (int o = TEAM / 2; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(mask, best, o);
+                const int oi = __shfl_xor_sync(mask, bi, o);
+                if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+        }
+        if (!(best < CUDART_INF)) { status = PDMPFLUX_CHAIN_STEP_LIMIT; return; }  // "erronous t_togo": cannot happen
+        flow_inplace(best);
+        if (bi % TEAM == tl) ACS(bi / TEAM) = 0.0;   // freeze the coordinate
+        t += best + ts;
+        ts = 0.0;
+    }
+
+    __device__ void sticky_thaw_one_coordinate() {  // StickySamplingLoop.jl:138-164
+        flow_inplace(tt);
+        const double total = frozen_rate();
+        const double u = rand_uniform() * total;
+        // first frozen coordinate (in coordinate order) whose cumulative kappa reaches u
+        double carry = 0.0;
+        int m = -1;
+        for (int j = 0; j < nown && m < 0; ++j) {
+            const double kj = (owns(j) && ACS(j) == 0.0) ? __ldg(p.kappa + coord(j)) : 0.0;
+            const double incl = team_scan_incl<TEAM>(kj, mask, tl) + carry;
+            const bool hit = owns(j) && ACS(j) == 0.0 && (incl >= u);
+            if constexpr (TEAM == 1) { if (hit) m = j; }
+            else {
+                unsigned b = __ballot_sync(mask, hit) & mask;
+                b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
+                if (b) m = (__ffs(b) - 1) + TEAM * j;
+            }
+            carry = team_bcast<TEAM>(incl, TEAM - 1, mask);
+        }
+        if (m >= 0 && m % TEAM == tl) ACS(m / TEAM) = 1.0;   // thaw it
+        // QUIRK: the clock advances by tt only; the horizon moves made since the last event (ts) are dropped
+        t += tt;
+        ts = 0.0;
+    }
+
+    __device__ int64_t run_events_sticky(int64_t c, bool valid) {
+        int64_t ev = 0;
+        bool live = valid && status == 0 && p.n_events > 0;
+        while (live) {
+            begin_event(ev);
+            accept = false;
+            bool stick = false;
+            int steps = 0;
+            while (!accept && !stick && live) {   // get_event_state!
+                if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; live = false; break; }
+                // one_step_of_thinning_or_sticking_or_thawing, StickySamplingLoop.jl:30-67
+                compute_functionals();
+                build_bound(horizon);
+                const double e = rand_exp();
+                next_event(e, tp, lambda_bar);
+                exp_rv = e;
+                const double rt = frozen_rate();
+                tt = (rt == 0) ? CUDART_INF : rand_exp() / rt;
+                if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; break; }
+                const double event_time = fmin(fmin(tp, horizon), tt);
+                bool crossed = false;
+                for_owned([&](int j) {
+                    const double xj = XS(j);
+                    crossed = crossed || (xj * (xj + VU(j) * event_time) < 0);
+                });
+                if constexpr (TEAM > 1) crossed = (__ballot_sync(mask, crossed) & mask) != 0u;
+                if (crossed) {
+                    sticky_move_to_axes_and_stick();
+                    stick = true;
+                } else if (fmin(tp, tt) > horizon) {  // move_to_horizon!, SamplingLoopInplace.jl:87-101
+                    flow_inplace(horizon);
+                    ts += horizon;
+                    hh += 1;
+                    horizon = p.adaptive ? horizon * 1.01 : horizon;
+                } else {  // moves_until_horizon_or_axes, StickySamplingLoop.jl:121-132
+                    while (fmin(tp, tt) < horizon && !accept && !stick && live) {
+                        if (tp < tt) {  // ac_step!, SamplingLoopInplace.jl:113-129
+                            ++n_rates;
+                            const double lt = rate_unsigned(tp);
+                            ar = lt / lambda_bar;
+                            if (ar > 1.0) {  // erroneous_acceptance_rate!, :131-151
+                                const double h2 = horizon / 2;
+                                build_bound(h2);
+                                const double e2 = rand_exp();
+                                next_event(e2, tp, lambda_bar);
+                                exp_rv = e2;
+                                horizon = p.adaptive ? h2 : horizon;
+                                eb += 1;
+                                const int slot = eb % 5;
+#pragma unroll
+                                for (int k = 0; k < 5; ++k)
+                                    if (k == slot) eva[k] = ar;
+                            } else if (rand_uniform() < ar) {  // if_accept!, :170-186
+                                flow_inplace(tp);
+                                velocity_jump();
+                                t = t + tp + ts;
+                                ts = 0.0;
+                                tp = 0.0;
+                                accept = true;
+                            } else {  // if_reject!, :188-203
+                                const double e3 = exp_rv + rand_exp();
+                                next_event(e3, tp, lambda_bar);
+                                horizon = p.adaptive ? horizon / 1.04 : horizon;
+                                exp_rv = e3;
+                                rej += 1;
+                                if (fmin(tp, tt) > horizon) {  // move_to_horizon2!, :205-217
+                                    flow_inplace(horizon);
+                                    ts += horizon;
+                                    hh += 1;
+                                }
+                            }
+                        } else {
+                            sticky_thaw_one_coordinate();
+                            stick = true;
+                        }
+                        if (exhausted) { status = PDMPFLUX_CHAIN_TAPE_EXHAUSTED; live = false; }
+                        else if (status != 0) live = false;
+                        if (++steps > p.max_steps) { status = PDMPFLUX_CHAIN_STEP_LIMIT; live = false; }
+                    }
+                }
+                if (status != 0) live = false;
+            }
+            if (!live) break;
+            record(c, p.col0 + ev);
+            ++ev;
+            live = ev < p.n_events;
         }
         return ev;
     }
@@ -1568,6 +1731,9 @@ struct Chain {
                 if (p.V)
                     for (int j = 0; j < nown; ++j) p.V[orow * d + j] = VS(j);
             }
+        }
+        if constexpr (kSticky) {  // is_active[:, k] (Composites.jl:254-258), one byte per coordinate
+            if (p.ACT) for_owned([&](int j) { p.ACT[orow * d + coord(j)] = ACS(j) != 0.0 ? 1 : 0; });
         }
         if (tl != 0) return;
         // ---- t, horizon, ar: 4 events per 256-bit store ----
@@ -1678,6 +1844,13 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
         ch.sc2 = base + 2 * (size_t)vec;
         if (p.scratch_in_smem && SAMPLER == PDMPFLUX_FECMC) used += 3;
     }
+    ch.off_ac = 0;
+    ch.tt = CUDART_INF;
+    if constexpr (SAMPLER == PDMPFLUX_STICKY_ZIGZAG) {
+        ch.off_ac = used * vec + toff;
+        used += 1;
+        ch.for_owned([&](int j) { g_smem[ch.off_ac + j * ch.kStr] = p.sact[c * p.d + ch.coord(j)] ? 1.0 : 0.0; });
+    }
     ch.off_m1 = ch.off_m2 = 0;
     if (p.accumulate_moments) {
         ch.off_m1 = used * vec + toff;
@@ -1734,8 +1907,12 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
         }
         return;
     }
-    const int64_t n_rec = ch.run_events(c, valid);
+    int64_t n_rec;
+    if constexpr (SAMPLER == PDMPFLUX_STICKY_ZIGZAG) n_rec = ch.run_events_sticky(c, valid);
+    else n_rec = ch.run_events(c, valid);
     if (!valid) return;
+    if constexpr (SAMPLER == PDMPFLUX_STICKY_ZIGZAG)
+        ch.for_owned([&](int j) { p.sact[c * p.d + ch.coord(j)] = g_smem[ch.off_ac + j * ch.kStr] != 0.0 ? 1 : 0; });
     ch.finish_output(c, n_rec);
     // store PDMPState
     for (int j = 0; j < ch.nown; ++j)

@@ -66,6 +66,10 @@ struct KernelParams {
     int32_t *EB, *REJ, *HH;
     int64_t ld_cols, col0;        // scalar columns: leading dimension / first column of this launch
     int64_t ld_rows, col0_rows;   // X, V rows (may live in a narrower slab than the scalar columns)
+    // Sticky Zig-Zag (StickySamplingLoop.jl): thawing rates, per-chain activity flags (state, in/out), is_active output
+    const double* kappa;   // [d]
+    uint8_t* sact;         // [C][d]
+    uint8_t* ACT;          // [C][n_cols][d] (may be null)
     // per-block scratch vectors in global memory (used when they do not fit in shared memory)
     double* scratch;
     int scratch_in_smem;

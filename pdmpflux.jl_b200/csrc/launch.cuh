@@ -16,7 +16,8 @@ template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
 cudaError_t launch_one(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
     // combinations without a fast path fall back to the generic kernel (same results, more passes)
     constexpr bool ok = PATH == kPathGeneric ||
-                        (Pot<POT>::kAffine && !(SAMPLER == PDMPFLUX_BOOMERANG && Pot<POT>::kSpecial > 0));
+                        (SAMPLER != PDMPFLUX_STICKY_ZIGZAG && Pot<POT>::kAffine &&
+                         !(SAMPLER == PDMPFLUX_BOOMERANG && Pot<POT>::kSpecial > 0));
     if constexpr (!ok) return cudaErrorInvalidValue;
     else {
         auto kern = skeleton_kernel<TEAM, SAMPLER, POT, PATH, NW>;
@@ -91,6 +92,7 @@ inline int select_path(int sampler, int pot, int grid_size, int vectorized, int 
     const bool affine = pot == PDMPFLUX_GAUSS_STD || pot == PDMPFLUX_GAUSS_DIAG || pot == PDMPFLUX_GAUSS_EQUICORR ||
                         pot == PDMPFLUX_BANANA;
     if (!affine || (sampler == PDMPFLUX_BOOMERANG && pot == PDMPFLUX_BANANA)) return kPathGeneric;
+    if (sampler == PDMPFLUX_STICKY_ZIGZAG) return kPathGeneric;  // masked velocities: per-node evaluation only
     if (grid_size == 0) return kPathFastBrent;
     if (sampler == PDMPFLUX_ZIGZAG) {
         // vectorised bound with analytic derivatives only: with finite differences the reference's cell maximum
@@ -114,5 +116,6 @@ cudaError_t launch_skeleton_zigzag(int team, int pot, int path, const KernelPara
 cudaError_t launch_skeleton_bps(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_skeleton_fecmc(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_skeleton_boomerang(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_skeleton_sticky(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 
 }  // namespace pdmpflux

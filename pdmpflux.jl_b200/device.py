@@ -24,11 +24,11 @@ def _dev_ptr(a):
 def device_history_view(n_cols, **buffers):
     """Build a `pdmpflux_history` over device buffers (torch tensors or integer device pointers).  Keyword names
     are the PDMPHistory fields; omitted fields are not stored."""
-    unknown = set(buffers) - set(_FIELDS)
+    unknown = set(buffers) - set(_FIELDS) - {"is_active"}
     if unknown:
         raise _lib.ArgumentError(f"unknown history fields: {sorted(unknown)}")
     ptrs = [_dev_ptr(buffers.get(f)) for f in _FIELDS]
-    return _lib.History(*ptrs, None, None, None, int(n_cols), 1)
+    return _lib.History(*ptrs, None, None, None, int(n_cols), 1, _dev_ptr(buffers.get("is_active")))
 
 
 class DeviceChains:

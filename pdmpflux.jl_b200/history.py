@@ -10,14 +10,15 @@ class PDMPHistory:
     hitting_horizon int32 (n,), is_active (d, n) all True.  `.x` / `.v` give lists of column copies
     (Composites.jl:225-234)."""
 
-    def __init__(self, X, V, t, horizon, ar, errored_bound, error_value_ar, rejected, hitting_horizon):
+    def __init__(self, X, V, t, horizon, ar, errored_bound, error_value_ar, rejected, hitting_horizon, is_active=None):
         self.X, self.V, self.t, self.horizon, self.ar = X, V, t, horizon, ar
         self.errored_bound, self.error_value_ar = errored_bound, error_value_ar
         self.rejected, self.hitting_horizon = rejected, hitting_horizon
+        self._is_active = is_active   # (d, n) bool, only stored by the sticky samplers
 
     @property
     def is_active(self):
-        return np.ones(self.X.shape, dtype=bool)
+        return np.ones(self.X.shape, dtype=bool) if self._is_active is None else self._is_active
 
     @property
     def x(self):
@@ -34,8 +35,9 @@ class PDMPHistory:
 class PDMPHistoryBatch:
     """C chains, chain-major: X[c] is chain c's (n_sk, d) slab, i.e. the memory of a Julia Matrix(d, n_sk)."""
 
-    def __init__(self, n_chains, n_sk, d, alloc=np.empty):
+    def __init__(self, n_chains, n_sk, d, alloc=np.empty, sticky=False):
         self.n_chains, self.n_sk, self.d = n_chains, n_sk, d
+        self.is_active = alloc((n_chains, n_sk, d), dtype=np.uint8) if sticky else None
         self.X = alloc((n_chains, n_sk, d), dtype=np.float64)
         self.V = alloc((n_chains, n_sk, d), dtype=np.float64)
         self.t = alloc((n_chains, n_sk), dtype=np.float64)
@@ -51,7 +53,8 @@ class PDMPHistoryBatch:
 
     def chain(self, c=0) -> PDMPHistory:
         return PDMPHistory(self.X[c].T, self.V[c].T, self.t[c], self.horizon[c], self.ar[c], self.errored_bound[c],
-                           self.error_value_ar[c].T, self.rejected[c], self.hitting_horizon[c])
+                           self.error_value_ar[c].T, self.rejected[c], self.hitting_horizon[c],
+                           None if self.is_active is None else self.is_active[c].T.astype(bool))
 
     def __len__(self):
         return self.n_chains

@@ -68,10 +68,10 @@ def sample_skeleton(sampler: AbstractPDMP, n_sk, xinit, vinit, *, seed=None, ver
     n_chains = x.shape[0]
     if seed is None:
         seed = int.from_bytes(os.urandom(8), "little")
-    hb = PDMPHistoryBatch(n_chains, int(n_sk), sampler.dim)
+    hb = PDMPHistoryBatch(n_chains, int(n_sk), sampler.dim, sticky=getattr(sampler, "kappa", None) is not None)
     view = _lib.History(_ptr(hb.X), _ptr(hb.V), _ptr(hb.t), _ptr(hb.horizon), _ptr(hb.ar), _ptr(hb.error_value_ar),
                         _ptr(hb.errored_bound), _ptr(hb.rejected), _ptr(hb.hitting_horizon), _ptr(hb.status),
-                        _ptr(hb.tape_pos), _ptr(hb.counters), int(n_sk), 0)
+                        _ptr(hb.tape_pos), _ptr(hb.counters), int(n_sk), 0, _ptr(hb.is_active))
     t, keep = _make_tape(tape, n_chains)
     t0a = None if t0 is None else np.ascontiguousarray(np.broadcast_to(t0, (n_chains,)), dtype=np.float64)
     h0a = None if horizon0 is None else np.ascontiguousarray(np.broadcast_to(horizon0, (n_chains,)), dtype=np.float64)
@@ -94,6 +94,8 @@ def sample_skeleton_until(sampler: AbstractPDMP, T, xinit, vinit, *, seed=None, 
     T = float(T)
     if not math.isfinite(T) or T < 0:
         raise _lib.ArgumentError(f"T must be finite and non-negative. Current value: {T}")
+    if getattr(sampler, "kappa", None) is not None:
+        raise _lib.UnsupportedError("the time-horizon sample_skeleton is not available for StickyZigZag on the device path")
     x, v, batched = _init_arrays(sampler, xinit, vinit)
     if batch is not None:
         batched = batch
@@ -150,6 +152,12 @@ def sample_from_skeleton(sampler: AbstractPDMP, N, history, dt=None, *, discard_
     n_chains, n_sk, d = X.shape
     ld = d if discard_vt else 2 * d + 1
     out = np.empty((n_chains, int(N), ld))
+    if getattr(sampler, "kappa", None) is not None:   # sample_from_skeleton(::StickyPDMP, ...) (src/sample.jl:516-561)
+        act = history.is_active if isinstance(history, PDMPHistoryBatch) else np.ascontiguousarray(history.is_active.T)[None]
+        act = np.ascontiguousarray(act, dtype=np.uint8)
+        _lib.check(_lib.lib().pdmpflux_sample_from_skeleton_sticky(d, n_sk, n_chains, _ptr(X), _ptr(V), _ptr(t), _ptr(act),
+                                                                   int(N), int(bool(discard_vt)), _ptr(out), 0, None))
+        return out if isinstance(history, PDMPHistoryBatch) else out[0].T
     _lib.check(_lib.lib().pdmpflux_sample_from_skeleton(sampler.flow_kind, d, n_sk, n_chains, _ptr(X), _ptr(V), _ptr(t),
                                                         int(N), int(bool(discard_vt)), _ptr(out), 0, None))
     return out if isinstance(history, PDMPHistoryBatch) else out[0].T

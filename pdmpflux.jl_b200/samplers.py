@@ -4,6 +4,7 @@ ZigZag / ZigZagAD          src/Samplers/ZigZagSamplers.jl:58-60, :118-119
 BPS / BPSAD                src/Samplers/BouncyParticleSamplers.jl:21-24, :86-87
 ForwardECMC / ...AD        src/Samplers/ForwardEventChainMonteCarlo.jl:301-303, :367-369
 Boomerang / BoomerangAD    src/Samplers/BoomerangSamplers.jl:21-23, :79-80
+StickyZigZag / ...AD       src/Samplers/StickyZigZagSamplers.jl:60-111, :117-127 (third positional argument: kappa)
 
 The second positional argument is a device potential descriptor (potentials.py) instead of a Julia closure.
 """
@@ -15,7 +16,7 @@ import warnings
 from . import _lib
 from .potentials import Potential
 
-ZIGZAG, BPS_KIND, FECMC, BOOMERANG = 0, 1, 2, 3
+ZIGZAG, BPS_KIND, FECMC, BOOMERANG, STICKY_ZIGZAG = 0, 1, 2, 3, 4
 DERIV_JVP, DERIV_FD = 0, 1
 
 _EXACT_AD = {"ForwardDiff", "Zygote", "ReverseDiff", "Enzyme", "PolyesterForwardDiff"}
@@ -57,7 +58,11 @@ class AbstractPDMP:
         self._pot_handle = potential._create(dim)
         h = C.c_void_p()
         try:
-            _lib.check(_lib.lib().pdmpflux_sampler_create(self._kind, dim, self._pot_handle, C.byref(cfg), C.byref(h)))
+            if self._kind == STICKY_ZIGZAG:
+                _lib.check(_lib.lib().pdmpflux_sampler_create_sticky(dim, self._pot_handle, C.byref(cfg),
+                                                                      self.kappa.ctypes.data, C.byref(h)))
+            else:
+                _lib.check(_lib.lib().pdmpflux_sampler_create(self._kind, dim, self._pot_handle, C.byref(cfg), C.byref(h)))
         except Exception:
             _lib.lib().pdmpflux_potential_destroy(self._pot_handle)
             self._pot_handle = None
@@ -156,3 +161,27 @@ def BoomerangAD(dim, potential, *, refresh_rate=0.0, grid_size=10, tmax=2.0, vec
                 adaptive=True, AD_backend="ForwardDiff", max_steps=0):
     return Boomerang(dim, potential, refresh_rate=refresh_rate, grid_size=grid_size, tmax=tmax,
                      signed_bound=signed_bound, adaptive=adaptive, AD_backend=AD_backend, max_steps=max_steps)
+
+
+class StickyZigZag(ZigZag):
+    """StickyZigZag(dim, grad U, kappa; kw...) (StickyZigZagSamplers.jl:60-111): the Zig-Zag closures plus thawing rates
+    `kappa` (prior inclusion); coordinates stick to their axis when they cross it and thaw at rate kappa_i
+    (src/StickySamplingLoop.jl)."""
+    _kind = STICKY_ZIGZAG
+
+    def __init__(self, dim, potential, kappa, *, refresh_rate=0.0, grid_size=10, tmax=2.0, vectorized_bound=True,
+                 signed_bound=True, adaptive=True, AD_backend="FiniteDiff", max_steps=0):
+        import numpy as np
+        self.kappa = np.ascontiguousarray(kappa, dtype=np.float64)
+        if self.kappa.shape != (int(dim),):
+            raise _lib.DimensionMismatch(f"kappa must have length dim ({dim}). Current length: {self.kappa.size}")
+        super().__init__(dim, potential, grid_size=grid_size, tmax=tmax, refresh_rate=refresh_rate,
+                         vectorized_bound=vectorized_bound, signed_bound=signed_bound, adaptive=adaptive,
+                         AD_backend=AD_backend, max_steps=max_steps)
+
+
+def StickyZigZagAD(dim, potential, kappa, *, refresh_rate=0.0, grid_size=10, tmax=2.0, vectorized_bound=True,
+                   signed_bound=True, adaptive=True, AD_backend="ForwardDiff", max_steps=0):
+    return StickyZigZag(dim, potential, kappa, refresh_rate=refresh_rate, grid_size=grid_size, tmax=tmax,
+                        vectorized_bound=vectorized_bound, signed_bound=signed_bound, adaptive=adaptive,
+                        AD_backend=AD_backend, max_steps=max_steps)

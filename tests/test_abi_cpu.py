@@ -26,14 +26,14 @@ def test_header_and_binding_agree(p):
     l = C.CDLL(p.LIB_PATH)
     for name in declared:
         assert hasattr(l, name), name
-    assert p.lib().pdmpflux_version() == 100
+    assert p.lib().pdmpflux_version() == 200
 
 
 def test_struct_layouts_match_header(p):
     from pdmpflux_b200 import _lib
     assert C.sizeof(_lib.Config) == 10 * 4 + 4 * 8
     assert C.sizeof(_lib.Tape) == 3 * 8 + 3 * 8 + 8
-    assert C.sizeof(_lib.History) == 12 * 8 + 8 + 8
+    assert C.sizeof(_lib.History) == 12 * 8 + 8 + 8 + 8   # is_active appended in 0.2.0
 
 
 def test_constructor_validation_and_rewrites(p):
