@@ -467,6 +467,8 @@ def main():
             os.environ["PDMPFLUX_VBITS"] = "1"
             dist.barrier()
         res = e2e(p, sampler, name, nch, n_ev, world, dev)
+        if world > 1:
+            dist.barrier()    # the two modes are measured one after the other on ALL ranks (they share the host)
         mom = e2e_moments(p, sampler, name, nch, n_ev, dev)
         if world > 1:
             worst = torch.tensor([res["ms_per_step"], mom["ms_per_step"] or 0.0], dtype=f64, device=dev)
@@ -625,6 +627,7 @@ def e2e(p, sampler, name, nch, n_ev, world, dev):
     times.sort()
     dt = times[len(times) // 2]
     ok = bool(np.isfinite(arrs["t"][:, -1]).all())
+    arrs.clear()                             # views of the pinned buffers freed next
     for ptr in ptrs:
         lib.pdmpflux_host_free(ptr)
     lib.pdmpflux_sampler_release_workspace(sampler._handle)
@@ -676,11 +679,13 @@ def e2e_moments(p, sampler, name, nch, n_ev, dev):
         t0 = time.perf_counter(); call(7 + i); times.append(time.perf_counter() - t0)
     times.sort()
     dt = times[len(times) // 2]
+    finite = bool(np.isfinite(sums_h).all())
+    del sums_h, x0, v0                       # views of the pinned buffers freed next
     for ptr in (px, pv, ps):
         lib.pdmpflux_host_free(ptr)
     return {"value": nch * n_ev / dt, "unit": "events/s", "h2d_bytes_per_step": 2 * 8 * d * nch, "d2h_bytes_per_step": 4 * 8 * d,
             "ms_per_step": dt * 1e3, "ms_mean": 1e3 * sum(times) / reps, "ms_max": times[-1] * 1e3,
-            "finite": bool(np.isfinite(sums_h).all()), "timing": "median of %d individually timed calls" % reps,
+            "finite": finite, "timing": "median of %d individually timed calls" % reps,
             "call": "pdmpflux_chains_create + enable_moments + chains_advance(NULL history) + moments_reduce, host (pinned) initial states in, 4 x d moment sums out"}
 
 

@@ -117,8 +117,12 @@ int pdmpflux_moments_reduce(int dim, int64_t n_chains, const double* m1, const d
     const int n_split = (int)std::min<int64_t>(kMaxSplit, (n_chains + 255) / 256);
     const size_t nd = sizeof(double) * (size_t)dim * n_chains;
     double *d1 = nullptr, *d2 = nullptr, *dT = nullptr, *dS = nullptr, *part = nullptr;
+    // Partial sums (<= 3 MB): a grow-only device buffer cached per host thread and device, so the per-step call issues
+    // no allocation at all (a stream-ordered allocation here costs a pool round trip every step).  Calls made by one
+    // host thread on the same device must therefore be issued on one stream at a time.
+    struct Scratch { double* p = nullptr; size_t bytes = 0; int dev = -1; };
+    thread_local Scratch scratch;
     auto cleanup = [&] {
-        if (part) cudaFreeAsync(part, stream);
         if (!on_device) { if (d1) cudaFreeAsync(d1, stream); if (d2) cudaFreeAsync(d2, stream); if (dT) cudaFreeAsync(dT, stream); if (dS) cudaFreeAsync(dS, stream); }
     };
 #define TRY_(expr)                                                                                                   \
@@ -126,7 +130,18 @@ int pdmpflux_moments_reduce(int dim, int64_t n_chains, const double* m1, const d
         cudaError_t e_ = (expr);                                                                                     \
         if (e_ != cudaSuccess) { cleanup(); return pdmpflux_fail_(PDMPFLUX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } \
     } while (0)
-    TRY_(cudaMallocAsync(&part, sizeof(double) * 3 * (size_t)dim * n_split, stream));
+    {
+        int dev = 0;
+        TRY_(cudaGetDevice(&dev));
+        const size_t need = sizeof(double) * 3 * (size_t)dim * n_split;
+        if (scratch.dev != dev || scratch.bytes < need) {
+            if (scratch.p && scratch.dev == dev) cudaFree(scratch.p);   // (a buffer of another device is left to its context)
+            scratch = Scratch{};
+            TRY_(cudaMalloc(reinterpret_cast<void**>(&scratch.p), need));
+            scratch.bytes = need; scratch.dev = dev;
+        }
+        part = scratch.p;
+    }
     const double *p1 = m1, *p2 = m2, *pT = T;
     double* pS = sums;
     if (!on_device) {
