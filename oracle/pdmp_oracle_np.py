@@ -845,6 +845,75 @@ def rv_diagnostic(X, V, t, U, B=0):
 # masked-velocity variants of the thinning steps (src/SamplingLoopInplace.jl:13-25, 87-217) and the
 # StickyZigZag closures (src/Samplers/StickyZigZagSamplers.jl:69-101, identical to Zig-Zag's).  Oracle only so
 # far: the CUDA path for it is the next row of the scope table.
+
+# --------------------------------------------------------------------------------------------
+# Speed-Up Zig-Zag (src/Samplers/SpeedUpZigZagSamplers.jl:35-130): Zig-Zag with the position-dependent speed
+# s(x) = sqrt(1 + |x|^2), i.e. the closed-form nonlinear flow of :71-79 and the effective gradient
+# grad U_eff = s grad U - grad s (:81-83).  Everything else (bounds, thinning loop, categorical flip) is the generic
+# machinery with these closures.  The reference obtains d/dt of the rate by ForwardDiff through the flow; here it is
+# taken by complex-step differentiation of the very same expressions (exact to rounding for analytic functions), so
+# that the oracle's derivative is independent of the hand-derived formulas of the device code.
+# --------------------------------------------------------------------------------------------
+class SpeedUpSampler(Sampler):
+    def __init__(self, dim, pot, cfg: Config):
+        super().__init__(dim, pot, cfg)
+        if self.kind != ZIGZAG:
+            raise ValueError("SpeedUpSampler restates SpeedUpZigZag only")
+
+    def flow(self, x, v, t):  # SpeedUpZigZagSamplers.jl:71-79 (literal)
+        d = self.dim
+        y = x - v[0] * x[0] * v
+        c = v[0] * np.dot(y, v)
+        a = (1 + np.dot(y, y)) / d - (c ** 2) / (d ** 2)
+        Y_0 = x[0] + (c / d)
+        b_t = (Y_0 + np.sqrt(Y_0 ** 2 + a)) * np.exp(math.sqrt(d) * v[0] * t)
+        X_1 = (b_t ** 2 - a) / (2 * b_t) - (c / d)
+        return y + v[0] * X_1 * v, v
+
+    def grad_eff(self, x):  # :81-83
+        speed = np.sqrt(1.0 + np.dot(x, x))
+        return speed * self.pot.grad(x) - x / speed
+
+    def rate(self, x0, v0, t):  # :86-89
+        xt, vt = self.flow(x0, v0, t)
+        return float(np.sum(np.maximum(0.0, self.grad_eff(xt) * vt)))
+
+    def _signed_vect_complex(self, x0, v0, t):
+        h = 1e-30
+        xt, vt = self.flow(x0.astype(complex), v0.astype(complex), complex(t, h))
+        y = self.grad_eff(xt) * vt
+        return y.real.copy(), y.imag / h
+
+    def bound_func_vect(self, x0, v0, t, signed):  # :91-99 + d/dt
+        y, dy = self._signed_vect_complex(x0, v0, t)
+        if signed:
+            return y, dy
+        mask = ~(0.0 > y)
+        return np.maximum(0.0, y), np.where(mask, dy, 0.0)
+
+    def bound_func_scalar(self, x0, v0, t, signed):  # vectorized_bound = false: the scalar unsigned rate
+        y, dy = self._signed_vect_complex(x0, v0, t)
+        mask = ~(0.0 > y)
+        return float(np.sum(np.maximum(0.0, y))), float(np.sum(np.where(mask, dy, 0.0)))
+
+    def velocity_jump(self, x, v, tape: Tape):  # :102-108
+        lam = np.maximum(0.0, self.grad_eff(x) * v)
+        p = lam / np.sum(lam)
+        sp = float(np.sum(p))
+        if not (np.all(p >= 0.0) and abs(sp - 1.0) <= SQRT_EPS * max(abs(sp), 1.0)):
+            raise FloatingPointError("SpeedUpZigZag jump: rate vector is not a probability vector")
+        u = tape.rand()
+        n = len(p)
+        cp = p[0]
+        i = 0
+        while cp <= u and i < n - 1:
+            i += 1
+            cp += p[i]
+        v = v.copy()
+        v[i] *= -1
+        return v
+
+
 # --------------------------------------------------------------------------------------------
 class StickyHistory(History):
     """PDMPHistory with the is_active BitMatrix that record! stores (Composites.jl:239-260)."""

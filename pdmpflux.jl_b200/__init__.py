@@ -13,12 +13,12 @@ from .history import PDMPHistory, PDMPHistoryBatch
 from .potentials import (Banana, BananaReadmeScalar, GaussDiag, GaussEquicorr, GaussStd, LogReg, Potential)
 from .sample import (RV_diagnostic, ess_from_chain_means, sample, sample_from_skeleton, sample_skeleton,
                      sample_skeleton_until, sample_skeleton_with_diagnostic, skeleton_moments)
-from .samplers import (BPS, BPSAD, AbstractPDMP, Boomerang, BoomerangAD, ForwardECMC, ForwardECMCAD, StickyZigZag,
-                       StickyZigZagAD, ZigZag, ZigZagAD)
+from .samplers import (BPS, BPSAD, AbstractPDMP, Boomerang, BoomerangAD, ForwardECMC, ForwardECMCAD, SpeedUpZigZag,
+                       SpeedUpZigZagAD, StickyZigZag, StickyZigZagAD, ZigZag, ZigZagAD)
 
 __all__ = [
     "ZigZag", "ZigZagAD", "BPS", "BPSAD", "ForwardECMC", "ForwardECMCAD", "Boomerang", "BoomerangAD", "StickyZigZag",
-    "StickyZigZagAD",
+    "StickyZigZagAD", "SpeedUpZigZag", "SpeedUpZigZagAD",
     "AbstractPDMP", "sample", "sample_skeleton", "RV_diagnostic", "sample_skeleton_with_diagnostic", "sample_skeleton_until", "CapacityError", "sample_from_skeleton", "skeleton_moments",
     "ess_from_chain_means", "PDMPHistory", "PDMPHistoryBatch", "Potential", "GaussStd", "GaussDiag",
     "GaussEquicorr", "Banana", "BananaReadmeScalar", "LogReg", "ArgumentError", "DimensionMismatch",

@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpdmpflux_cuda.so")
+# PDMPFLUX_CUDA_LIB points at another build of the same library (A/B experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("PDMPFLUX_CUDA_LIB") or os.path.join(_HERE, "lib", "libpdmpflux_cuda.so")
 
 OK, ERR_ARGUMENT, ERR_DIMENSION_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR_CHAIN, ERR_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 

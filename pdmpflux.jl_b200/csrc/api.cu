@@ -116,6 +116,7 @@ struct pdmpflux_chains_s {
     int team = 32, n_own = 0, scratch_in_smem = 1, path = 0, vec_elems = 0, dpad = 0;
     size_t smem = 0;
     unsigned grid = 0;
+    int64_t n_groups = 0;   // groups of chains (one block's worth); grid < n_groups: persistent blocks walk over the groups
     DevBuf x, v, t, horizon, ar, tape_pos, status, counters, scratch, ncols, m1, m2, wq, act;
     int moments = 0;
     double t_stop = 0.0;
@@ -172,6 +173,7 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     p.inv_gm1 = c.grid_size > 1 ? 1.0 / (double)(c.grid_size - 1) : 0.0;
     p.pot = s->pot->pp;
     p.n_chains = ch->n_chains; p.chain_offset = ch->chain_offset; p.seed = ch->seed;
+    p.n_groups = ch->n_groups;
     p.event0 = ch->event0; p.n_events = n_events;
     p.sx = ch->x.as<double>(); p.sv = ch->v.as<double>(); p.st = ch->t.as<double>();
     p.shorizon = ch->horizon.as<double>(); p.sar = ch->ar.as<double>();
@@ -542,6 +544,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     ch->n_own = (d + ch->team - 1) / ch->team;
     const int cpb = kBlockThreads / ch->team;
     ch->grid = (unsigned)((n_chains + cpb - 1) / cpb);
+    ch->n_groups = ch->grid;
     if (ch->team == 1) { ch->dpad = 0; ch->vec_elems = ch->n_own * kBlockThreads; }
     else {
         ch->dpad = (ch->n_own * ch->team + 7) / 8 * 8;                  // 64-byte aligned chain slots (TMA source)
@@ -555,7 +558,14 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     if (s->kind == PDMPFLUX_FECMC) {
         if ((nvec + 3) * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = (nvec + 3) * vec_bytes; }
         else {
+            // Scratch vectors in global memory: run a persistent grid (one block per resident slot: the kernel is built
+            // for 3 blocks of a warp-per-chain team per SM) so that the scratch is indexed by the resident block, fits
+            // the L2 (a few tens of MB) and is rewritten in place.
             ch->scratch_in_smem = 0;
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+            ch->grid = (unsigned)std::min<int64_t>(ch->n_groups, (int64_t)3 * n_sm);
             CUDA_TRY(ch->scratch.alloc((size_t)ch->grid * 3 * vec_bytes));
         }
     }

@@ -715,9 +715,13 @@ struct Chain {
         if constexpr (kFast && !kZZ) {  // O(1) nodes from the line model
             // value and d/dt of the bound function at node time tt: analytic, or the reference's
             // finite_difference_derivative (UpperBound.jl:50-76) applied to the closed-form value
-            auto node = [&](double tt, double& val, double& dval) {
-                double y, dy, s0 = 0.0, c0 = 1.0;
-                if constexpr (kRot) { sincos(tt, &s0, &c0); line_scalar_sc(s0, c0, y, dy); }
+            // (rotation flow: s0 = sin tt, c0 = cos tt are supplied by the caller -- the nodes are equally spaced, so they
+            // follow from sin / cos of the grid step by the angle-addition recurrence: ONE sincos per bound instead of one
+            // per node.  The recurrence error (~k ulp) is common to a node's value and to its finite-difference stencil,
+            // which is built from the same (s0, c0), so it is not amplified by 1 / h.)
+            auto node = [&](double tt, double s0, double c0, double& val, double& dval) {
+                double y, dy;
+                if constexpr (kRot) line_scalar_sc(s0, c0, y, dy);
                 else line_scalar(tt, y, dy);
                 finish_scalar(y, dy, val, dval);
                 if (p.deriv_mode != PDMPFLUX_DERIV_JVP) {
@@ -761,10 +765,17 @@ struct Chain {
                     return;
                 }
             }
-            node(0.0, vl, gl);
+            double s1 = 0.0, c1 = 1.0, sk = 0.0, ck = 1.0;
+            if constexpr (kRot) sincos(step, &s1, &c1);
+            node(0.0, sk, ck, vl, gl);
             for (int k = 0; k < G - 1; ++k) {
                 double vr, gr;
-                node(grid_t(k + 1), vr, gr);
+                if constexpr (kRot) {
+                    const double sn = sk * c1 + ck * s1;
+                    ck = ck * c1 - sk * s1;
+                    sk = sn;
+                }
+                node(grid_t(k + 1), sk, ck, vr, gr);
                 const double b = scalar_cell(vl, gl, vr, gr);
                 BOX(k) = b;
                 cs += b;
@@ -1813,7 +1824,15 @@ template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
 __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PATH == kPathFastBrent ? 2 : (TEAM == 32 ? 3 : PDMPFLUX_MINBLOCKS_GRID))) skeleton_kernel(const __grid_constant__ KernelParams p) {
     constexpr int CPB = kBlockThreads / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
-    const int64_t c_raw = (int64_t)blockIdx.x * CPB + c_local;
+    // A block normally owns one group of CPB chains (grid = number of groups).  With p.n_groups > gridDim.x the grid is
+    // persistent (one block per resident slot) and walks over the groups: the per-block scratch vectors in global
+    // memory are then indexed by the resident block, stay in the L2 and are rewritten in place instead of being
+    // flushed to DRAM behind the history rows (ForwardECMC at large d).
+    // (only the warp-per-chain kernels are ever launched that way; for the others the loop is compiled away)
+    constexpr bool kPersistent = (TEAM == 32);
+    int64_t grp = blockIdx.x;
+    do {
+    const int64_t c_raw = grp * CPB + c_local;
     const bool valid = c_raw < p.n_chains;  // out-of-range lanes stay (warp-wide votes) but never touch memory
     const int64_t c = valid ? c_raw : 0;
 
@@ -1905,12 +1924,12 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
             ch.finish_output(c, 1);
             if (ch.tl == 0) p.ncols[c] += 1;
         }
-        return;
+        continue;
     }
     int64_t n_rec;
     if constexpr (SAMPLER == PDMPFLUX_STICKY_ZIGZAG) n_rec = ch.run_events_sticky(c, valid);
     else n_rec = ch.run_events(c, valid);
-    if (!valid) return;
+    if (!valid) continue;   // (only whole teams are invalid, and only in the last group)
     if constexpr (SAMPLER == PDMPFLUX_STICKY_ZIGZAG)
         ch.for_owned([&](int j) { p.sact[c * p.d + ch.coord(j)] = g_smem[ch.off_ac + j * ch.kStr] != 0.0 ? 1 : 0; });
     ch.finish_output(c, n_rec);
@@ -1936,6 +1955,7 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
         p.tape_pos[3 * c] = ch.pE; p.tape_pos[3 * c + 1] = ch.pU; p.tape_pos[3 * c + 2] = ch.pN;
         p.ncols[c] += n_rec;
     }
+    } while (kPersistent && (grp += gridDim.x) < p.n_groups);
 }
 
 }  // namespace pdmpflux

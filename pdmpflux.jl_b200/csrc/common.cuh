@@ -33,6 +33,7 @@ struct KernelParams {
     PotParams pot;
     // chains
     int64_t n_chains, chain_offset;
+    int64_t n_groups;  // groups of (kBlockThreads / TEAM) chains; > gridDim.x for a persistent grid
     uint64_t seed;
     int64_t event0;    // events already generated per chain (the next event has index event0+1)
     int64_t n_events;  // events to generate in this launch
@@ -89,9 +90,15 @@ __device__ __forceinline__ void st256(double* g, double a, double b, double c, d
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(g), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 // TMA bulk copy shared -> global (SASS: UBLKCP.G.S); size and both addresses are multiples of 16 bytes
+// History rows are written once and never read by the kernel: the L2 evict-first policy keeps them from displacing the
+// per-block scratch vectors (and the chains' state) that live in the L2.
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s), "r"(bytes),
+                 "l"(policy)
+                 : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

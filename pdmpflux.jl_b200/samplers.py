@@ -5,6 +5,7 @@ BPS / BPSAD                src/Samplers/BouncyParticleSamplers.jl:21-24, :86-87
 ForwardECMC / ...AD        src/Samplers/ForwardEventChainMonteCarlo.jl:301-303, :367-369
 Boomerang / BoomerangAD    src/Samplers/BoomerangSamplers.jl:21-23, :79-80
 StickyZigZag / ...AD       src/Samplers/StickyZigZagSamplers.jl:60-111, :117-127 (third positional argument: kappa)
+SpeedUpZigZag / ...AD      src/Samplers/SpeedUpZigZagSamplers.jl:58-116, :119-129
 
 The second positional argument is a device potential descriptor (potentials.py) instead of a Julia closure.
 """
@@ -16,7 +17,7 @@ import warnings
 from . import _lib
 from .potentials import Potential
 
-ZIGZAG, BPS_KIND, FECMC, BOOMERANG, STICKY_ZIGZAG = 0, 1, 2, 3, 4
+ZIGZAG, BPS_KIND, FECMC, BOOMERANG, STICKY_ZIGZAG, SPEEDUP_ZIGZAG = 0, 1, 2, 3, 4, 5
 DERIV_JVP, DERIV_FD = 0, 1
 
 _EXACT_AD = {"ForwardDiff", "Zygote", "ReverseDiff", "Enzyme", "PolyesterForwardDiff"}
@@ -185,3 +186,25 @@ def StickyZigZagAD(dim, potential, kappa, *, refresh_rate=0.0, grid_size=10, tma
     return StickyZigZag(dim, potential, kappa, refresh_rate=refresh_rate, grid_size=grid_size, tmax=tmax,
                         vectorized_bound=vectorized_bound, signed_bound=signed_bound, adaptive=adaptive,
                         AD_backend=AD_backend, max_steps=max_steps)
+
+
+class SpeedUpZigZag(AbstractPDMP):
+    """SpeedUpZigZag(dim, grad U; kw...) (SpeedUpZigZagSamplers.jl:58-116): Zig-Zag with the position-dependent speed
+    sqrt(1 + |x|^2) -- the closed-form nonlinear flow of :71-79 and the effective gradient of :81-83."""
+    _kind = SPEEDUP_ZIGZAG
+    flow_kind = 2
+
+    def __init__(self, dim, potential, *, grid_size=10, tmax=2.0, refresh_rate=0.0, vectorized_bound=True,
+                 signed_bound=True, adaptive=True, AD_backend="FiniteDiff", max_steps=0):
+        if signed_bound and not vectorized_bound:
+            warnings.warn("Signed bound is not compatible with non-vectorized bound for ZigZag, switching to unsigned bound")
+        super().__init__(dim, potential, grid_size=grid_size, tmax=tmax, refresh_rate=refresh_rate,
+                         vectorized_bound=vectorized_bound, signed_bound=signed_bound, adaptive=adaptive,
+                         AD_backend=AD_backend, max_steps=max_steps)
+
+
+def SpeedUpZigZagAD(dim, potential, *, refresh_rate=0.0, grid_size=10, tmax=2.0, vectorized_bound=True, signed_bound=True,
+                    adaptive=True, AD_backend="ForwardDiff", max_steps=0):
+    return SpeedUpZigZag(dim, potential, refresh_rate=refresh_rate, grid_size=grid_size, tmax=tmax,
+                         vectorized_bound=vectorized_bound, signed_bound=signed_bound, adaptive=adaptive,
+                         AD_backend=AD_backend, max_steps=max_steps)
