@@ -40,8 +40,10 @@ typedef enum pdmpflux_error {
 /* src/Samplers/{ZigZagSamplers,BouncyParticleSamplers,ForwardEventChainMonteCarlo,BoomerangSamplers}.jl */
 typedef enum pdmpflux_sampler_kind {
     PDMPFLUX_ZIGZAG = 0, PDMPFLUX_BPS = 1, PDMPFLUX_FECMC = 2, PDMPFLUX_BOOMERANG = 3,
-    PDMPFLUX_STICKY_ZIGZAG = 4 /* src/Samplers/StickyZigZagSamplers.jl + src/StickySamplingLoop.jl; create it with
-                                  pdmpflux_sampler_create_sticky (it needs the thawing rates kappa) */
+    PDMPFLUX_STICKY_ZIGZAG = 4, /* src/Samplers/StickyZigZagSamplers.jl + src/StickySamplingLoop.jl; create it with
+                                   pdmpflux_sampler_create_sticky (it needs the thawing rates kappa) */
+    PDMPFLUX_SPEEDUP_ZIGZAG = 5 /* src/Samplers/SpeedUpZigZagSamplers.jl: Zig-Zag with speed sqrt(1 + |x|^2) (closed-form
+                                   nonlinear flow :71-79, effective gradient :81-83); generic path, no fused moments */
 } pdmpflux_sampler_kind;
 
 /* Device potential plugins (replace the Julia closure `grad U`).  params layout:
@@ -222,7 +224,8 @@ int pdmpflux_chains_status(pdmpflux_chains_t ch, int32_t* status, int64_t* tape_
 int pdmpflux_chains_destroy(pdmpflux_chains_t ch);
 
 /* replaces sample_from_skeleton(sampler, N, history; discard_vt) (src/sample.jl:475-513), per chain:
- * out is [C][N][d] (or [C][N][2d+1]); flow_kind 0 = linear (ZigZag/BPS/FECMC), 1 = rotation (Boomerang). */
+ * out is [C][N][d] (or [C][N][2d+1]); flow_kind 0 = linear (ZigZag/BPS/FECMC), 1 = rotation (Boomerang),
+ * 2 = the Speed-Up Zig-Zag flow (SpeedUpZigZagSamplers.jl:71-79). */
 int pdmpflux_sample_from_skeleton(int flow_kind, int dim, int64_t n_sk, int64_t n_chains, const double* X,
                                   const double* V, const double* t, int64_t N, int32_t discard_vt, double* out,
                                   int32_t on_device, void* cuda_stream);

@@ -245,6 +245,7 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     case PDMPFLUX_FECMC: e = launch_skeleton_fecmc(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
     case PDMPFLUX_BOOMERANG: e = launch_skeleton_boomerang(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
     case PDMPFLUX_STICKY_ZIGZAG: e = launch_skeleton_sticky(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
+    case PDMPFLUX_SPEEDUP_ZIGZAG: e = launch_skeleton_speedup(ch->team, s->pot->kind, ch->path, p, ch->grid, smem_launch, stream); break;
     default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(PDMPFLUX_ERR_CUDA, std::string("skeleton kernel launch: ") + cudaGetErrorString(e));
@@ -291,7 +292,8 @@ __global__ void __launch_bounds__(256) pack_signs_kernel(const double* __restric
 __global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64_t n_sk, int64_t ld_sk, int64_t N,
                                                      int discard_vt, double dt_fixed, const double* __restrict__ X,
                                                      const double* __restrict__ V, const double* __restrict__ T,
-                                                     const uint8_t* __restrict__ act, double* __restrict__ out) {
+                                                     const uint8_t* __restrict__ act, const double* __restrict__ su,
+                                                     double* __restrict__ out) {
     const int64_t c = blockIdx.x;  // chains on grid.x (up to 2^31 - 1), output elements grid-strided over grid.y
     const double* t = T + c * ld_sk;
     const double dt = dt_fixed > 0.0 ? dt_fixed : t[n_sk - 1] / (double)N;
@@ -320,10 +322,36 @@ __global__ void __launch_bounds__(256) interp_kernel(int flow_kind, int d, int64
                 double s, co;
                 sincos(tau, &s, &co);
                 r = a < d ? xi * co + vi * s : -xi * s + vi * co;
+            } else if (flow_kind == 2) {  // SpeedUpZigZagSamplers.jl:71-79 from the segment scalars (speedup_scalars_kernel)
+                const double* sc = su + (c * ld_sk + lo) * 4;   // <y,y>, <y,v>, v1 x1, v1
+                const double dd = (double)d, vx1 = sc[2], v1 = sc[3], cc = v1 * sc[1];
+                const double aa = (1 + sc[0]) / dd - (cc * cc) / (dd * dd), Y0 = v1 * vx1 + cc / dd;   // x1 = v1 (v1 x1)
+                const double bt = (Y0 + sqrt(Y0 * Y0 + aa)) * exp(sqrt(dd) * v1 * tau);
+                const double X1 = (bt * bt - aa) / (2 * bt) - cc / dd;
+                r = a < d ? (xi - vx1 * vi) + v1 * X1 * vi : vi;
             } else r = a < d ? xi + vi * tau : vi;
         }
         out[(c * N + j) * ld + a] = r;
     }
+}
+
+// Speed-Up Zig-Zag: the four scalars of a skeleton point that fix its flow (y = x - v1 x1 v): <y,y>, <y,v>, v1 x1, v1.
+// One warp per (chain, column).
+__global__ void __launch_bounds__(256) speedup_scalars_kernel(int d, int64_t n_rows, const double* __restrict__ X,
+                                                              const double* __restrict__ V, double* __restrict__ su) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const double* x = X + r * d;
+    const double* v = V + r * d;
+    const double v1 = v[0], vx1 = v[0] * x[0];
+    double yy = 0.0, yv = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double y = x[i] - vx1 * v[i];
+        yy += y * y; yv += y * v[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) { yy += __shfl_xor_sync(0xffffffffu, yy, o); yv += __shfl_xor_sync(0xffffffffu, yv, o); }
+    if (lane == 0) { su[r * 4] = yy; su[r * 4 + 1] = yv; su[r * 4 + 2] = vx1; su[r * 4 + 3] = v1; }
 }
 
 // Closed-form time integrals of x_i and x_i^2 along each chain's piecewise flow (feeds moments / ESS).
@@ -361,7 +389,7 @@ int normalise_config(int kind, int dim, pdmpflux_config& c) {
     // constructor rewrites: ZigZagSamplers.jl:73-78, BouncyParticleSamplers.jl:29-37,
     // ForwardEventChainMonteCarlo.jl:306-323, BoomerangSamplers.jl:27-36
     if (c.tmax == 0.0) { c.tmax = 1.0; c.adaptive = 1; }
-    if (kind == PDMPFLUX_ZIGZAG || kind == PDMPFLUX_STICKY_ZIGZAG) {
+    if (kind == PDMPFLUX_ZIGZAG || kind == PDMPFLUX_STICKY_ZIGZAG || kind == PDMPFLUX_SPEEDUP_ZIGZAG) {
         if (c.signed_bound && !c.vectorized_bound) c.signed_bound = 0;
     } else c.vectorized_bound = 0;
     if (kind == PDMPFLUX_FECMC) {
@@ -472,7 +500,7 @@ static int sampler_create_impl(int kind, int dim, pdmpflux_potential_t pot, cons
     if (!out) return fail(PDMPFLUX_ERR_ARGUMENT, "out is NULL");
     *out = nullptr;
     if (!pot || !cfg) return fail(PDMPFLUX_ERR_ARGUMENT, "potential / config is NULL");
-    if (kind < PDMPFLUX_ZIGZAG || kind > PDMPFLUX_STICKY_ZIGZAG)
+    if (kind < PDMPFLUX_ZIGZAG || kind > PDMPFLUX_SPEEDUP_ZIGZAG)
         return fail(PDMPFLUX_ERR_UNSUPPORTED, "sampler kind outside the device path (Sticky/SpeedUp/RHMC are not ported; no CPU fallback)");
     if (dim <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "dimension dim must be positive. Current value: " + std::to_string(dim));
     if (dim != pot->dim) return fail(PDMPFLUX_ERR_DIMENSION_MISMATCH, "potential dim " + std::to_string(pot->dim) + " != sampler dim " + std::to_string(dim));
@@ -668,6 +696,7 @@ int pdmpflux_chains_get_state(pdmpflux_chains_t ch, double* x, double* v, double
 int pdmpflux_chains_enable_moments(pdmpflux_chains_t ch) {
     if (!ch) return fail(PDMPFLUX_ERR_ARGUMENT, "chains is NULL");
     if (ch->s->pot->kind == PDMPFLUX_LOGREG) return fail(PDMPFLUX_ERR_UNSUPPORTED, "fused moments are not available for the logistic-regression kernel");
+    if (ch->s->kind == PDMPFLUX_SPEEDUP_ZIGZAG) return fail(PDMPFLUX_ERR_UNSUPPORTED, "fused moments need closed-form segment integrals: not available for the Speed-Up Zig-Zag flow");
     if (ch->moments) return PDMPFLUX_OK;
     const size_t nd = sizeof(double) * ch->s->dim * ch->n_chains;
     CUDA_TRY(ch->m1.alloc(nd)); CUDA_TRY(ch->m2.alloc(nd));
@@ -1169,10 +1198,10 @@ static int interp_impl(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int6
                        const double* V, const double* t, int64_t N, double dt_fixed, int32_t discard_vt, double* out,
                        int32_t on_device, void* stream_, const uint8_t* act) {
     if (!X || !V || !t || !out || dim <= 0 || n_sk <= 0 || n_chains <= 0) return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
-    if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear) or 1 (rotation)");
+    if (flow_kind < 0 || flow_kind > 2) return fail(PDMPFLUX_ERR_ARGUMENT, "flow_kind must be 0 (linear), 1 (rotation) or 2 (Speed-Up Zig-Zag)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int ld = discard_vt ? dim : 2 * dim + 1;
-    DevBuf dX, dV, dt, dout, dact;
+    DevBuf dX, dV, dt, dout, dact, dsu;
     const double *pX = X, *pV = V, *pt = t;
     const uint8_t* pact = act;
     double* po = out;
@@ -1193,14 +1222,21 @@ static int interp_impl(int flow_kind, int dim, int64_t n_sk, int64_t ld_sk, int6
         pX = dX.as<double>(); pV = dV.as<double>(); pt = dt.as<double>(); po = dout.as<double>();
     }
     const int64_t total = N * (int64_t)ld;
+    if (flow_kind == 2) {
+        const int64_t rows = n_chains * ld_sk;
+        CUDA_TRY(dsu.alloc(sizeof(double) * 4 * (size_t)rows));
+        speedup_scalars_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(dim, rows, pX, pV, dsu.as<double>());
+        CUDA_TRY(cudaGetLastError());
+        g_launches.fetch_add(1);
+    }
     dim3 grid((unsigned)n_chains, (unsigned)std::min<int64_t>((total + 255) / 256, 65535));
-    interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, ld_sk, N, discard_vt, dt_fixed, pX, pV, pt, pact, po);
+    interp_kernel<<<grid, 256, 0, stream>>>(flow_kind, dim, n_sk, ld_sk, N, discard_vt, dt_fixed, pX, pV, pt, pact, dsu.as<double>(), po);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     if (!on_device) {
         CUDA_TRY(cudaMemcpyAsync(out, po, sizeof(double) * ld * N * n_chains, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-    }
+    } else if (flow_kind == 2) CUDA_TRY(cudaStreamSynchronize(stream));  // the segment scalars are freed on return
     return PDMPFLUX_OK;
 }
 
@@ -1209,6 +1245,7 @@ int pdmpflux_skeleton_moments(int flow_kind, int dim, int64_t n_sk, int64_t n_ch
                               int32_t on_device, void* stream_) {
     if (!X || !V || !t || !m1 || !m2 || dim <= 0 || n_sk <= 1 || n_chains <= 0 || col_begin < 0 || col_begin >= n_sk - 1)
         return fail(PDMPFLUX_ERR_ARGUMENT, "invalid argument");
+    if (flow_kind != 0 && flow_kind != 1) return fail(PDMPFLUX_ERR_UNSUPPORTED, "closed-form segment integrals exist for the linear and rotation flows only");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevBuf dX, dV, dt, d1, d2, dT;
     const double *pX = X, *pV = V, *pt = t;

@@ -73,8 +73,10 @@ struct Chain {
     static constexpr int KK = K > 0 ? K : 1;
     static constexpr bool kRot = (SAMPLER == PDMPFLUX_BOOMERANG);
     static constexpr bool kSticky = (SAMPLER == PDMPFLUX_STICKY_ZIGZAG);
-    static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG) || kSticky;   // StickyZigZagSamplers.jl:69-101: same closures
+    static constexpr bool kSpeedUp = (SAMPLER == PDMPFLUX_SPEEDUP_ZIGZAG);
+    static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG) || kSticky || kSpeedUp;   // StickyZigZagSamplers.jl:69-101: same closures
     static_assert(!kSticky || PATH == kPathGeneric, "Sticky Zig-Zag runs on the generic path");
+    static_assert(!kSpeedUp || PATH == kPathGeneric, "Speed-Up Zig-Zag runs on the generic path");
     static constexpr int kStr = (TEAM == 1) ? kBlockThreads : TEAM;  // stride between a thread's owned elements
     static constexpr int kBStr = (TEAM == 1) ? kBlockThreads : 1;    // stride between a chain's box / cum entries
 
@@ -94,6 +96,9 @@ struct Chain {
     double Lx[KK], Lv[KK];  // functionals of the current (x, v)
     // fast-path line model of the current (x, v)
     // (ZigZag + Brent keeps the per-owned-coordinate A_j, B_j in shared memory: AS(j), BS(j))
+    // Speed-Up Zig-Zag (SpeedUpZigZagSamplers.jl:71-83): scalars of the current (x, v) that determine the closed-form flow
+    // y = x - v1 x1 v:  <y,y>, <y,v>, <v,v>, <x,x>, v1 x1, and a, c/d, Y0 + sqrt(Y0^2 + a), sqrt(d) v1 of the reference
+    double su_yy, su_yv, su_vv, su_xx, su_vx1, su_v1, su_a, su_cd, su_root, su_rate;
     double ra[NWW], rb[NWW];  // NW > 0: A_j, B_j of the owned coordinates (registers: only indexed by unrolled loops)
     double la, lb;          // BPS/FECMC: a = sum A_i, b = sum B_i over the affine coordinates
     double pxx, pxv, pvv;   // Boomerang: <Px,x>, <Px,v>, <Pv,v>
@@ -238,14 +243,46 @@ struct Chain {
 #pragma unroll
             for (int k = 0; k < KK; ++k) { Lx[k] = acc[k]; Lv[k] = acc[KK + k]; }
         }
+        if constexpr (kSpeedUp) {  // SpeedUpZigZagSamplers.jl:72-76
+            const double x1 = team_bcast<TEAM>(XS(0), 0, mask), v1 = team_bcast<TEAM>(VS(0), 0, mask);  // coordinate 0: lane 0, slot 0
+            const double vx1 = v1 * x1;
+            double r4[4] = {0.0, 0.0, 0.0, 0.0};
+            for_owned([&](int j) {
+                const double xj = XS(j), vj = VS(j);
+                const double yj = xj - vx1 * vj;          // y = x - v[1] * x[1] * v
+                r4[0] += yj * yj; r4[1] += yj * vj; r4[2] += vj * vj; r4[3] += xj * xj;
+            });
+            team_sum_n<TEAM, 4>(r4, mask);
+            su_yy = r4[0]; su_yv = r4[1]; su_vv = r4[2]; su_xx = r4[3];
+            su_vx1 = vx1; su_v1 = v1;
+            const double dd = (double)d;
+            const double c = v1 * su_yv;                              // c = v[1] * (y . v)
+            su_a = (1 + su_yy) / dd - (c * c) / (dd * dd);            // a = (1 + y . y) / dim - c^2 / dim^2
+            su_cd = c / dd;
+            const double Y0 = x1 + su_cd;                             // Y_0 = x[1] + c / dim
+            su_root = Y0 + sqrt(Y0 * Y0 + su_a);
+            su_rate = sqrt(dd) * v1;
+        }
     }
 
     struct Flow {  // x_t = a x + b v ; v_t = c x + e v
         double a, b, c, e;
+        // Speed-Up Zig-Zag: x_t = (x - c v) + b v with c = v1 x1, b = v1 X_1(t); speed sqrt(1 + |x_t|^2) at x_t,
+        // d/dt of b (so that dx_t/dt = ds v) and d/dt of the speed
+        double sp, ds, dsp;
     };
     __device__ __forceinline__ Flow flow_coef(double tt) const {
         Flow f;
-        if constexpr (kRot) {  // BoomerangSamplers.jl:31
+        if constexpr (kSpeedUp) {  // SpeedUpZigZagSamplers.jl:71-79
+            const double bt = su_root * exp(su_rate * tt);            // b_t = (Y_0 + sqrt(Y_0^2 + a)) exp(sqrt(dim) v[1] t)
+            const double X1 = (bt * bt - su_a) / (2 * bt) - su_cd;    // X_1 = (b_t^2 - a) / (2 b_t) - c / dim
+            f.a = 1.0; f.e = 1.0;
+            f.c = su_vx1;
+            f.b = su_v1 * X1;
+            f.sp = sqrt(1.0 + (su_yy + 2.0 * f.b * su_yv + X1 * X1 * su_vv));
+            f.ds = su_v1 * su_rate * (bt * bt + su_a) / (2 * bt);     // v1 dX_1/dt
+            f.dsp = f.ds * (su_yv + f.b * su_vv) / f.sp;              // <x_t, dx_t/dt> / speed
+        } else if constexpr (kRot) {  // BoomerangSamplers.jl:31
             double s, c;
             sincos(tt, &s, &c);
             f.a = c; f.b = s; f.c = -s; f.e = c;
@@ -255,13 +292,20 @@ struct Chain {
         return f;
     }
     __device__ __forceinline__ void flow_point(const Flow& f, double xi, double vi, double& xt, double& vt) const {
-        if constexpr (kRot) { xt = xi * f.a + vi * f.b; vt = xi * f.c + vi * f.e; }
+        if constexpr (kSpeedUp) { xt = (xi - f.c * vi) + f.b * vi; vt = vi; }   // y + v[1] * X_1 * v
+        else if constexpr (kRot) { xt = xi * f.a + vi * f.b; vt = xi * f.c + vi * f.e; }
         else { xt = xi + vi * f.b; vt = vi; }
+    }
+    // effective gradient of the Speed-Up Zig-Zag at a point with speed sp: speed grad U - grad speed (:81-83)
+    __device__ __forceinline__ double grad_eff(double g, double xt, double sp) const {
+        if constexpr (kSpeedUp) return sp * g - xt / sp;
+        else return g;
     }
     __device__ __forceinline__ void flow_functionals(const Flow& f, double* Lxt, double* Lvt) const {
 #pragma unroll
         for (int k = 0; k < KK; ++k) {
-            if constexpr (kRot) { Lxt[k] = Lx[k] * f.a + Lv[k] * f.b; Lvt[k] = Lx[k] * f.c + Lv[k] * f.e; }
+            if constexpr (kSpeedUp) { Lxt[k] = (Lx[k] - f.c * Lv[k]) + f.b * Lv[k]; Lvt[k] = Lv[k]; }
+            else if constexpr (kRot) { Lxt[k] = Lx[k] * f.a + Lv[k] * f.b; Lvt[k] = Lx[k] * f.c + Lv[k] * f.e; }
             else { Lxt[k] = Lx[k] + Lv[k] * f.b; Lvt[k] = Lv[k]; }
         }
     }
@@ -457,7 +501,7 @@ struct Chain {
                 if (owns(j)) {
                     double xt, vt;
                     flow_point(f, XS(j), VU(j), xt, vt);
-                    const double y = P::grad(p.pot, coord(j), xt, Lxt) * vt;
+                    const double y = grad_eff(P::grad(p.pot, coord(j), xt, Lxt), xt, f.sp) * vt;
                     if constexpr (kZZ) s += (y > 0.0 ? y : 0.0);
                     else s += y;
                 }
@@ -509,20 +553,46 @@ struct Chain {
     // ---- vectorised (ZigZag) bound: value and d/dt of (signed_)rate_vect for one owned coordinate ----
     __device__ __forceinline__ double vect_value(int i, double xi, double vi, double tt) const {
         double Lxt[KK];
+        if constexpr (kSpeedUp) {
+            const Flow f = flow_coef(tt);
+            double Lvt[KK], xt, vt;
+            flow_functionals(f, Lxt, Lvt);
+            flow_point(f, xi, vi, xt, vt);
+            const double y = grad_eff(P::grad(p.pot, i, xt, Lxt), xt, f.sp) * vi;
+            return p.signed_bound ? y : (y > 0.0 ? y : 0.0);
+        }
 #pragma unroll
         for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
         const double y = P::grad(p.pot, i, xi + vi * tt, Lxt) * vi;
         return p.signed_bound ? y : (y > 0.0 ? y : 0.0);
     }
+    // Speed-Up Zig-Zag: value and d/dt of the signed coordinate rate grad U_eff,i(x_t) v_i at the flow point f
+    // (what ForwardDiff computes through the closed-form flow): dx_t/dt = ds v, d speed/dt = dsp
+    __device__ __forceinline__ void speedup_rate_and_slope(int i, double xi, double vi, const Flow& f, double& y, double& dy) const {
+        double Lxt[KK], Lvt[KK], Ld[KK], xt, vt;
+        flow_functionals(f, Lxt, Lvt);
+        flow_point(f, xi, vi, xt, vt);
+#pragma unroll
+        for (int k = 0; k < KK; ++k) Ld[k] = f.ds * Lv[k];
+        const double di = f.ds * vi;
+        double g, hd;
+        P::eval(p.pot, i, xt, di, Lxt, Ld, g, hd);
+        y = (f.sp * g - xt / f.sp) * vi;
+        dy = (f.dsp * g + f.sp * hd - di / f.sp + xt * f.dsp / (f.sp * f.sp)) * vi;
+    }
     __device__ __forceinline__ void vect_node(int i, double xi, double vi, double tt, double h, double& val,
                                               double& dval) const {
         if (p.deriv_mode == PDMPFLUX_DERIV_JVP) {
-            double Lxt[KK];
+            double y, dy;
+            if constexpr (kSpeedUp) speedup_rate_and_slope(i, xi, vi, flow_coef(tt), y, dy);
+            else {
+                double Lxt[KK];
 #pragma unroll
-            for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
-            double g, hv;
-            P::eval(p.pot, i, xi + vi * tt, vi, Lxt, Lv, g, hv);
-            const double y = g * vi, dy = hv * vi;
+                for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
+                double g, hv;
+                P::eval(p.pot, i, xi + vi * tt, vi, Lxt, Lv, g, hv);
+                y = g * vi; dy = hv * vi;
+            }
             if (p.signed_bound) { val = y; dval = dy; }
             else { val = (y > 0.0 ? y : 0.0); dval = (0.0 > y) ? 0.0 : dy; }
         } else {  // finite_difference_derivative, UpperBound.jl:50-76 with start = 0
@@ -677,17 +747,20 @@ struct Chain {
                         double xt, vt;
                         flow_point(fl[u], xi, vi, xt, vt);
                         if (want_d) {
-                            double g, hv;
+                            double g, hv, y, dy;
+                            if constexpr (kSpeedUp) speedup_rate_and_slope(i, xi, vi, fl[u], y, dy);
+                            else {
                             P::eval(p.pot, i, xt, vt, Lxt, Lvt, g, hv);  // dx_t/dt = v_t for both flows
-                            const double y = g * vt;
-                            double dy = hv * vt;
+                            y = g * vt;
+                            dy = hv * vt;
+                            }
                             if constexpr (kRot) dy -= g * xt;              // dv_t/dt = -x_t
                             if constexpr (kZZ) {                           // scalar ZigZag: sum(max.(0, g.*v))
                                 av[u] += (y > 0.0 ? y : 0.0);
                                 ad[u] += (0.0 > y) ? 0.0 : dy;
                             } else { av[u] += y; ad[u] += dy; }
                         } else {
-                            const double y = P::grad(p.pot, i, xt, Lxt) * vt;
+                            const double y = grad_eff(P::grad(p.pot, i, xt, Lxt), xt, fl[u].sp) * vt;
                             if constexpr (kZZ) av[u] += (y > 0.0 ? y : 0.0);
                             else av[u] += y;
                         }
@@ -941,9 +1014,10 @@ struct Chain {
         // cumsum(p)_m > u  <=>  cumsum(lambda)_m > u S, so the d divisions are not needed; isprobvec(p) (all p >= 0,
         // sum p ~ 1, else the reference's Categorical constructor throws) holds iff S is finite and positive.
         double S = 0.0;
+        const double sp0 = kSpeedUp ? sqrt(1.0 + su_xx) : 1.0;  // speed(x) at the current point (compute_functionals ran on it)
         for (int j = 0; j < nown; ++j)
             if (owns(j)) {
-                const double y = P::grad(p.pot, coord(j), XS(j), Lx) * VS(j);
+                const double y = grad_eff(P::grad(p.pot, coord(j), XS(j), Lx), XS(j), sp0) * VS(j);
                 S += (y > 0.0 ? y : 0.0);
             }
         S = team_sum<TEAM>(S, mask);
@@ -954,7 +1028,7 @@ struct Chain {
         for (int j = 0; j < nown; ++j) {
             double lj = 0.0;
             if (owns(j)) {
-                const double y = P::grad(p.pot, coord(j), XS(j), Lx) * VS(j);
+                const double y = grad_eff(P::grad(p.pot, coord(j), XS(j), Lx), XS(j), sp0) * VS(j);
                 lj = (y > 0.0 ? y : 0.0);
             }
             const double incl = team_scan_incl<TEAM>(lj, mask, tl) + carry;
@@ -1450,7 +1524,7 @@ struct Chain {
                             status = PDMPFLUX_CHAIN_DONE;
                             live = false;
                         } else {
-                        if constexpr (kZZ && !kSticky) accept_zigzag(tp, lt);
+                        if constexpr (kZZ && !kSticky && !kSpeedUp) accept_zigzag(tp, lt);
                         else {
                             flow_inplace(tp);
                             velocity_jump();

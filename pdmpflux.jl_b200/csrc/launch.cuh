@@ -16,7 +16,7 @@ template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
 cudaError_t launch_one(const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
     // combinations without a fast path fall back to the generic kernel (same results, more passes)
     constexpr bool ok = PATH == kPathGeneric ||
-                        (SAMPLER != PDMPFLUX_STICKY_ZIGZAG && Pot<POT>::kAffine &&
+                        (SAMPLER != PDMPFLUX_STICKY_ZIGZAG && SAMPLER != PDMPFLUX_SPEEDUP_ZIGZAG && Pot<POT>::kAffine &&
                          !(SAMPLER == PDMPFLUX_BOOMERANG && Pot<POT>::kSpecial > 0));
     if constexpr (!ok) return cudaErrorInvalidValue;
     else {
@@ -93,6 +93,7 @@ inline int select_path(int sampler, int pot, int grid_size, int vectorized, int 
                         pot == PDMPFLUX_BANANA;
     if (!affine || (sampler == PDMPFLUX_BOOMERANG && pot == PDMPFLUX_BANANA)) return kPathGeneric;
     if (sampler == PDMPFLUX_STICKY_ZIGZAG) return kPathGeneric;  // masked velocities: per-node evaluation only
+    if (sampler == PDMPFLUX_SPEEDUP_ZIGZAG) return kPathGeneric; // nonlinear flow: no affine line model
     if (grid_size == 0) return kPathFastBrent;
     if (sampler == PDMPFLUX_ZIGZAG) {
         // vectorised bound with analytic derivatives only: with finite differences the reference's cell maximum
@@ -117,5 +118,6 @@ cudaError_t launch_skeleton_bps(int team, int pot, int path, const KernelParams&
 cudaError_t launch_skeleton_fecmc(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_skeleton_boomerang(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_skeleton_sticky(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_skeleton_speedup(int team, int pot, int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream);
 
 }  // namespace pdmpflux
