@@ -144,12 +144,13 @@ int pick_team(int d, int64_t n_chains, bool zz_brent_fast) {
     // SMs; 8 lanes per chain win for d up to a few hundred (fewer shuffle stages than a full warp, 4 chains share a
     // warp's instruction stream); a warp per chain beyond that (and whenever the shared-memory state would not fit).
     if (d <= 16) return n_chains >= 8192 ? 1 : 8;
-    // Zig-Zag x Brent is a serial recurrence of ~40 rate evaluations per bound whose scalar part every lane of the
-    // team repeats: 4 lanes per chain (<= 16 coordinates per lane, line model in registers) halve that redundancy.
-    // Measured (B200, banana d = 50): with enough chains to give every scheduler several warps the kernel is
-    // issue bound and teams of 4 win (3.6e8 vs 2.3e8 events/s at 65536 chains); at 4096 chains a team of 4 leaves
-    // one latency-bound warp per scheduler and teams of 8 (two warps per scheduler) win (1.9e8 vs 1.7e8).
-    if (zz_brent_fast && d <= 64 && n_chains >= 16384) return 4;
+    // Zig-Zag x Brent with a chain per thread: the rate function is compressed per bracket to one line plus the few
+    // sign-changing coordinates (chain.cuh: classify_line), so the serial Brent recurrence runs without any cross-lane
+    // reduction and 32 chains share every instruction; wins at every chain count once x and v fit in shared memory.
+    if (zz_brent_fast && d <= 64 && n_chains >= 8192) return 1;
+    // (Measured on the way there, B200, banana d = 50: teams of 8 with the line model in registers 1.9e8 events/s at
+    // 4096 chains and 2.3e8 at 65536; teams of 4 1.7e8 / 3.6e8 -- both issue bound by the Brent bookkeeping that every
+    // lane of a team repeats.  PDMPFLUX_TEAM=4 / 8 still select them.)
     if (d <= 256) return 8;
     return 32;
 }
@@ -567,20 +568,24 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     if (const char* e = std::getenv("PDMPFLUX_FORCE_GENERIC")) { if (std::atoi(e)) ch->path = kPathGeneric; }
     ch->team = pick_team(d, n_chains, s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && !logreg);
     // widen the team until x and v (per-thread-owned shared-memory columns) fit next to a second block
-    while (ch->team < 32 && 4 * (size_t)((d + ch->team - 1) / ch->team) * kBlockThreads * sizeof(double) > 100 * 1024)
+    const bool zz_brent_fast = s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && !logreg;
+    const size_t vecs_needed = (zz_brent_fast && ch->team == 1) ? 2 : 4;   // thread-per-chain Brent keeps no A / B vectors
+    while (ch->team < 32 && vecs_needed * (size_t)((d + ch->team - 1) / ch->team) *
+                                    block_threads_rt(ch->team, s->kind, ch->path) * sizeof(double) > 110 * 1024)
         ch->team = ch->team < 8 ? 8 : 32;
     ch->n_own = (d + ch->team - 1) / ch->team;
-    const int cpb = kBlockThreads / ch->team;
+    const int bt = block_threads_rt(ch->team, s->kind, ch->path);   // threads per block of the kernel that will run
+    const int cpb = bt / ch->team;
     ch->grid = (unsigned)((n_chains + cpb - 1) / cpb);
     ch->n_groups = ch->grid;
-    if (ch->team == 1) { ch->dpad = 0; ch->vec_elems = ch->n_own * kBlockThreads; }
+    if (ch->team == 1) { ch->dpad = 0; ch->vec_elems = ch->n_own * bt; }
     else {
         ch->dpad = (ch->n_own * ch->team + 7) / 8 * 8;                  // 64-byte aligned chain slots (TMA source)
         if (ch->team < 32 && ch->dpad % 16 != 8) ch->dpad += 8;         // chains of a warp land on distinct bank halves
         ch->vec_elems = cpb * ch->dpad;
     }
     const size_t vec_bytes = (size_t)ch->vec_elems * sizeof(double);
-    const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent &&
+    const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && ch->team > 1 &&
                          brent_reg_nw(s->kind, ch->path, ch->team, ch->n_own) == 0) ? 4 : 2;
     ch->smem = (nvec + (s->kind == PDMPFLUX_STICKY_ZIGZAG ? 1 : 0)) * vec_bytes;
     if (s->kind == PDMPFLUX_FECMC) {
@@ -597,10 +602,10 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
             CUDA_TRY(ch->scratch.alloc((size_t)ch->grid * 3 * vec_bytes));
         }
     }
-    if (ch->team == 1) ch->smem += 6 * kBlockThreads * sizeof(double);  // row carry slots (record())
+    if (ch->team == 1) ch->smem += 6 * (size_t)bt * sizeof(double);  // row carry slots (record())
     {
         const size_t gb = s->cfg.grid_size > 2 ? s->cfg.grid_size : 2;      // box_max / cum_sum, one copy per chain
-        ch->smem += (ch->team == 1 ? (size_t)kBlockThreads : (size_t)cpb) * 2 * gb * sizeof(double);
+        ch->smem += (ch->team == 1 ? (size_t)bt : (size_t)cpb) * 2 * gb * sizeof(double);
     }
     if (logreg) {  // logreg_chains_per_block() chains per CTA, one warp each
         const int lcpb = logreg_chains_per_block();

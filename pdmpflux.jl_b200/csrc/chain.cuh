@@ -56,7 +56,9 @@ extern __shared__ __align__(128) double g_smem[];
 //               per grid node;
 //   * Boomerang (kSpecial == 0): <P x_t, v_t> = sin cos (pvv - pxx) + (cos^2 - sin^2) pxv.
 // Results differ from the generic path (and the oracle) only by floating-point reassociation (~1e-16 relative).
-enum { kPathGeneric = 0, kPathFastBrent = 1, kPathFastGrid = 2 };
+// Thread-per-chain Zig-Zag x Brent ("compressed line model"): capacity of the per-chain register list of coordinates
+// whose rate changes sign inside the bound's bracket (see Chain::classify_line)
+constexpr int kCrossMax = 12;
 
 // NW > 0 (Zig-Zag + kPathFastBrent only): compile-time capacity of the owned-coordinate loops; the line model
 // (A_j, B_j) of the owned coordinates then lives in registers (slots >= n_own hold A = B = 0) and the ~40 rate
@@ -77,8 +79,9 @@ struct Chain {
     static constexpr bool kZZ = (SAMPLER == PDMPFLUX_ZIGZAG) || kSticky || kSpeedUp;   // StickyZigZagSamplers.jl:69-101: same closures
     static_assert(!kSticky || PATH == kPathGeneric, "Sticky Zig-Zag runs on the generic path");
     static_assert(!kSpeedUp || PATH == kPathGeneric, "Speed-Up Zig-Zag runs on the generic path");
-    static constexpr int kStr = (TEAM == 1) ? kBlockThreads : TEAM;  // stride between a thread's owned elements
-    static constexpr int kBStr = (TEAM == 1) ? kBlockThreads : 1;    // stride between a chain's box / cum entries
+    static constexpr int kBT = block_threads_rt(TEAM, SAMPLER, PATH);   // threads per block
+    static constexpr int kStr = (TEAM == 1) ? kBT : TEAM;  // stride between a thread's owned elements
+    static constexpr int kBStr = (TEAM == 1) ? kBT : 1;    // stride between a chain's box / cum entries
 
     const KernelParams& p;
     int off_ac;                      // Sticky Zig-Zag: is_active flags of the owned coordinates (1.0 / 0.0)
@@ -99,6 +102,10 @@ struct Chain {
     // Speed-Up Zig-Zag (SpeedUpZigZagSamplers.jl:71-83): scalars of the current (x, v) that determine the closed-form flow
     // y = x - v1 x1 v:  <y,y>, <y,v>, <v,v>, <x,x>, v1 x1, and a, c/d, Y0 + sqrt(Y0^2 + a), sqrt(d) v1 of the reference
     double su_yy, su_yv, su_vv, su_xx, su_vx1, su_v1, su_a, su_cd, su_root, su_rate;
+    static constexpr bool kCompressed = (TEAM == 1) && (SAMPLER == PDMPFLUX_ZIGZAG) && (PATH == kPathFastBrent);
+    double cl_al, cl_be;      // compressed line model: sum of A_i, B_i over the coordinates that are active on the whole bracket
+    int cl_n;                 // ... number of sign-changing coordinates kept in ca / cb (unused slots hold 0); > kCrossMax: not compressed
+    double ca[kCompressed ? kCrossMax : 1], cb[kCompressed ? kCrossMax : 1];   // registers: only indexed by unrolled loops
     double ra[NWW], rb[NWW];  // NW > 0: A_j, B_j of the owned coordinates (registers: only indexed by unrolled loops)
     double la, lb;          // BPS/FECMC: a = sum A_i, b = sum B_i over the affine coordinates
     double pxx, pxv, pvv;   // Boomerang: <Px,x>, <Px,v>, <Pv,v>
@@ -120,7 +127,7 @@ struct Chain {
     int nb;
 
     // output staging (see record())
-    int off_f;               // TEAM == 1: 2 x 3 carry slots (x, v) in shared memory, slot s at off_f + s * kBlockThreads
+    int off_f;               // TEAM == 1: 2 x 3 carry slots (x, v) in shared memory, slot s at off_f + s * kBT
     int fcnt, fskip;         // row stream: elements carried over / leading phantom slots of the first 32-byte group
     int scnt, sskip;         // scalar columns t / horizon / ar: staged events / leading phantom slots
     double st_t[3], st_h[3], st_a[3];
@@ -388,6 +395,8 @@ struct Chain {
                     }
                     ra[j] = A; rb[j] = B;
                 }
+            } else if constexpr (kCompressed) {
+                // nothing to store: classify_line() compresses the model per bracket
             } else if constexpr (PATH == kPathFastBrent) {
                 for (int j = 0; j < nown; ++j) {
                     double A = 0.0, B = 0.0;  // A = B = 0 contributes max(0, 0) = 0 for unowned / special slots
@@ -467,6 +476,38 @@ struct Chain {
             }
             const double s = team_sum<TEAM>((acc[0] + acc[1]) + (acc[2] + acc[3]), mask);
             return fma(0.5, s, sp_);
+        } else if constexpr (kCompressed) {
+            // sum_i max(0, A_i + t B_i) over the affine coordinates = (al + t be) over the always-active ones
+            //                                                       + the few coordinates that change sign in the bracket
+            double s = 0.0;
+            if (cl_n <= kCrossMax) {
+                double c[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < kCrossMax; ++k) {   // empty slots are A = B = 0: max(0, 0) = 0
+                    const double y = fma(tt, cb[k], ca[k]);
+                    c[k & 3] += y + fabs(y);
+                }
+                s = fma(0.5, (c[0] + c[1]) + (c[2] + c[3]), fma(tt, cl_be, cl_al));
+            } else {  // more sign changes than the list holds (rare): every coordinate from (x, v)
+                double c0 = 0.0;
+                for (int j = NS; j < nown; ++j) {
+                    const double vi = VS(j);
+                    double g, hv;
+                    P::eval(p.pot, j, XS(j), vi, Lx, Lv, g, hv);
+                    const double y = fma(tt, hv * vi, g * vi);
+                    c0 += y + fabs(y);
+                }
+                s = 0.5 * c0;
+            }
+            if constexpr (NS > 0) {
+                double ys[NS], dys[NS];
+                special_rates(tt, ys, dys);
+                double sp_ = 0.0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) sp_ += ys[k] + fabs(ys[k]);
+                s = fma(0.5, sp_, s);
+            }
+            return s;
         } else if constexpr (kZZ && PATH == kPathFastBrent) {
             // max(0, y) = (y + |y|) / 2 exactly in binary floating point: one DADD (|.| is an operand modifier)
             // instead of a compare and two selects; the halving is applied once to the sum.
@@ -560,11 +601,12 @@ struct Chain {
             flow_point(f, xi, vi, xt, vt);
             const double y = grad_eff(P::grad(p.pot, i, xt, Lxt), xt, f.sp) * vi;
             return p.signed_bound ? y : (y > 0.0 ? y : 0.0);
-        }
+        } else {
 #pragma unroll
-        for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
-        const double y = P::grad(p.pot, i, xi + vi * tt, Lxt) * vi;
-        return p.signed_bound ? y : (y > 0.0 ? y : 0.0);
+            for (int k = 0; k < KK; ++k) Lxt[k] = Lx[k] + Lv[k] * tt;
+            const double y = P::grad(p.pot, i, xi + vi * tt, Lxt) * vi;
+            return p.signed_bound ? y : (y > 0.0 ? y : 0.0);
+        }
     }
     // Speed-Up Zig-Zag: value and d/dt of the signed coordinate rate grad U_eff,i(x_t) v_i at the flow point f
     // (what ForwardDiff computes through the closed-form flow): dx_t/dt = ds v, d speed/dt = dsp
@@ -919,7 +961,38 @@ struct Chain {
     //     branch: for the piecewise-linear Zig-Zag rates the maximum sits at an end of [0, h], the parabola through
     //     three collinear points is degenerate and Brent takes golden-section steps only (BASELINE config C2: not one
     //     parabolic step in 2.4e4 iterations), so the warps skip the division altogether.
+    // Thread-per-chain Zig-Zag x Brent.  On the bracket [0, h] of one bound every affine coordinate rate A_i + t B_i
+    // either stays positive (its max(0, .) is the line itself: summed once into al + t be), stays non-positive
+    // (contributes nothing) or changes sign (kept individually).  The ~40 rate evaluations of the Brent recurrence and
+    // the thinning evaluations that follow (all at times inside the bracket) then cost one fused multiply-add plus a
+    // handful of max(0, .) terms instead of a pass over the d coordinates -- and, with a chain per thread, no
+    // cross-lane reduction at all.  Same values as the per-coordinate sum up to reassociation.
+    __device__ void classify_line(double h) {
+        double al = 0.0, be = 0.0;
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < kCrossMax; ++k) { ca[k] = 0.0; cb[k] = 0.0; }
+#pragma unroll 2
+        for (int j = NS; j < nown; ++j) {
+            const double vi = VS(j);
+            double g, hv;
+            P::eval(p.pot, j, XS(j), vi, Lx, Lv, g, hv);
+            const double A = g * vi, B = hv * vi;
+            const double yh = fma(h, B, A);
+            const bool p0 = A > 0.0, ph = yh > 0.0;
+            if (p0 && ph) { al += A; be += B; }
+            else if (p0 || ph) {  // push onto the register list (static indices only: shift, then slot 0)
+#pragma unroll
+                for (int k = kCrossMax - 1; k > 0; --k) { ca[k] = ca[k - 1]; cb[k] = cb[k - 1]; }
+                ca[0] = A; cb[0] = B;
+                ++n;    // more than kCrossMax: the oldest entries fall off the end and rate_unsigned() takes the full pass
+            }
+        }
+        cl_al = al; cl_be = be; cl_n = n;
+    }
+
     __device__ void build_bound_brent(double h) {
+        if constexpr (kCompressed) classify_line(h);
         const double golden = 0.3819660112501051;  // (3 - sqrt(5)) / 2
         double lo = 0.0, hi = h;
         double x = __dadd_rn(lo, __dmul_rn(golden, __dadd_rn(hi, -lo)));
@@ -1753,7 +1826,7 @@ struct Chain {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int pos = 4 * q + k;
-            vq[k] = pos < r ? g_smem[off_carry + pos * kBlockThreads] : g_smem[off_src + (pos - r) * kBlockThreads];
+            vq[k] = pos < r ? g_smem[off_carry + pos * kBT] : g_smem[off_src + (pos - r) * kBT];
         }
         double* dst = G + gfirst + 4 * q;
         if (q == 0 && fskip > 0) {  // first group of this launch starts mid-sector: scalar stores for the real part
@@ -1794,19 +1867,19 @@ struct Chain {
                 if (p.X)
                     for (int q = 0; q < ng; ++q) row_group_tm1(p.X, gfirst, q, r, off_x, off_f);
                 if (p.V)
-                    for (int q = 0; q < ng; ++q) row_group_tm1(p.V, gfirst, q, r, off_v, off_f + 3 * kBlockThreads);
+                    for (int q = 0; q < ng; ++q) row_group_tm1(p.V, gfirst, q, r, off_v, off_f + 3 * kBT);
                 const int rem = total - 4 * ng;
                 if (ng > 0) {
                     for (int k = 0; k < rem; ++k) {  // tail of the row becomes the next carry
                         const int pos = 4 * ng + k;
-                        g_smem[off_f + k * kBlockThreads] = g_smem[off_x + (pos - r) * kBlockThreads];
-                        g_smem[off_f + (3 + k) * kBlockThreads] = g_smem[off_v + (pos - r) * kBlockThreads];
+                        g_smem[off_f + k * kBT] = g_smem[off_x + (pos - r) * kBT];
+                        g_smem[off_f + (3 + k) * kBT] = g_smem[off_v + (pos - r) * kBT];
                     }
                     fskip = 0;
                 } else {  // d < 4 and the group is still open: append
                     for (int k = r; k < total; ++k) {
-                        g_smem[off_f + k * kBlockThreads] = g_smem[off_x + (k - r) * kBlockThreads];
-                        g_smem[off_f + (3 + k) * kBlockThreads] = g_smem[off_v + (k - r) * kBlockThreads];
+                        g_smem[off_f + k * kBT] = g_smem[off_x + (k - r) * kBT];
+                        g_smem[off_f + (3 + k) * kBT] = g_smem[off_v + (k - r) * kBT];
                     }
                 }
                 fcnt = rem;
@@ -1878,8 +1951,8 @@ struct Chain {
             if (p.vec32) {
                 for (int k = fskip; k < fcnt; ++k) {
                     const int64_t g = r_next * d - fcnt + k;
-                    if (p.X) p.X[g] = g_smem[off_f + k * kBlockThreads];
-                    if (p.V) p.V[g] = g_smem[off_f + (3 + k) * kBlockThreads];
+                    if (p.X) p.X[g] = g_smem[off_f + k * kBT];
+                    if (p.V) p.V[g] = g_smem[off_f + (3 + k) * kBT];
                 }
             }
         } else {
@@ -1890,13 +1963,14 @@ struct Chain {
 };
 
 // One launch advances every chain by p.n_events accepted events (or just records the current state when
-// n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBlockThreads / TEAM)).
+// n_events == 0 and col0 names the column).  Grid = ceil(n_chains / (kBT / TEAM)).
 #ifndef PDMPFLUX_MINBLOCKS_GRID
 #define PDMPFLUX_MINBLOCKS_GRID 4
 #endif
 template <int TEAM, int SAMPLER, int POT, int PATH, int NW = 0>
-__global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PATH == kPathFastBrent ? 2 : (TEAM == 32 ? 3 : PDMPFLUX_MINBLOCKS_GRID))) skeleton_kernel(const __grid_constant__ KernelParams p) {
-    constexpr int CPB = kBlockThreads / TEAM;  // chains per block
+__global__ void __launch_bounds__(block_threads_rt(TEAM, SAMPLER, PATH), PATH == kPathGeneric ? 1 : (PATH == kPathFastBrent ? (TEAM == 1 && SAMPLER == PDMPFLUX_ZIGZAG ? 4 : 2) : (TEAM == 32 ? 3 : PDMPFLUX_MINBLOCKS_GRID))) skeleton_kernel(const __grid_constant__ KernelParams p) {
+    constexpr int kBT = block_threads_rt(TEAM, SAMPLER, PATH);
+    constexpr int CPB = kBT / TEAM;  // chains per block
     const int c_local = threadIdx.x / TEAM;
     // A block normally owns one group of CPB chains (grid = number of groups).  With p.n_groups > gridDim.x the grid is
     // persistent (one block per resident slot) and walks over the groups: the per-block scratch vectors in global
@@ -1924,7 +1998,7 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
     ch.off_v = vec + toff;
     int used = 2;
     ch.off_a = ch.off_b = 0;
-    if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent && NW == 0) {
+    if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent && NW == 0 && TEAM > 1) {
         ch.off_a = 2 * vec + toff;
         ch.off_b = 3 * vec + toff;
         used = 4;
@@ -1958,10 +2032,10 @@ __global__ void __launch_bounds__(kBlockThreads, PATH == kPathGeneric ? 1 : (PAT
     ch.off_f = used * vec + (int)threadIdx.x;  // TEAM == 1 only: 6 carry slots per thread
     {
         const int gb = p.G > 2 ? p.G : 2;      // entries per array (Brent uses 1 + 2)
-        const int base = used * vec + (TEAM == 1 ? 6 * kBlockThreads : 0);
+        const int base = used * vec + (TEAM == 1 ? 6 * kBT : 0);
         if constexpr (TEAM == 1) {
             ch.off_box = base + (int)threadIdx.x;
-            ch.off_cum = base + gb * kBlockThreads + (int)threadIdx.x;
+            ch.off_cum = base + gb * kBT + (int)threadIdx.x;
         } else {
             ch.off_box = base + c_local * 2 * gb;
             ch.off_cum = ch.off_box + gb;

@@ -8,7 +8,16 @@
 
 namespace pdmpflux {
 
-constexpr int kBlockThreads = 128;
+constexpr int kBlockThreads = 128;   // threads per block of every kernel except the one below
+
+// PATH of a skeleton kernel (chain.cuh)
+enum { kPathGeneric = 0, kPathFastBrent = 1, kPathFastGrid = 2 };
+
+// Thread-per-chain Zig-Zag x Brent is limited by the shared memory its chains' x and v take (16 d bytes per chain):
+// blocks of 64 threads pack the SM with four blocks (8 warps) where blocks of 128 leave room for one or two.
+__host__ __device__ constexpr int block_threads_rt(int team, int sampler, int path) {
+    return (team == 1 && sampler == PDMPFLUX_ZIGZAG && path == kPathFastBrent) ? 64 : kBlockThreads;
+}
 constexpr int kMaxGrid = 64;        // largest supported grid_size (per-thread local arrays)
 constexpr int kChunk = 8;           // grid nodes / cells processed per register chunk
 constexpr double kSqrtEps = 1.4901161193847656e-08;

@@ -25,7 +25,7 @@ cudaError_t launch_one(const KernelParams& p, unsigned grid, size_t smem, cudaSt
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<grid, kBlockThreads, smem, stream>>>(p);
+        kern<<<grid, block_threads_rt(TEAM, SAMPLER, PATH), smem, stream>>>(p);
         return cudaGetLastError();
     }
 }
