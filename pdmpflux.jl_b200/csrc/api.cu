@@ -131,7 +131,7 @@ struct pdmpflux_chains_s {
 namespace {
 
 // Team widths built: 1, 8, 32 for everything; 4 only for the register-resident Zig-Zag x Brent kernels (launch.cuh).
-int pick_team(int d, int64_t n_chains, bool zz_brent_fast) {
+int pick_team(int d, int64_t n_chains, bool zz_brent_fast, int sampler) {
     if (const char* e = std::getenv("PDMPFLUX_TEAM")) {
         const int t = std::atoi(e);  // only the team widths launch_for_sampler instantiates
         if (t == 1 || t == 8 || t == 32) return t;
@@ -148,6 +148,9 @@ int pick_team(int d, int64_t n_chains, bool zz_brent_fast) {
     // sign-changing coordinates (chain.cuh: classify_line), so the serial Brent recurrence runs without any cross-lane
     // reduction and 32 chains share every instruction; wins at every chain count once x and v fit in shared memory.
     if (zz_brent_fast && d <= 64 && n_chains >= 8192) return 1;
+    // (A chain per thread does NOT pay for BPS / Boomerang at d ~ 100 -- measured 1.1e8 events/s against 3.4e8 with
+    // teams of 8 on BASELINE config 3: a refresh draws d normals, and with 32 chains per warp some lane refreshes in
+    // almost every event, so the whole warp pays the d-normal pass every time.)
     // (Measured on the way there, B200, banana d = 50: teams of 8 with the line model in registers 1.9e8 events/s at
     // 4096 chains and 2.3e8 at 65536; teams of 4 1.7e8 / 3.6e8 -- both issue bound by the Brent bookkeeping that every
     // lane of a team repeats.  PDMPFLUX_TEAM=4 / 8 still select them.)
@@ -566,13 +569,17 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     const bool logreg = s->pot->kind == PDMPFLUX_LOGREG;
     ch->path = select_path(s->kind, s->pot->kind, s->cfg.grid_size, s->cfg.vectorized_bound, s->cfg.deriv_mode);
     if (const char* e = std::getenv("PDMPFLUX_FORCE_GENERIC")) { if (std::atoi(e)) ch->path = kPathGeneric; }
-    ch->team = pick_team(d, n_chains, s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && !logreg);
-    // widen the team until x and v (per-thread-owned shared-memory columns) fit next to a second block
+    ch->team = pick_team(d, n_chains, s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && !logreg, s->kind);
+    // widen the team until the per-thread-owned shared-memory columns of a block (x, v, Zig-Zag x Brent A / B, moments,
+    // sticky flags; ForwardECMC scratch goes to global memory when it is large) leave room for a second block
     const bool zz_brent_fast = s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && !logreg;
-    const size_t vecs_needed = (zz_brent_fast && ch->team == 1) ? 2 : 4;   // thread-per-chain Brent keeps no A / B vectors
-    while (ch->team < 32 && vecs_needed * (size_t)((d + ch->team - 1) / ch->team) *
-                                    block_threads_rt(ch->team, s->kind, ch->path) * sizeof(double) > 110 * 1024)
-        ch->team = ch->team < 8 ? 8 : 32;
+    auto vectors_bytes = [&](int team) {
+        const int bt_ = block_threads_rt(team, s->kind, ch->path);
+        const size_t nv = (zz_brent_fast && team > 1 && brent_reg_nw(s->kind, ch->path, team, (d + team - 1) / team) == 0) ? 4 : 2;
+        return (nv + 2 /* fused moments may be enabled later */ + (s->kind == PDMPFLUX_STICKY_ZIGZAG ? 1 : 0)) *
+               (size_t)((d + team - 1) / team) * bt_ * sizeof(double);
+    };
+    while (ch->team < 32 && vectors_bytes(ch->team) > 110 * 1024) ch->team = ch->team < 8 ? 8 : 32;
     ch->n_own = (d + ch->team - 1) / ch->team;
     const int bt = block_threads_rt(ch->team, s->kind, ch->path);   // threads per block of the kernel that will run
     const int cpb = bt / ch->team;
@@ -598,7 +605,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
             int dev = 0, n_sm = 148;
             cudaGetDevice(&dev);
             if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-            ch->grid = (unsigned)std::min<int64_t>(ch->n_groups, (int64_t)3 * n_sm);
+            ch->grid = (unsigned)std::min<int64_t>(ch->n_groups, (int64_t)(ch->team == 32 ? 3 : 4) * n_sm);
             CUDA_TRY(ch->scratch.alloc((size_t)ch->grid * 3 * vec_bytes));
         }
     }

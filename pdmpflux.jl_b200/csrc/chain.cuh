@@ -1976,8 +1976,8 @@ __global__ void __launch_bounds__(block_threads_rt(TEAM, SAMPLER, PATH), PATH ==
     // persistent (one block per resident slot) and walks over the groups: the per-block scratch vectors in global
     // memory are then indexed by the resident block, stay in the L2 and are rewritten in place instead of being
     // flushed to DRAM behind the history rows (ForwardECMC at large d).
-    // (only the warp-per-chain kernels are ever launched that way; for the others the loop is compiled away)
-    constexpr bool kPersistent = (TEAM == 32);
+    // (only the warp-per-chain and the ForwardECMC kernels are ever launched that way; for the others the loop is compiled away)
+    constexpr bool kPersistent = (TEAM == 32) || (SAMPLER == PDMPFLUX_FECMC);
     int64_t grp = blockIdx.x;
     do {
     const int64_t c_raw = grp * CPB + c_local;

@@ -15,8 +15,13 @@ enum { kPathGeneric = 0, kPathFastBrent = 1, kPathFastGrid = 2 };
 
 // Thread-per-chain Zig-Zag x Brent is limited by the shared memory its chains' x and v take (16 d bytes per chain):
 // blocks of 64 threads pack the SM with four blocks (8 warps) where blocks of 128 leave room for one or two.
+// The same holds for thread-per-chain BPS / Boomerang / ForwardECMC at d ~ 100 (1.8 kB of state per chain): blocks of
+// one warp.  (Thread-per-chain Zig-Zag with a grid bound is used at small d only and keeps 128.)
 __host__ __device__ constexpr int block_threads_rt(int team, int sampler, int path) {
-    return (team == 1 && sampler == PDMPFLUX_ZIGZAG && path == kPathFastBrent) ? 64 : kBlockThreads;
+    if (team != 1) return kBlockThreads;
+    if (sampler == PDMPFLUX_ZIGZAG) return path == kPathFastBrent ? 64 : kBlockThreads;
+    if (sampler == PDMPFLUX_BPS || sampler == PDMPFLUX_FECMC || sampler == PDMPFLUX_BOOMERANG) return 32;
+    return kBlockThreads;
 }
 constexpr int kMaxGrid = 64;        // largest supported grid_size (per-thread local arrays)
 constexpr int kChunk = 8;           // grid nodes / cells processed per register chunk

@@ -181,3 +181,25 @@ def test_fused_moments_against_independent_closed_form(p, kind):
     e1, e2 = np.abs(m1 - r1).max() / mag1, np.abs(m2 - r2).max() / mag2
     record_parity_error(f"fused_moments/{kind}", m1=e1, m2=e2, tol=1e-12)
     assert e1 < 1e-12 and e2 < 1e-12, (e1, e2)
+
+
+def test_fecmc_global_scratch_with_more_groups_than_resident_blocks(p):
+    """ForwardECMC keeps its two scratch vectors in global memory once they no longer fit in shared memory; the grid is
+    then persistent (one block per resident slot walking over the chain groups).  With more groups than resident blocks
+    every chain must still be advanced, for both team widths, and agree with the oracle's Philox restatement."""
+    d, nch, n_sk = 200, 9700, 4
+    g = np.random.default_rng(3)
+    x0 = g.standard_normal((nch, d)); v0 = g.standard_normal((nch, d)); v0 /= np.linalg.norm(v0, axis=1, keepdims=True)
+    s = p.ForwardECMC(d, p.GaussStd())
+    outs = {}
+    for team in (8, 32):
+        os.environ["PDMPFLUX_TEAM"] = str(team)
+        try:
+            outs[team] = p.sample_skeleton(s, n_sk, x0, v0, seed=17)
+        finally:
+            os.environ.pop("PDMPFLUX_TEAM")
+        h = outs[team]
+        assert np.isfinite(h.X).all() and (np.diff(h.t, axis=1) > 0).all(), team   # every chain moved
+    assert relerr(outs[8].X, outs[32].X) < 1e-9 and relerr(outs[8].t, outs[32].t) < 1e-9
+    r = oc.sample_skeleton(oc.make_cfg(2, 0, d), n_sk, x0[-3:], v0[-3:], seed=17, chain_offset=nch - 3)
+    assert relerr(outs[8].X[-3:], r.X) < 1e-7 and relerr(outs[8].t[-3:], r.t) < 1e-7
