@@ -282,12 +282,18 @@ def c4_flops(d, builds, rates, n_chain_launches):
     return alg, exe
 
 
-def roofline_block(name, nch, n_ev, kern_s, builds, rates, n_chain_launches, hbm_peak, peak_src, fp64, clock_mhz):
+def roofline_block(name, nch, n_ev, kern_s, builds, rates, n_chain_launches, hbm_peak, peak_src, fp64, clock_mhz, prof_key=None):
     """The governing roofline north_star names for the workload (HBM skeleton writes; FP64 DMMA for C4), from the
     kernel's CUDA-event time in THIS run, plus what actually limits it (instruction issue) where that is not the roofline."""
     d = CONFIGS[name]["d"]
-    traffic, inst_per_event, prof_note = measured_profile(name)
+    traffic, inst_per_event, prof_note = measured_profile(prof_key or name)
     events = nch * n_ev
+    if traffic is not None:   # the capture was taken at the bench's launch shape; scale if this run's differs
+        try:
+            ev_prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[prof_key or name]["events_in_launch"]
+            traffic = traffic * events / ev_prof
+        except (OSError, ValueError, KeyError):
+            pass
     if name == "c4":
         alg, exe = c4_flops(d, builds, rates, n_chain_launches)
         peak = float(fp64["dmma_tflops"])
@@ -560,7 +566,8 @@ def extra_workloads(p, main, hbm_peak, peak_src, fp64, clock_mhz):
         if name == "c4" and nch > 8192:
             continue
         best, builds, rates = timed_launches(p, torch, name, nch, n_ev, dev)
-        rl = roofline_block(name, nch, n_ev, best, builds, rates, nch, hbm_peak, peak_src, fp64, clock_mhz)
+        rl = roofline_block(name, nch, n_ev, best, builds, rates, nch, hbm_peak, peak_src, fp64, clock_mhz,
+                            prof_key=(f"{name}@{nch}" if nch != DEFAULT_CHAINS[name] else None))
         e = {"workload": CONFIGS[name]["desc"], "chains": nch, "events_per_chain": n_ev, "events_per_s": nch * n_ev / best,
              "ms": best * 1e3, "roofline": rl}
         if rl["bound"] == "hbm":

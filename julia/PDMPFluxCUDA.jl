@@ -84,7 +84,7 @@ function CuPDMP(kind, dim::Int, pot::CuPotential, cfg::CConfig; kappa::Union{Not
         ccall((:pdmpflux_potential_destroy, LIB), Cint, (Ptr{Cvoid},), hp[])
         check(rc)
     end
-    s = CuPDMP(kind, dim, hp[], hs[], kind == 3 ? 1 : 0, kappa !== nothing, nothing)
+    s = CuPDMP(kind, dim, hp[], hs[], kind == 3 ? 1 : (kind == 5 ? 2 : 0), kappa !== nothing, nothing)   # flow_kind
     finalizer(s) do x
         ccall((:pdmpflux_sampler_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle)
         ccall((:pdmpflux_potential_destroy, LIB), Cint, (Ptr{Cvoid},), x.pot)
@@ -132,6 +132,12 @@ PDMPFlux.StickyZigZag(dim::Int, pot::CuPotential, κ::Vector{Float64}; refresh_r
                                 Float64(tmax), refresh_rate, 0.5, 1.0); kappa=κ)
 PDMPFlux.StickyZigZagAD(dim::Int, pot::CuPotential, κ::Vector{Float64}; kw...) =
     PDMPFlux.StickyZigZag(dim, pot, κ; AD_backend="ForwardDiff", kw...)
+# SpeedUpZigZagSamplers.jl:58-60 / :119-129
+PDMPFlux.SpeedUpZigZag(dim::Int, pot::CuPotential; grid_size::Int=10, tmax=2.0, refresh_rate::Float64=0.0,
+                       vectorized_bound::Bool=true, signed_bound::Bool=true, adaptive::Bool=true, AD_backend::String="FiniteDiff") =
+    CuPDMP(5, dim, pot, CConfig(grid_size, vectorized_bound, signed_bound, adaptive, deriv_mode(AD_backend), 0, 0, 1, 1, 0,
+                                Float64(tmax), refresh_rate, 0.5, 1.0))
+PDMPFlux.SpeedUpZigZagAD(dim::Int, pot::CuPotential; kw...) = PDMPFlux.SpeedUpZigZag(dim, pot; AD_backend="ForwardDiff", kw...)
 
 # ---- histories ---------------------------------------------------------------------------------------------------
 """
