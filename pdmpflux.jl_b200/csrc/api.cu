@@ -114,6 +114,7 @@ struct pdmpflux_chains_s {
     int64_t n_chains = 0, chain_offset = 0, event0 = 0;
     uint64_t seed = 0;
     int team = 32, n_own = 0, scratch_in_smem = 1, path = 0, vec_elems = 0, dpad = 0;
+    int brent_nw = 0;   // Zig-Zag x Brent line-model variant (brent_reg_nw), fixed when the chains are created
     size_t smem = 0;
     unsigned grid = 0;
     int64_t n_groups = 0;   // groups of chains (one block's worth); grid < n_groups: persistent blocks walk over the groups
@@ -198,6 +199,7 @@ int launch(pdmpflux_chains_s* ch, int64_t n_events, const pdmpflux_history* h, i
     p.col0 = col0;
     p.kappa = s->kappa.as<double>(); p.sact = ch->act.as<uint8_t>(); p.ACT = h ? h->is_active : nullptr;
     p.scratch = ch->scratch.as<double>(); p.scratch_in_smem = ch->scratch_in_smem; p.n_own = ch->n_own;
+    p.brent_nw = ch->brent_nw;
     p.vec_elems = ch->vec_elems; p.dpad = ch->dpad;
     if (h) {
         auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
@@ -575,7 +577,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     const bool zz_brent_fast = s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && !logreg;
     auto vectors_bytes = [&](int team) {
         const int bt_ = block_threads_rt(team, s->kind, ch->path);
-        const size_t nv = (zz_brent_fast && team > 1 && brent_reg_nw(s->kind, ch->path, team, (d + team - 1) / team) == 0) ? 4 : 2;
+        const size_t nv = (zz_brent_fast && team > 1 && brent_reg_nw(s->kind, ch->path, team, (d + team - 1) / team) <= 0) ? 4 : 2;
         return (nv + 2 /* fused moments may be enabled later */ + (s->kind == PDMPFLUX_STICKY_ZIGZAG ? 1 : 0)) *
                (size_t)((d + team - 1) / team) * bt_ * sizeof(double);
     };
@@ -592,8 +594,8 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
         ch->vec_elems = cpb * ch->dpad;
     }
     const size_t vec_bytes = (size_t)ch->vec_elems * sizeof(double);
-    const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && ch->team > 1 &&
-                         brent_reg_nw(s->kind, ch->path, ch->team, ch->n_own) == 0) ? 4 : 2;
+    ch->brent_nw = brent_reg_nw(s->kind, ch->path, ch->team, ch->n_own);
+    const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && ch->team > 1 && ch->brent_nw <= 0) ? 4 : 2;
     ch->smem = (nvec + (s->kind == PDMPFLUX_STICKY_ZIGZAG ? 1 : 0)) * vec_bytes;
     if (s->kind == PDMPFLUX_FECMC) {
         if ((nvec + 3) * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = (nvec + 3) * vec_bytes; }

@@ -70,6 +70,10 @@ struct Chain {
     static constexpr bool kRegLine = (NW > 0);
     static constexpr int NWW = NW > 0 ? NW : 1;
     static_assert(NW == 0 || (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent), "NW is a Zig-Zag x Brent option");
+    // NW < 0: "transposed" team Brent -- every lane of the team keeps the chain's compressed line model and evaluates
+    // ONE abscissa of a speculative batch of TEAM Brent iterations (see build_bound_brent)
+    static constexpr bool kTeamSpec = (NW < 0);
+    static_assert(!kTeamSpec || (TEAM > 1 && TEAM < 32), "transposed Brent: teams of 4 or 8 lanes");
     static constexpr int NS = P::kSpecial;
     static constexpr int K = P::K;
     static constexpr int KK = K > 0 ? K : 1;
@@ -102,7 +106,7 @@ struct Chain {
     // Speed-Up Zig-Zag (SpeedUpZigZagSamplers.jl:71-83): scalars of the current (x, v) that determine the closed-form flow
     // y = x - v1 x1 v:  <y,y>, <y,v>, <v,v>, <x,x>, v1 x1, and a, c/d, Y0 + sqrt(Y0^2 + a), sqrt(d) v1 of the reference
     double su_yy, su_yv, su_vv, su_xx, su_vx1, su_v1, su_a, su_cd, su_root, su_rate;
-    static constexpr bool kCompressed = (TEAM == 1) && (SAMPLER == PDMPFLUX_ZIGZAG) && (PATH == kPathFastBrent);
+    static constexpr bool kCompressed = (TEAM == 1 || kTeamSpec) && (SAMPLER == PDMPFLUX_ZIGZAG) && (PATH == kPathFastBrent);
     double cl_al, cl_be;      // compressed line model: sum of A_i, B_i over the coordinates that are active on the whole bracket
     int cl_n;                 // ... number of sign-changing coordinates kept in ca / cb (unused slots hold 0); > kCrossMax: not compressed
     double ca[kCompressed ? kCrossMax : 1], cb[kCompressed ? kCrossMax : 1];   // registers: only indexed by unrolled loops
@@ -227,6 +231,9 @@ struct Chain {
         else return tl + TEAM * j < d;
     }
     __device__ __forceinline__ int coord(int j) const { return tl + TEAM * j; }
+    // coordinate i of this lane's chain, owned or not (TEAM > 1: the chain-contiguous run starts tl elements earlier)
+    __device__ __forceinline__ double x_all(int i) const { return TEAM == 1 ? XS(i) : g_smem[off_x - tl + i]; }
+    __device__ __forceinline__ double v_all(int i) const { return TEAM == 1 ? VS(i) : g_smem[off_v - tl + i]; }
     // f(j) for every owned slot: an unpredicated main loop over the slots every lane owns, then the ragged last slot
     // (U = unroll factor of the main loop: 4 for light bodies, 1 for bodies that draw normals)
     template <int U = 4, class F>
@@ -490,10 +497,10 @@ struct Chain {
                 s = fma(0.5, (c[0] + c[1]) + (c[2] + c[3]), fma(tt, cl_be, cl_al));
             } else {  // more sign changes than the list holds (rare): every coordinate from (x, v)
                 double c0 = 0.0;
-                for (int j = NS; j < nown; ++j) {
-                    const double vi = VS(j);
+                for (int i = NS; i < d; ++i) {
+                    const double vi = v_all(i);
                     double g, hv;
-                    P::eval(p.pot, j, XS(j), vi, Lx, Lv, g, hv);
+                    P::eval(p.pot, i, x_all(i), vi, Lx, Lv, g, hv);
                     const double y = fma(tt, hv * vi, g * vi);
                     c0 += y + fabs(y);
                 }
@@ -549,6 +556,73 @@ struct Chain {
             s = team_sum<TEAM>(s, mask);
             if constexpr (kZZ) return s;
             else return (s > 0.0 ? s : 0.0) + extra_rate();
+        }
+    }
+
+    // rate_unsigned at B times at once (the speculative Brent batches): the same operations in the same order per time
+    // as rate_unsigned(), so the values are bit-identical; the B evaluations are independent instruction streams and
+    // their team reductions travel together.
+    template <int B>
+    __device__ __forceinline__ void rate_unsigned_n(const double (&tt)[B], double (&out)[B]) {
+        if constexpr (kRegLine) {
+            double acc[B][4];
+#pragma unroll
+            for (int b = 0; b < B; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NW; ++j)
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const double y = fma(tt[b], rb[j], ra[j]);
+                    acc[b][j & 3] += y + fabs(y);
+                }
+            double sp_[B], s[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                sp_[b] = 0.0;
+                if constexpr (NS > 0) {
+                    double ys[NS], dys[NS];
+                    special_rates(tt[b], ys, dys);
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) sp_[b] += ys[k] + fabs(ys[k]);
+                    sp_[b] *= 0.5;
+                }
+                s[b] = (acc[b][0] + acc[b][1]) + (acc[b][2] + acc[b][3]);
+            }
+            team_sum_n<TEAM, B>(s, mask);
+#pragma unroll
+            for (int b = 0; b < B; ++b) out[b] = fma(0.5, s[b], sp_[b]);
+        } else if constexpr (kCompressed) {
+            if (cl_n <= kCrossMax) {
+                double c[B][4];
+#pragma unroll
+                for (int b = 0; b < B; ++b) c[b][0] = c[b][1] = c[b][2] = c[b][3] = 0.0;
+#pragma unroll
+                for (int k = 0; k < kCrossMax; ++k)
+#pragma unroll
+                    for (int b = 0; b < B; ++b) {
+                        const double y = fma(tt[b], cb[k], ca[k]);
+                        c[b][k & 3] += y + fabs(y);
+                    }
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    double s = fma(0.5, (c[b][0] + c[b][1]) + (c[b][2] + c[b][3]), fma(tt[b], cl_be, cl_al));
+                    if constexpr (NS > 0) {
+                        double ys[NS], dys[NS];
+                        special_rates(tt[b], ys, dys);
+                        double sp_ = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) sp_ += ys[k] + fabs(ys[k]);
+                        s = fma(0.5, sp_, s);
+                    }
+                    out[b] = s;
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; ++b) out[b] = rate_unsigned(tt[b]);
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < B; ++b) out[b] = rate_unsigned(tt[b]);
         }
     }
 
@@ -968,6 +1042,7 @@ struct Chain {
     // handful of max(0, .) terms instead of a pass over the d coordinates -- and, with a chain per thread, no
     // cross-lane reduction at all.  Same values as the per-coordinate sum up to reassociation.
     __device__ void classify_line(double h) {
+        if constexpr (kTeamSpec) { classify_line_team(h); return; }
         double al = 0.0, be = 0.0;
         int n = 0;
 #pragma unroll
@@ -991,63 +1066,320 @@ struct Chain {
         cl_al = al; cl_be = be; cl_n = n;
     }
 
+    // The same classification with the coordinates spread over the lanes of a team: always-active sums by one team
+    // reduction, the sign-changing coordinates appended to a per-chain list in shared memory (the slots of the A / B
+    // vectors; positions from a ballot) and then read back by every lane into its registers -- afterwards each lane
+    // evaluates the chain's rate on its own.
+    __device__ void classify_line_team(double h) {
+        double ab[2] = {0.0, 0.0};
+        int n = 0;
+        const int tshift = (int)(threadIdx.x & 31u) & ~(TEAM - 1);
+        const unsigned below = (1u << tl) - 1u;
+        for (int j = 0; j < nown; ++j) {
+            double A = 0.0, B = 0.0;
+            if (owns(j) && coord(j) >= NS) {
+                const double vi = VS(j);
+                double g, hv;
+                P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
+                A = g * vi; B = hv * vi;
+            }
+            const double yh = fma(h, B, A);
+            const bool p0 = A > 0.0, ph = yh > 0.0;
+            if (p0 && ph) { ab[0] += A; ab[1] += B; }
+            const bool cr = p0 != ph;
+            const unsigned bal = (__ballot_sync(mask, cr) >> tshift) & ((1u << TEAM) - 1u);
+            if (cr) {
+                const int pos = n + __popc(bal & below);
+                if (pos < kCrossMax) { g_smem[off_a - tl + pos] = A; g_smem[off_b - tl + pos] = B; }
+            }
+            n += __popc(bal);
+        }
+        team_sum_n<TEAM, 2>(ab, mask);
+        __syncwarp(mask);
+#pragma unroll
+        for (int k = 0; k < kCrossMax; ++k) {
+            ca[k] = 0.0; cb[k] = 0.0;
+            if (k < n) { ca[k] = g_smem[off_a - tl + k]; cb[k] = g_smem[off_b - tl + k]; }
+        }
+        __syncwarp(mask);
+        cl_al = ab[0]; cl_be = ab[1]; cl_n = n;
+    }
+
+    // Speculative batches.  A golden-section step that finds a new best point (the only kind of step the monotone
+    // Zig-Zag rates ever produce on the way to an end of the bracket) moves (lo, hi, x) by a rule that does not involve
+    // the function values at all.  So the next kSpecB abscissae are predicted from the bracket alone, the rate is
+    // evaluated at all of them at once (independent instruction streams, one set of team reductions), and the
+    // iterations are then checked side by side against the values: parabola rejected and f(u) < f(x) at every step.
+    // If all hold, the state after kSpecB iterations is exactly what the one-at-a-time recurrence produces -- the same
+    // operations on the same operands -- at about a quarter of its dependent latency, which is what bounds the 4096-chain
+    // configuration (1.7 warps per scheduler).  If any check fails the same iterations are replayed one at a time
+    // (brent_step), reusing the batch's values for as long as the abscissae still agree.
+    struct Brent { double lo, hi, x, w, v, fx, fw, fv, stp, old; };
+    static constexpr double kGolden = 0.3819660112501051;  // (3 - sqrt(5)) / 2
+#ifndef PDMPFLUX_SPEC_B
+#define PDMPFLUX_SPEC_B 4
+#endif
+#ifndef PDMPFLUX_SUPER
+#define PDMPFLUX_SUPER 5
+#endif
+    static constexpr int kSuper = PDMPFLUX_SUPER;   // transposed team Brent: iterations per lane per pass
+    static constexpr int kSpecB = kRegLine ? PDMPFLUX_SPEC_B : 0;   // measured gain only where the team reduction is the latency (+4..13 %); thread-per-chain kernels are issue bound
+
+    // tolerance, midpoint and golden-section abscissa of the iteration that starts from the bracket (lo, hi) and best x
+    __device__ static __forceinline__ double brent_golden(double lo, double hi, double x, double& tol, double& mid,
+                                                          double& og, double& gstp) {
+        tol = __dadd_rn(__dmul_rn(kSqrtEps, fabs(x)), kEps);
+        mid = (hi + lo) * 0.5;                                   // (hi + lo) / 2
+        og = (x < mid) ? hi - x : lo - x;
+        gstp = kGolden * og;
+        return x + ((fabs(gstp) >= tol) ? gstp : ((gstp > 0.0) ? tol : -tol));
+    }
+    // parabola through (x, fx), (w, fw), (v, fv): does the recurrence take it?  Only considered when |old_step| > tol.
+    __device__ static __forceinline__ bool brent_parabola(const Brent& s, double tol, double& pp, double& q) {
+        const double xw = s.x - s.w, xv = s.x - s.v;
+        const double r = xw * (s.fx - s.fv);
+        q = xv * (s.fx - s.fw);
+        pp = __dadd_rn(__dmul_rn(xv, q), -__dmul_rn(xw, r));
+        q = q - r;
+        q = q + q;                                               // 2 (q - r)
+        pp = (q > 0.0) ? -pp : pp;
+        q = fabs(q);                                             // `if q > 0: p = -p else: q = -q`
+        const double hx = s.hi - s.x, xl = s.x - s.lo;
+        return (int)(fabs(s.old) > tol) & (int)(fabs(pp) < fabs(q * s.old * 0.5)) & (int)(pp < q * hx) & (int)(pp < q * xl);
+    }
+    // one iteration; true when the stopping rule fires (state untouched).  With HINT, f(hu) = hf is already known.
+    template <bool HINT>
+    __device__ __forceinline__ bool brent_step(Brent& s, double hu, double hf) {
+        double tol, mid, og, gstp;
+        double u = brent_golden(s.lo, s.hi, s.x, tol, mid, og, gstp);
+        const double tol2 = tol + tol;
+        if (fabs(s.x - mid) <= fma(s.hi - s.lo, -0.5, tol2)) return true;  // 2 tol - (hi - lo) / 2: the halving is exact
+        double pp, q;
+        const bool use_para = brent_parabola(s, tol, pp, q);
+        double new_old = og, new_stp = gstp;
+        if (use_para) {                                          // parabolic step (an IEEE division: 124 cycles)
+            double sp = pp / q;
+            const double xt = s.x + sp;
+            const bool near_end = (int)((xt - s.lo) < tol2) | (int)((s.hi - xt) < tol2);
+            sp = near_end ? ((s.x < mid) ? tol : -tol) : sp;
+            new_old = s.stp; new_stp = sp;
+            u = s.x + ((fabs(sp) >= tol) ? sp : ((sp > 0.0) ? tol : -tol));
+        }
+        s.old = new_old; s.stp = new_stp;
+        double fu;
+        if (HINT && u == hu) fu = hf;
+        else fu = -rate_unsigned(u);
+        // bookkeeping.  A new best point shifts (x, w, v) <- (u, x, w); the other outcomes are a fixed set of selects
+        // on the values before the update.
+        const bool left = u < s.x;
+        if (fu < s.fx) {
+            s.hi = left ? s.x : s.hi;
+            s.lo = left ? s.lo : s.x;
+            s.v = s.w; s.fv = s.fw; s.w = s.x; s.fw = s.fx; s.x = u; s.fx = fu;
+        } else {
+            const bool c1 = (int)(fu <= s.fw) | (int)(s.w == s.x);
+            const bool c2 = (int)(fu <= s.fv) | (int)(s.v == s.x) | (int)(s.v == s.w);
+            s.lo = left ? u : s.lo;
+            s.hi = left ? s.hi : u;
+            const bool v_u = !c1 & c2;
+            s.v = c1 ? s.w : (v_u ? u : s.v);
+            s.fv = c1 ? s.fw : (v_u ? fu : s.fv);
+            s.w = c1 ? u : s.w;
+            s.fw = c1 ? fu : s.fw;
+        }
+        return false;
+    }
+
     __device__ void build_bound_brent(double h) {
         if constexpr (kCompressed) classify_line(h);
-        const double golden = 0.3819660112501051;  // (3 - sqrt(5)) / 2
-        double lo = 0.0, hi = h;
-        double x = __dadd_rn(lo, __dmul_rn(golden, __dadd_rn(hi, -lo)));
-        double fx = -rate_unsigned(x);
-        double stp = 0.0, old_step = 0.0, w = x, vv = x, fw = fx, fv = fx;
-        for (int it = 0; it < 1000; ++it) {
-            const double tol = __dadd_rn(__dmul_rn(kSqrtEps, fabs(x)), kEps);
-            const double tol2 = tol + tol;
-            const double mid = (hi + lo) * 0.5;                      // (hi + lo) / 2
-            if (fabs(x - mid) <= fma(hi - lo, -0.5, tol2)) break;    // 2 tol - (hi - lo) / 2: the halving is exact
-            // parabola through (x, fx), (w, fw), (v, fv); only used when |old_step| > tol
-            const double xw = x - w, xv = x - vv;
-            const double r = xw * (fx - fv);
-            double q = xv * (fx - fw);
-            double pp = __dadd_rn(__dmul_rn(xv, q), -__dmul_rn(xw, r));
-            q = q - r;
-            q = q + q;                                               // 2 (q - r)
-            pp = (q > 0.0) ? -pp : pp;
-            q = fabs(q);                                             // `if q > 0: p = -p else: q = -q`
-            const double hx = hi - x, xl = x - lo;
-            const bool use_para = (int)(fabs(old_step) > tol) & (int)(fabs(pp) < fabs(q * old_step * 0.5)) &
-                                  (int)(pp < q * hx) & (int)(pp < q * xl);
-            // golden-section step
-            const double og = (x < mid) ? hx : -xl;                  // hi - x : lo - x
-            double new_old = og, new_stp = golden * og;
-            if (use_para) {                                          // parabolic step
-                double sp = pp / q;
-                const double xt = x + sp;
-                const bool near_end = (int)((xt - lo) < tol2) | (int)((hi - xt) < tol2);
-                sp = near_end ? ((x < mid) ? tol : -tol) : sp;
-                new_old = stp; new_stp = sp;
+        Brent s;
+        s.lo = 0.0; s.hi = h;
+        s.x = __dadd_rn(s.lo, __dmul_rn(kGolden, __dadd_rn(s.hi, -s.lo)));
+        s.fx = -rate_unsigned(s.x);
+        s.stp = 0.0; s.old = 0.0; s.w = s.x; s.v = s.x; s.fw = s.fx; s.fv = s.fx;
+        if constexpr (kTeamSpec) {
+            // Transposed passes: lane tl of the team takes iterations tl, tl + TEAM, tl + 2 TEAM, ... of the next
+            // kSuper * TEAM iterations -- on BASELINE config C2 a whole bound (36 iterations) is one pass.  While golden
+            // steps keep finding a new best point the search walks towards one end E of the bracket: that end stays,
+            // the other end becomes the previous best point and x <- x + golden (E - x), whatever the function values
+            // are.  Every lane runs this three-operation recurrence through all iterations of the pass, noting the
+            // points of its own ones; then it does ITS iterations in full, side by side -- tolerance, stopping rule,
+            // golden abscissa, the rate there (the compressed line model is complete in every lane: no reduction), the
+            // parabola test with the function values of the three iterations before (fetched from the neighbouring
+            // lanes) -- and checks that each is of the assumed kind.  Ballots decide for the team: the first iteration
+            // whose stopping rule fires ends the search, provided every iteration before it is vouched for by its lane.
+            // Otherwise TEAM iterations are replayed one at a time and the next pass starts from there.  The operations
+            // and operands of every iteration are the one-at-a-time recurrence's, so the result is bit-identical.
+            constexpr int S = kSuper;
+            const int tshift = (int)(threadIdx.x & 31u) & ~(TEAM - 1);
+            const unsigned tbits = (1u << TEAM) - 1u;
+            auto rot = [&](double v, int j) { return __shfl_sync(mask, v, (tl - j) & (TEAM - 1), TEAM); };
+            bool done = false;
+            for (int it = 0; it < 1000 && !done;) {
+                const bool right = s.x < (s.hi + s.lo) * 0.5;
+                const double E = right ? s.hi : s.lo;
+                double X[S], W[S], V[S];
+                {
+                    double mx = s.x, mw = s.w, mv = s.v;
+#pragma unroll
+                    for (int k = 0; k < TEAM - 1; ++k) {
+                        if (k < tl) {
+                            const double u = __dadd_rn(mx, __dmul_rn(kGolden, E - mx));
+                            mv = mw; mw = mx; mx = u;
+                        }
+                    }
+                    __syncwarp(mask);
+                    X[0] = mx; W[0] = mw; V[0] = mv;
+#pragma unroll
+                    for (int b = 1; b < S; ++b) {
+#pragma unroll
+                        for (int k = 0; k < TEAM; ++k) {
+                            const double u = __dadd_rn(mx, __dmul_rn(kGolden, E - mx));
+                            mv = mw; mw = mx; mx = u;
+                        }
+                        X[b] = mx; W[b] = mw; V[b] = mv;
+                    }
+                }
+                double F[S], TOL[S], ulast = 0.0;
+                unsigned long long stopmask = 0ull, goodmask = 0ull;
+                bool asok[S];
+#pragma unroll
+                for (int b = 0; b < S; ++b) {
+                    const bool first = (b == 0) && (tl == 0);
+                    const double moving = first ? (right ? s.lo : s.hi) : W[b];
+                    const double lo_ = right ? moving : s.lo, hi_ = right ? s.hi : moving;
+                    double mid, og, gstp;
+                    const double u = brent_golden(lo_, hi_, X[b], TOL[b], mid, og, gstp);
+                    const bool stop = fabs(X[b] - mid) <= fma(hi_ - lo_, -0.5, TOL[b] + TOL[b]);
+                    asok[b] = ((X[b] < mid) == right) & (fabs(gstp) >= TOL[b]);
+                    F[b] = -rate_unsigned(u);
+                    if (b == S - 1) ulast = u;
+                    stopmask |= (unsigned long long)((__ballot_sync(mask, stop) >> tshift) & tbits) << (TEAM * b);
+                }
+                {
+                    double r1p = 0.0, r2p = 0.0, r3p = 0.0;   // the rotations of the previous block of TEAM iterations
+#pragma unroll
+                    for (int b = 0; b < S; ++b) {
+                        const double r1 = rot(F[b], 1), r2 = rot(F[b], 2), r3 = rot(F[b], 3);
+                        Brent m;
+                        if (b == 0) {
+                            m.fx = tl >= 1 ? r1 : s.fx;
+                            m.fw = tl >= 2 ? r2 : (tl == 1 ? s.fx : s.fw);
+                            m.fv = tl >= 3 ? r3 : (tl == 2 ? s.fx : (tl == 1 ? s.fw : s.fv));
+                        } else {
+                            m.fx = tl >= 1 ? r1 : r1p;
+                            m.fw = tl >= 2 ? r2 : r2p;
+                            m.fv = tl >= 3 ? r3 : r3p;
+                        }
+                        r1p = r1; r2p = r2; r3p = r3;
+                        const bool first = (b == 0) && (tl == 0);
+                        const double moving = first ? (right ? s.lo : s.hi) : W[b];
+                        m.lo = right ? moving : s.lo;
+                        m.hi = right ? s.hi : moving;
+                        m.x = X[b]; m.w = W[b]; m.v = V[b]; m.stp = 0.0;
+                        m.old = first ? s.old : E - W[b];
+                        double pp, qq;
+                        const bool para = brent_parabola(m, TOL[b], pp, qq);
+                        const bool good = !para & (F[b] < m.fx) & asok[b];
+                        goodmask |= (unsigned long long)((__ballot_sync(mask, good) >> tshift) & tbits) << (TEAM * b);
+                    }
+                }
+                constexpr int N = S * TEAM;
+                const int nterm = stopmask ? __ffsll((long long)stopmask) - 1 : N;   // first iteration that stops
+                const int nbad = __ffsll((long long)~goodmask) - 1;                   // first iteration not as assumed (>= N: none)
+                const int nc = min(nterm, min(nbad, N));                              // iterations 0 .. nc-1 stand
+                // value a lane noted for iteration `step` (team-uniform argument)
+                auto at = [&](const double (&arr)[S], int step) {
+                    const int bb = step / TEAM;
+                    double sel = arr[0];
+#pragma unroll
+                    for (int b = 1; b < S; ++b) sel = (bb == b) ? arr[b] : sel;
+                    return team_bcast<TEAM>(sel, step & (TEAM - 1), mask);
+                };
+                it += nc;
+                if (nterm <= nbad && nterm < N) {   // the stopping rule fired: only the best value is needed
+                    if (nterm >= 1) s.fx = at(F, nterm - 1);
+                    done = true;
+                } else {
+                    if (nc >= 1) {                  // the state at the start of iteration nc
+                        const double xn = (nc < N) ? at(X, min(nc, N - 1)) : team_bcast<TEAM>(ulast, TEAM - 1, mask);
+                        const double wn = at(X, nc - 1);
+                        const double vn = nc >= 2 ? at(X, nc - 2) : s.w;
+                        const double f1 = at(F, nc - 1);
+                        const double f2 = nc >= 2 ? at(F, nc - 2) : s.fx;
+                        const double f3 = nc >= 3 ? at(F, nc - 3) : (nc == 2 ? s.fx : s.fw);
+                        s.x = xn; s.w = wn; s.v = vn; s.fx = f1; s.fw = f2; s.fv = f3;
+                        s.lo = right ? wn : s.lo;
+                        s.hi = right ? s.hi : wn;
+                        s.old = E - wn;
+                        s.stp = kGolden * s.old;
+                    }
+                    if (nc < N) {                   // an iteration of another kind: one at a time for a while
+#pragma unroll 1
+                        for (int k = 0; k < TEAM && !done; ++k) {
+                            done = brent_step<false>(s, 0.0, 0.0);
+                            ++it;
+                        }
+                    }
+                }
             }
-            old_step = new_old; stp = new_stp;
-            const double u = x + ((fabs(stp) >= tol) ? stp : ((stp > 0.0) ? tol : -tol));
-            const double fu = -rate_unsigned(u);
-            // bookkeeping.  A new best point shifts (x, w, v) <- (u, x, w): plain register moves behind a branch that is
-            // uniform whenever the chains of the warp agree (always, on the monotone rates of the Zig-Zag
-            // configurations); the other outcomes are a fixed set of selects on the values before the update.
-            const bool left = u < x;
-            if (fu < fx) {
-                hi = left ? x : hi;
-                lo = left ? lo : x;
-                vv = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
-            } else {
-                const bool c1 = (int)(fu <= fw) | (int)(w == x);
-                const bool c2 = (int)(fu <= fv) | (int)(vv == x) | (int)(vv == w);
-                lo = left ? u : lo;
-                hi = left ? hi : u;
-                const bool v_u = !c1 & c2;
-                vv = c1 ? w : (v_u ? u : vv);
-                fv = c1 ? fw : (v_u ? fu : fv);
-                w = c1 ? u : w;
-                fw = c1 ? fu : fw;
+        } else if constexpr (kSpecB > 0) {
+            bool done = false;
+            for (int it = 0; it < 1000 && !done;) {
+                double U[kSpecB], F[kSpecB];
+                {
+                    double pl = s.lo, ph = s.hi, px = s.x;
+#pragma unroll
+                    for (int k = 0; k < kSpecB; ++k) {
+                        double tol, mid, og, gstp;
+                        const double u = brent_golden(pl, ph, px, tol, mid, og, gstp);
+                        U[k] = u;
+                        const bool left = u < px;
+                        ph = left ? px : ph;
+                        pl = left ? pl : px;
+                        px = u;
+                    }
+                }
+                rate_unsigned_n<kSpecB>(U, F);
+#pragma unroll
+                for (int k = 0; k < kSpecB; ++k) F[k] = -F[k];
+                Brent q = s;
+                bool ok = true, term = false;
+                double fterm = s.fx;
+                int nsteps = 0;
+#pragma unroll
+                for (int k = 0; k < kSpecB; ++k) {
+                    double tol, mid, og, gstp, pp, qq;
+                    const double u = brent_golden(q.lo, q.hi, q.x, tol, mid, og, gstp);  // == U[k]
+                    const bool stop = fabs(q.x - mid) <= fma(q.hi - q.lo, -0.5, tol + tol);
+                    fterm = (!term && stop) ? q.fx : fterm;
+                    term |= stop;
+                    const bool para = brent_parabola(q, tol, pp, qq);
+                    ok &= term | (!para & (F[k] < q.fx));
+                    nsteps += term ? 0 : 1;
+                    const bool left = u < q.x;
+                    q.hi = left ? q.x : q.hi;
+                    q.lo = left ? q.lo : q.x;
+                    q.v = q.w; q.fv = q.fw; q.w = q.x; q.fw = q.fx; q.x = u; q.fx = F[k];
+                    q.old = og; q.stp = gstp;
+                }
+                if (ok) {
+                    it += nsteps;
+                    if (term) { s.fx = fterm; done = true; }
+                    else s = q;
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < kSpecB && !done; ++k) {
+                        done = brent_step<true>(s, U[k], F[k]);
+                        ++it;
+                    }
+                }
             }
+        } else {
+            for (int it = 0; it < 1000; ++it)
+                if (brent_step<false>(s, 0.0, 0.0)) break;
         }
+        const double fx = s.fx;
         BOX(0) = -fx + 0.0;  // init_state passes no refresh here (AbstractPDMP.jl:122-125)
         CUM(0) = 0.0; CUM(1) = BOX(0) * (h - 0.0);
         step = h - 0.0;
@@ -1998,7 +2330,7 @@ __global__ void __launch_bounds__(block_threads_rt(TEAM, SAMPLER, PATH), PATH ==
     ch.off_v = vec + toff;
     int used = 2;
     ch.off_a = ch.off_b = 0;
-    if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent && NW == 0 && TEAM > 1) {
+    if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && PATH == kPathFastBrent && NW <= 0 && TEAM > 1) {
         ch.off_a = 2 * vec + toff;
         ch.off_b = 3 * vec + toff;
         used = 4;

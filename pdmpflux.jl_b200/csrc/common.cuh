@@ -89,6 +89,7 @@ struct KernelParams {
     double* scratch;
     int scratch_in_smem;
     int n_own;      // ceil(d / TEAM)
+    int brent_nw;   // Zig-Zag x Brent: the kernel variant chosen at chains_create (launch.cuh, brent_reg_nw)
     int vec_elems;  // doubles per shared-memory state vector of a block (x, v, A, B, scratch each take one)
     int dpad;       // TEAM > 1: doubles reserved per chain inside a state vector (chain-contiguous layout)
     // output path

@@ -1,14 +1,25 @@
 // Host-side dispatch from (team width, potential kind) to a kernel instantiation.
 #pragma once
+#include <cstdlib>
+
 #include "chain.cuh"
 
 namespace pdmpflux {
 
-// Zig-Zag + Brent: capacity of the register-resident line model (0: the shared-memory A/B arrays are used).
-// Mirrors the instantiations below; api.cu sizes the shared memory with it.
+// Zig-Zag + Brent on a team of lanes: which line model the kernel keeps (the NW template argument).
+//   -1  transposed Brent: teams of 8 with at most 8 owned coordinates per lane (d <= 64) -- every lane keeps the chain's
+//       compressed model and takes its own iterations of the search (chain.cuh, build_bound_brent)
+//   8 / 16  register-resident (A_j, B_j) of the owned coordinates, team reduction per rate evaluation
+//   0   the shared-memory A/B arrays
+// Mirrors the instantiations below; api.cu sizes the shared memory with it.  PDMPFLUX_TSPEC=0 switches the transposed
+// search off (the tests compare the two).
 inline int brent_reg_nw(int sampler, int path, int team, int n_own) {
     if (sampler != PDMPFLUX_ZIGZAG || path != kPathFastBrent) return 0;
     if (team != 4 && team != 8) return 0;
+    if (team == 8 && n_own <= 8) {
+        const char* e = std::getenv("PDMPFLUX_TSPEC");
+        if (!e || std::atoi(e) != 0) return -1;
+    }
     return n_own <= 8 ? 8 : (n_own <= 16 ? 16 : 0);
 }
 
@@ -34,7 +45,7 @@ template <int TEAM, int SAMPLER, int POT>
 cudaError_t launch_for_pot(int path, const KernelParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
     if constexpr (TEAM == 4) {  // only built for the register-resident Zig-Zag x Brent kernels
         if constexpr (SAMPLER == PDMPFLUX_ZIGZAG && Pot<POT>::kAffine) {
-            switch (brent_reg_nw(SAMPLER, path, TEAM, p.n_own)) {
+            switch (p.brent_nw) {
             case 8: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 8>(p, grid, smem, stream);
             case 16: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 16>(p, grid, smem, stream);
             }
@@ -45,7 +56,8 @@ cudaError_t launch_for_pot(int path, const KernelParams& p, unsigned grid, size_
         case kPathGeneric: return launch_one<TEAM, SAMPLER, POT, kPathGeneric>(p, grid, smem, stream);
         case kPathFastBrent:
             if constexpr (TEAM == 8 && SAMPLER == PDMPFLUX_ZIGZAG && Pot<POT>::kAffine) {
-                switch (brent_reg_nw(SAMPLER, path, TEAM, p.n_own)) {
+                switch (p.brent_nw) {
+                case -1: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, -1>(p, grid, smem, stream);
                 case 8: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 8>(p, grid, smem, stream);
                 case 16: return launch_one<TEAM, SAMPLER, POT, kPathFastBrent, 16>(p, grid, smem, stream);
                 }

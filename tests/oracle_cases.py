@@ -13,6 +13,14 @@ CASES = [
     ("zz_gauss_scalar_fd", ZIGZAG, GAUSS_STD, None, 3, dict(vectorized_bound=False, deriv_mode=1, grid_size=4), 600),
     ("zz_gauss1d_g2", ZIGZAG, GAUSS_STD, None, 1, dict(grid_size=2, tmax=0.0), 600),
     ("zz_banana50_brent", ZIGZAG, BANANA, None, 50, dict(grid_size=0), 1000),
+    # more Brent brackets: rates that fall towards the far end of the bracket (the search walks left, ~70 iterations) and
+    # fixed horizons
+    ("zz_diag33_brent", ZIGZAG, GAUSS_DIAG, "linspace", 33, dict(grid_size=0), 600),
+    ("zz_gauss12_brent_nonadaptive", ZIGZAG, GAUSS_STD, None, 12, dict(grid_size=0, adaptive=False, tmax=0.7), 600),
+    # a saddle (half of the curvatures negative): coordinate rates that fall along the flow, so the total rate is not
+    # monotone on the bracket and Brent's search changes direction, fails golden steps and ends at either end -- every
+    # branch of the speculative search is exercised.  (Not a distribution; the short run stays finite.)
+    ("zz_saddle20_brent", ZIGZAG, GAUSS_DIAG, "mixed_sign", 20, dict(grid_size=0, tmax=0.5), 250),
     ("zz_banana5_grid_fd", ZIGZAG, BANANA, None, 5, dict(grid_size=8, deriv_mode=1), 1000),
     ("zz_banana40_jvp", ZIGZAG, BANANA, None, 40, dict(grid_size=6), 800),
     ("zz_readme_scalar", ZIGZAG, BANANA_README, None, 6, dict(grid_size=0), 7),
@@ -53,6 +61,8 @@ def logreg_data(n, d, seed=2024, sigma0=10.0):
 def pot_params(pp, d):
     if isinstance(pp, str) and pp == "linspace":
         return np.linspace(0.5, 2.0, d)
+    if isinstance(pp, str) and pp == "mixed_sign":   # saddle: every other coordinate has negative curvature
+        return np.where(np.arange(d) % 2 == 0, 1.0, -1.0) * np.linspace(0.5, 2.0, d)
     if isinstance(pp, str) and pp.startswith("logreg:"):
         X, y, s0 = logreg_data(int(pp.split(":")[1]), d)
         return np.concatenate([[float(X.shape[0]), s0], X.ravel(), y])

@@ -66,12 +66,19 @@ def set_team(team):
 
 
 @pytest.mark.parametrize("generic", [0, 1], ids=["auto", "generic"])
-@pytest.mark.parametrize("team", [1, 4, 8, 32])
+@pytest.mark.parametrize("team", [1, 4, 8, 32, "8r"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_one_step_parity(p, case, team, generic):
     """`auto` runs the path the library picks (affine fast paths where they exist); `generic` forces the
-    per-node generic kernel on the same case, so both implementations are held to the oracle."""
+    per-node generic kernel on the same case, so both implementations are held to the oracle.  Team "8r": teams of 8
+    with the transposed Brent search switched off (the register-resident line model the library uses for 64 < d <= 128)."""
     name, sampler, pk, pp, d, kw, n_sk = case
+    zz_brent_affine = sampler == 0 and kw.get("grid_size", 10) == 0 and pk in (0, 1, 2, 3) and not generic
+    tspec_off = team == "8r"
+    if tspec_off:
+        if not zz_brent_affine:
+            pytest.skip("only the Zig-Zag x Brent fast path has two team-of-8 variants")
+        team = 8
     if team == 4 and not (sampler == 0 and kw.get("grid_size", 10) == 0 and pk in (0, 1, 2, 3) and not generic):
         pytest.skip("teams of 4 are built for the register-resident Zig-Zag x Brent kernels only")
     if generic and team != 8:
@@ -96,12 +103,17 @@ def test_one_step_parity(p, case, team, generic):
     s = make_sampler(p, sampler, pk, pp, d, kw)
     set_team(team)
     os.environ["PDMPFLUX_FORCE_GENERIC"] = str(generic)
+    if tspec_off:
+        os.environ["PDMPFLUX_TSPEC"] = "0"
     try:
         h = p.sample_skeleton(s, 2, r.X[0, :-1], r.V[0, :-1], tape=(tE, tU, tN), t0=r.t[0, :-1],
                               horizon0=r.horizon[0, :-1], batch=True)
     finally:
         set_team(None)
         os.environ.pop("PDMPFLUX_FORCE_GENERIC")
+        os.environ.pop("PDMPFLUX_TSPEC", None)
+    if tspec_off:
+        team = "8r"
     tol = tier_tolerance(kw)
     assert np.array_equal(h.X[:, 0], r.X[0, :-1]) and np.array_equal(h.t[:, 0], r.t[0, :-1])
     scale_x = np.maximum(np.abs(r.X[0, 1:]).max(axis=1), 1e-300)
