@@ -145,16 +145,16 @@ int pick_team(int d, int64_t n_chains, bool zz_brent_fast, int sampler) {
     // SMs; 8 lanes per chain win for d up to a few hundred (fewer shuffle stages than a full warp, 4 chains share a
     // warp's instruction stream); a warp per chain beyond that (and whenever the shared-memory state would not fit).
     if (d <= 16) return n_chains >= 8192 ? 1 : 8;
-    // Zig-Zag x Brent with a chain per thread: the rate function is compressed per bracket to one line plus the few
-    // sign-changing coordinates (chain.cuh: classify_line), so the serial Brent recurrence runs without any cross-lane
-    // reduction and 32 chains share every instruction; wins at every chain count once x and v fit in shared memory.
-    if (zz_brent_fast && d <= 64 && n_chains >= 8192) return 1;
+    // Zig-Zag x Brent: the rate function is compressed per bracket to one line plus the few sign-changing coordinates
+    // (chain.cuh: classify_line).  With a chain per thread the serial Brent recurrence runs without any cross-lane
+    // reduction and 32 chains share every instruction: 4.9e8 events/s at 16384 chains, 9e8 at 65536 (banana d = 50).
+    // Below ~10k chains there are too few warps for that, and teams of 8 running the transposed search (each lane its
+    // own iterations, one pass per bound) are ahead: 3.1e8 at 4096 and at 8192 chains against 2.5e8 thread-per-chain
+    // at 8192.
+    if (zz_brent_fast && d <= 64 && n_chains >= 10240) return 1;
     // (A chain per thread does NOT pay for BPS / Boomerang at d ~ 100 -- measured 1.1e8 events/s against 3.4e8 with
     // teams of 8 on BASELINE config 3: a refresh draws d normals, and with 32 chains per warp some lane refreshes in
     // almost every event, so the whole warp pays the d-normal pass every time.)
-    // (Measured on the way there, B200, banana d = 50: teams of 8 with the line model in registers 1.9e8 events/s at
-    // 4096 chains and 2.3e8 at 65536; teams of 4 1.7e8 / 3.6e8 -- both issue bound by the Brent bookkeeping that every
-    // lane of a team repeats.  PDMPFLUX_TEAM=4 / 8 still select them.)
     if (d <= 256) return 8;
     return 32;
 }

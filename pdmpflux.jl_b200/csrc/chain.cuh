@@ -1072,27 +1072,42 @@ struct Chain {
     // evaluates the chain's rate on its own.
     __device__ void classify_line_team(double h) {
         double ab[2] = {0.0, 0.0};
-        int n = 0;
-        const int tshift = (int)(threadIdx.x & 31u) & ~(TEAM - 1);
-        const unsigned below = (1u << tl) - 1u;
+        // first pass: the lane's own coordinates -- sums of the always-active ones, how many change sign
+        int mine = 0;
         for (int j = 0; j < nown; ++j) {
-            double A = 0.0, B = 0.0;
             if (owns(j) && coord(j) >= NS) {
                 const double vi = VS(j);
                 double g, hv;
                 P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
-                A = g * vi; B = hv * vi;
+                const double A = g * vi, B = hv * vi;
+                const bool p0 = A > 0.0, ph = fma(h, B, A) > 0.0;
+                if (p0 && ph) { ab[0] += A; ab[1] += B; }
+                mine += (p0 != ph) ? 1 : 0;
             }
-            const double yh = fma(h, B, A);
-            const bool p0 = A > 0.0, ph = yh > 0.0;
-            if (p0 && ph) { ab[0] += A; ab[1] += B; }
-            const bool cr = p0 != ph;
-            const unsigned bal = (__ballot_sync(mask, cr) >> tshift) & ((1u << TEAM) - 1u);
-            if (cr) {
-                const int pos = n + __popc(bal & below);
-                if (pos < kCrossMax) { g_smem[off_a - tl + pos] = A; g_smem[off_b - tl + pos] = B; }
+        }
+        // list positions: exclusive scan of the counts over the lanes (shuffles; see team_or about ballots)
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < TEAM; o <<= 1) {
+            const int up = __shfl_up_sync(mask, incl, o, TEAM);
+            if (tl >= o) incl += up;
+        }
+        const int n = __shfl_sync(mask, incl, TEAM - 1, TEAM);
+        if (mine > 0) {   // second pass over the same coordinates (same operations: same classification)
+            int pos = incl - mine;
+            for (int j = 0; j < nown; ++j) {
+                if (owns(j) && coord(j) >= NS) {
+                    const double vi = VS(j);
+                    double g, hv;
+                    P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
+                    const double A = g * vi, B = hv * vi;
+                    const bool p0 = A > 0.0, ph = fma(h, B, A) > 0.0;
+                    if (p0 != ph) {
+                        if (pos < kCrossMax) { g_smem[off_a - tl + pos] = A; g_smem[off_b - tl + pos] = B; }
+                        ++pos;
+                    }
+                }
             }
-            n += __popc(bal);
         }
         team_sum_n<TEAM, 2>(ab, mask);
         __syncwarp(mask);
@@ -1206,13 +1221,11 @@ struct Chain {
             // points of its own ones; then it does ITS iterations in full, side by side -- tolerance, stopping rule,
             // golden abscissa, the rate there (the compressed line model is complete in every lane: no reduction), the
             // parabola test with the function values of the three iterations before (fetched from the neighbouring
-            // lanes) -- and checks that each is of the assumed kind.  Ballots decide for the team: the first iteration
+            // lanes) -- and checks that each is of the assumed kind.  The team's votes decide: the first iteration
             // whose stopping rule fires ends the search, provided every iteration before it is vouched for by its lane.
             // Otherwise TEAM iterations are replayed one at a time and the next pass starts from there.  The operations
             // and operands of every iteration are the one-at-a-time recurrence's, so the result is bit-identical.
             constexpr int S = kSuper;
-            const int tshift = (int)(threadIdx.x & 31u) & ~(TEAM - 1);
-            const unsigned tbits = (1u << TEAM) - 1u;
             auto rot = [&](double v, int j) { return __shfl_sync(mask, v, (tl - j) & (TEAM - 1), TEAM); };
             bool done = false;
             for (int it = 0; it < 1000 && !done;) {
@@ -1254,7 +1267,7 @@ struct Chain {
                     asok[b] = ((X[b] < mid) == right) & (fabs(gstp) >= TOL[b]);
                     F[b] = -rate_unsigned(u);
                     if (b == S - 1) ulast = u;
-                    stopmask |= (unsigned long long)((__ballot_sync(mask, stop) >> tshift) & tbits) << (TEAM * b);
+                    stopmask |= (unsigned long long)(stop ? 1u : 0u) << (TEAM * b + tl);   // my bits; merged below
                 }
                 {
                     double r1p = 0.0, r2p = 0.0, r3p = 0.0;   // the rotations of the previous block of TEAM iterations
@@ -1281,9 +1294,11 @@ struct Chain {
                         double pp, qq;
                         const bool para = brent_parabola(m, TOL[b], pp, qq);
                         const bool good = !para & (F[b] < m.fx) & asok[b];
-                        goodmask |= (unsigned long long)((__ballot_sync(mask, good) >> tshift) & tbits) << (TEAM * b);
+                        goodmask |= (unsigned long long)(good ? 1u : 0u) << (TEAM * b + tl);
                     }
                 }
+                stopmask = team_or64<TEAM>(stopmask, mask);
+                goodmask = team_or64<TEAM>(goodmask, mask);
                 constexpr int N = S * TEAM;
                 const int nterm = stopmask ? __ffsll((long long)stopmask) - 1 : N;   // first iteration that stops
                 const int nbad = __ffsll((long long)~goodmask) - 1;                   // first iteration not as assumed (>= N: none)
@@ -1441,8 +1456,7 @@ struct Chain {
             int first = -1;
             if constexpr (TEAM == 1) first = hit ? 0 : -1;
             else {
-                unsigned b = __ballot_sync(mask, hit) & mask;
-                b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
+                const unsigned b = team_ballot<TEAM>(hit, tl, mask);
                 first = b ? (__ffs(b) - 1) : -1;
             }
             if (first >= 0) { m = first + TEAM * j; break; }
@@ -1810,8 +1824,7 @@ struct Chain {
             const double incl = team_scan_incl<TEAM>(tot, mask, tl);
             double excl = __shfl_up_sync(mask, incl, 1, TEAM);
             if (tl == 0) excl = 0.0;
-            unsigned b = __ballot_sync(mask, (i0 < i1) && (incl > uS)) & mask;
-            b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
+            const unsigned b = team_ballot<TEAM>((i0 < i1) && (incl > uS), tl, mask);
             const int first = b ? (__ffs(b) - 1) : -1;
             if (first < 0) {  // rounding left the total below u S: the reference's scan ends on the last index
                 if (tl == (d - 1) / nown) g_smem[cbv + d - 1] = -g_smem[cbv + d - 1];
@@ -2021,8 +2034,7 @@ struct Chain {
             const bool hit = owns(j) && ACS(j) == 0.0 && (incl >= u);
             if constexpr (TEAM == 1) { if (hit) m = j; }
             else {
-                unsigned b = __ballot_sync(mask, hit) & mask;
-                b >>= ((threadIdx.x & 31u) & ~(unsigned)(TEAM - 1));
+                const unsigned b = team_ballot<TEAM>(hit, tl, mask);
                 if (b) m = (__ffs(b) - 1) + TEAM * j;
             }
             carry = team_bcast<TEAM>(incl, TEAM - 1, mask);
@@ -2058,7 +2070,7 @@ struct Chain {
                     const double xj = XS(j);
                     crossed = crossed || (xj * (xj + VU(j) * event_time) < 0);
                 });
-                if constexpr (TEAM > 1) crossed = (__ballot_sync(mask, crossed) & mask) != 0u;
+                if constexpr (TEAM > 1) crossed = team_ballot<TEAM>(crossed, tl, mask) != 0u;
                 if (crossed) {
                     sticky_move_to_axes_and_stick();
                     stick = true;

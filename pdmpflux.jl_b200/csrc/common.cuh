@@ -160,6 +160,29 @@ __device__ __forceinline__ double team_scan_incl(double v, unsigned mask, int tl
     return v;
 }
 
+// Team vote without vote.sync: a ballot whose member mask differs between the teams of a warp is compiled into a loop
+// over the distinct masks (MATCH.ANY + REDUX + one VOTE per team: ~100 extra warp instructions per event and a fifth
+// of the stall samples on the Zig-Zag x Brent kernel); an OR butterfly over the team's lanes is three shuffles.
+template <int TEAM>
+__device__ __forceinline__ unsigned team_or(unsigned v, unsigned mask) {
+#pragma unroll
+    for (int o = TEAM / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <int TEAM>
+__device__ __forceinline__ unsigned long long team_or64(unsigned long long v, unsigned mask) {
+#pragma unroll
+    for (int o = TEAM / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(mask, v, o);
+    return v;
+}
+// bit tl of the result = pred of team lane tl (what ballot >> team shift gives)
+template <int TEAM>
+__device__ __forceinline__ unsigned team_ballot(bool pred, int tl, unsigned mask) {
+    if constexpr (TEAM == 1) return pred ? 1u : 0u;
+    else if constexpr (TEAM == 32) return __ballot_sync(0xffffffffu, pred);   // one mask for the whole warp: a plain VOTE
+    else return team_or<TEAM>(pred ? (1u << tl) : 0u, mask);
+}
+
 template <int TEAM>
 __device__ __forceinline__ double team_bcast(double v, int src_tl, unsigned mask) {
     if constexpr (TEAM == 1) return v;

@@ -38,7 +38,7 @@ def run(name, mk, d, nch, n_sk, team=None, unit=False, **env):
 
 for team in (1, 4, 8, 32):
     run(f"zz_brent_banana_t{team}", lambda: p.ZigZag(50, p.Banana(), grid_size=0), 50, 37, 9, team)
-run("zz_brent_thread_per_chain_auto", lambda: p.ZigZag(33, p.GaussDiag(np.linspace(0.5, 2, 33)), grid_size=0), 33, 8200, 4)
+run("zz_brent_thread_per_chain_auto", lambda: p.ZigZag(33, p.GaussDiag(np.linspace(0.5, 2, 33)), grid_size=0), 33, 10300, 4)
 run("zz_grid_t1", lambda: p.ZigZagAD(10, p.GaussStd()), 10, 70, 11, 1)
 run("zz_grid_t8_equi", lambda: p.ZigZagAD(33, p.GaussEquicorr(0.5)), 33, 13, 9, 8)
 run("zz_generic_readme", lambda: p.ZigZag(6, p.BananaReadmeScalar(), grid_size=0), 6, 5, 6)
