@@ -93,7 +93,7 @@ def case_inputs(name, sampler, d, n_sk, n_chains=1, seed=0):
 def tier_tolerance(kw, base=1e-10):
     """Parity tiers.  Everything with an analytic derivative -- grid bounds AND the constant
     (Brent) bound -- is held to `base`, the north_star's 1e-10: the Brent recurrence is evaluated without
-    multiply-add contraction, i.e. with the reference's roundings, and the achieved one-step errors are <= 4e-14
+    multiply-add contraction, i.e. with the reference's roundings, and the achieved one-step errors are <= 5.1e-14
     (profiles/r2_parity_errors.json).  Only the sqrt(eps) finite-difference derivative mode keeps a looser tier:
     dividing O(1e-16) summation-order differences by h = sqrt(eps) leaves ~1e-8 in the derivative (measured worst
     case 1.6e-8, zz_banana5_grid_fd; the two CPU restatements differ by the same amount), so it is held to 1e-6 and
