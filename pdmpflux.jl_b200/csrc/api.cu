@@ -597,6 +597,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
     ch->brent_nw = brent_reg_nw(s->kind, ch->path, ch->team, ch->n_own);
     const size_t nvec = (s->kind == PDMPFLUX_ZIGZAG && ch->path == kPathFastBrent && ch->team > 1 && ch->brent_nw <= 0) ? 4 : 2;
     ch->smem = (nvec + (s->kind == PDMPFLUX_STICKY_ZIGZAG ? 1 : 0)) * vec_bytes;
+    const size_t list_slack = ch->brent_nw < 0 ? 16 * sizeof(double) : 0;   // transposed Brent: unconditional reads of the 12-slot list
     if (s->kind == PDMPFLUX_FECMC) {
         if ((nvec + 3) * vec_bytes <= 64 * 1024) { ch->scratch_in_smem = 1; ch->smem = (nvec + 3) * vec_bytes; }
         else {
@@ -616,6 +617,7 @@ int pdmpflux_chains_create(pdmpflux_sampler_t s, int64_t n_chains, const double*
         const size_t gb = s->cfg.grid_size > 2 ? s->cfg.grid_size : 2;      // box_max / cum_sum, one copy per chain
         ch->smem += (ch->team == 1 ? (size_t)bt : (size_t)cpb) * 2 * gb * sizeof(double);
     }
+    ch->smem += list_slack;
     if (logreg) {  // logreg_chains_per_block() chains per CTA, one warp each
         const int lcpb = logreg_chains_per_block();
         ch->grid = (unsigned)((n_chains + lcpb - 1) / lcpb);

@@ -1072,7 +1072,9 @@ struct Chain {
     // evaluates the chain's rate on its own.
     __device__ void classify_line_team(double h) {
         double ab[2] = {0.0, 0.0};
-        // first pass: the lane's own coordinates -- sums of the always-active ones, how many change sign
+        // the lane's own coordinates: sums of the always-active ones; the sign-changing ones (seldom more than three
+        // of a lane's <= 8) wait in registers for their list positions
+        double qa0 = 0.0, qa1 = 0.0, qa2 = 0.0, qb0 = 0.0, qb1 = 0.0, qb2 = 0.0;
         int mine = 0;
         for (int j = 0; j < nown; ++j) {
             if (owns(j) && coord(j) >= NS) {
@@ -1082,10 +1084,14 @@ struct Chain {
                 const double A = g * vi, B = hv * vi;
                 const bool p0 = A > 0.0, ph = fma(h, B, A) > 0.0;
                 if (p0 && ph) { ab[0] += A; ab[1] += B; }
-                mine += (p0 != ph) ? 1 : 0;
+                else if (p0 != ph) {
+                    qa2 = qa1; qa1 = qa0; qa0 = A;
+                    qb2 = qb1; qb1 = qb0; qb0 = B;
+                    ++mine;
+                }
             }
         }
-        // list positions: exclusive scan of the counts over the lanes (shuffles; see team_or about ballots)
+        // list positions: exclusive scan of the counts over the lanes (shuffles; see team_ballot about ballots)
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < TEAM; o <<= 1) {
@@ -1093,8 +1099,13 @@ struct Chain {
             if (tl >= o) incl += up;
         }
         const int n = __shfl_sync(mask, incl, TEAM - 1, TEAM);
-        if (mine > 0) {   // second pass over the same coordinates (same operations: same classification)
-            int pos = incl - mine;
+        const int ia = off_a - tl, ib = off_b - tl;   // the chain's list: slots 0 .. kCrossMax-1 of its A / B vectors
+        int pos = incl - mine;
+        if (mine <= 3) {
+            if (mine > 0 && pos < kCrossMax) { g_smem[ia + pos] = qa0; g_smem[ib + pos] = qb0; }
+            if (mine > 1 && pos + 1 < kCrossMax) { g_smem[ia + pos + 1] = qa1; g_smem[ib + pos + 1] = qb1; }
+            if (mine > 2 && pos + 2 < kCrossMax) { g_smem[ia + pos + 2] = qa2; g_smem[ib + pos + 2] = qb2; }
+        } else {  // more than the registers hold: a second pass over the same coordinates (same operations)
             for (int j = 0; j < nown; ++j) {
                 if (owns(j) && coord(j) >= NS) {
                     const double vi = VS(j);
@@ -1103,7 +1114,7 @@ struct Chain {
                     const double A = g * vi, B = hv * vi;
                     const bool p0 = A > 0.0, ph = fma(h, B, A) > 0.0;
                     if (p0 != ph) {
-                        if (pos < kCrossMax) { g_smem[off_a - tl + pos] = A; g_smem[off_b - tl + pos] = B; }
+                        if (pos < kCrossMax) { g_smem[ia + pos] = A; g_smem[ib + pos] = B; }
                         ++pos;
                     }
                 }
@@ -1111,10 +1122,13 @@ struct Chain {
         }
         team_sum_n<TEAM, 2>(ab, mask);
         __syncwarp(mask);
+        // every lane reads the whole list (unconditional loads: api.cu leaves kCrossMax doubles of slack behind the
+        // vectors; slots >= n hold stale values and are replaced by A = B = 0)
 #pragma unroll
         for (int k = 0; k < kCrossMax; ++k) {
-            ca[k] = 0.0; cb[k] = 0.0;
-            if (k < n) { ca[k] = g_smem[off_a - tl + k]; cb[k] = g_smem[off_b - tl + k]; }
+            const double a_ = g_smem[ia + k], b_ = g_smem[ib + k];
+            ca[k] = k < n ? a_ : 0.0;
+            cb[k] = k < n ? b_ : 0.0;
         }
         __syncwarp(mask);
         cl_al = ab[0]; cl_be = ab[1]; cl_n = n;
