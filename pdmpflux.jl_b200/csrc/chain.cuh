@@ -2178,20 +2178,39 @@ struct Chain {
         fcnt = fskip = (int)((r0 * d) & 3);
     }
 
-    __device__ __forceinline__ void row_group_tm1(double* G, int64_t gfirst, int q, int r, int off_src, int off_carry) {
-        // group q of the combined stream (carry[0..r) ++ row): positions 4q .. 4q+3
-        double vq[4];
+    // TEAM == 1: the ng complete 32-byte groups of the stream (carry[0..R) ++ row) of one thread's chain.  R is a
+    // template argument so that which element comes from the carry and which from the row is decided at compile time:
+    // a group is four shared-memory loads with immediate offsets and one 256-bit store (the run-time variant spent a
+    // compare, an address select and a load per element: 6.5 % of config C1's instructions).
+    template <int R>
+    __device__ __forceinline__ void row_groups_tm1(double* G, int64_t gfirst, int ng, int off_src, int off_carry) {
+        if (ng <= 0) return;
+        double* dst = G + gfirst;
+        {
+            double vq[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int pos = 4 * q + k;
-            vq[k] = pos < r ? g_smem[off_carry + pos * kBT] : g_smem[off_src + (pos - r) * kBT];
+            for (int k = 0; k < 4; ++k) vq[k] = k < R ? g_smem[off_carry + k * kBT] : g_smem[off_src + (k - R) * kBT];
+            if (fskip > 0) {  // first group of this launch starts mid-sector: scalar stores for the real part
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k >= fskip) dst[k] = vq[k];
+            } else st256(dst, vq[0], vq[1], vq[2], vq[3]);
         }
-        double* dst = G + gfirst + 4 * q;
-        if (q == 0 && fskip > 0) {  // first group of this launch starts mid-sector: scalar stores for the real part
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k >= fskip) dst[k] = vq[k];
-        } else st256(dst, vq[0], vq[1], vq[2], vq[3]);
+        int o = off_src + (4 - R) * kBT;
+#pragma unroll 2
+        for (int q = 1; q < ng; ++q) {
+            dst += 4;
+            st256(dst, g_smem[o], g_smem[o + kBT], g_smem[o + 2 * kBT], g_smem[o + 3 * kBT]);
+            o += 4 * kBT;
+        }
+    }
+    __device__ __forceinline__ void row_stream_tm1(double* G, int64_t gfirst, int ng, int r, int off_src, int off_carry) {
+        switch (r) {
+        case 0: row_groups_tm1<0>(G, gfirst, ng, off_src, off_carry); break;
+        case 1: row_groups_tm1<1>(G, gfirst, ng, off_src, off_carry); break;
+        case 2: row_groups_tm1<2>(G, gfirst, ng, off_src, off_carry); break;
+        default: row_groups_tm1<3>(G, gfirst, ng, off_src, off_carry); break;
+        }
     }
 
     __device__ void record(int64_t c, int64_t col) {
@@ -2222,10 +2241,8 @@ struct Chain {
                 const int total = r + d;
                 const int ng = total >> 2;
                 const int64_t gfirst = orow * d - r;    // 4-aligned element index of the combined stream's start
-                if (p.X)
-                    for (int q = 0; q < ng; ++q) row_group_tm1(p.X, gfirst, q, r, off_x, off_f);
-                if (p.V)
-                    for (int q = 0; q < ng; ++q) row_group_tm1(p.V, gfirst, q, r, off_v, off_f + 3 * kBT);
+                if (p.X) row_stream_tm1(p.X, gfirst, ng, r, off_x, off_f);
+                if (p.V) row_stream_tm1(p.V, gfirst, ng, r, off_v, off_f + 3 * kBT);
                 const int rem = total - 4 * ng;
                 if (ng > 0) {
                     for (int k = 0; k < rem; ++k) {  // tail of the row becomes the next carry
