@@ -17,6 +17,10 @@ CASES = [
     # fixed horizons
     ("zz_diag33_brent", ZIGZAG, GAUSS_DIAG, "linspace", 33, dict(grid_size=0), 600),
     ("zz_gauss12_brent_nonadaptive", ZIGZAG, GAUSS_STD, None, 12, dict(grid_size=0, adaptive=False, tmax=0.7), 600),
+    # the ends of the transposed team search's range: 3 coordinates (five of a team's eight lanes own nothing) and 64
+    # (eight owned coordinates per lane, more sign changes per bracket than the 12-slot list holds now and then)
+    ("zz_gauss3_brent", ZIGZAG, GAUSS_STD, None, 3, dict(grid_size=0), 400),
+    ("zz_diag64_brent", ZIGZAG, GAUSS_DIAG, "linspace", 64, dict(grid_size=0, tmax=4.0), 300),
     # a saddle (half of the curvatures negative): coordinate rates that fall along the flow, so the total rate is not
     # monotone on the bracket and Brent's search changes direction, fails golden steps and ends at either end -- every
     # branch of the speculative search is exercised.  (Not a distribution; the short run stays finite.)
