@@ -41,7 +41,7 @@ for team in (1, 4, 8, 32):
 run("zz_brent_thread_per_chain_auto", lambda: p.ZigZag(33, p.GaussDiag(np.linspace(0.5, 2, 33)), grid_size=0), 33, 10300, 4)
 run("zz_grid_t1", lambda: p.ZigZagAD(10, p.GaussStd()), 10, 70, 11, 1)
 run("zz_grid_t8_equi", lambda: p.ZigZagAD(33, p.GaussEquicorr(0.5)), 33, 13, 9, 8)
-run("zz_generic_readme", lambda: p.ZigZag(6, p.BananaReadmeScalar(), grid_size=0), 6, 5, 6)
+run("zz_generic_fd", lambda: p.ZigZag(6, p.Banana(), grid_size=8), 6, 5, 6)  # finite differences: generic path
 run("bps_t8", lambda: p.BPS(100, p.GaussEquicorr(0.9)), 100, 19, 9, 8, unit=True)
 run("bps_t1", lambda: p.BPS(7, p.GaussStd(), refresh_rate=0.5), 7, 33, 9, 1, unit=True)
 run("fecmc_t32", lambda: p.ForwardECMC(1000, p.GaussStd()), 1000, 5, 5, 32, unit=True)
