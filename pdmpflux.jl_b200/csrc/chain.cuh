@@ -1507,6 +1507,68 @@ struct Chain {
         }
     }
 
+    // if_accept! for BPS on the affine fast path (SamplingLoopInplace.jl:170-186 + BouncyParticleSamplers.jl:50-74).
+    // The literal sequence is six passes over the coordinates per event: flow, functionals of the moved point, gradient
+    // and its two inner products, the new velocity, and -- for the next bound -- functionals and the line model again.
+    // Here the functionals ride along: those of the moved x with the flow pass, those of the reflected v with the pass
+    // that writes it (same summation order as compute_functionals, so the values are bit-identical and everything after
+    // an event stays a pure function of the recorded (x, v): resuming from a history column reproduces the run bit for
+    // bit).  Four passes for a reflection.  Returns true when (Lx, Lv) are the functionals of the new state.
+    // `T`: total flow time (deferred horizon moves included).
+    __device__ bool accept_bps_fused(double T) {
+        wait_row_stores();  // x / v are about to change: the TMA engine must have read the previous row
+        if (p.accumulate_moments) accumulate_segment(T, flow_coef(T));
+        double ax[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) ax[k] = 0.0;
+        for_owned([&](int j) {
+            const double xn = XS(j) + VS(j) * T;
+            XS(j) = xn;
+            if constexpr (K > 0) P::accum(p.pot, coord(j), xn, ax);
+        });
+        if constexpr (K > 0) {
+            team_sum_n<TEAM, KK>(ax, mask);
+#pragma unroll
+            for (int k = 0; k < KK; ++k) Lx[k] = ax[k];
+        }
+        double r2[2] = {0.0, 0.0};
+        for_owned([&](int j) {
+            const double g = P::grad(p.pot, coord(j), XS(j), Lx);
+            r2[0] += g * VS(j);
+            r2[1] += g * g;
+        });
+        team_sum_n<TEAM, 2>(r2, mask);
+        const double gv = r2[0], gg = r2[1];
+        const double bounce = (gv > 0.0 ? gv : 0.0);
+        const double prob = bounce / (bounce + p.refresh_rate);
+        const double u = rand_uniform();
+        if (u < prob) {
+            if (gg == 0) return true;   // v unchanged: Lv still valid
+            const double scale = 2 * gv / gg;
+            double av[KK];
+#pragma unroll
+            for (int k = 0; k < KK; ++k) av[k] = 0.0;
+            for_owned([&](int j) {
+                const double g = P::grad(p.pot, coord(j), XS(j), Lx);
+                const double vn = VS(j) - scale * g;
+                VS(j) = vn;
+                if constexpr (K > 0) P::accum(p.pot, coord(j), vn, av);
+            });
+            if constexpr (K > 0) {
+                team_sum_n<TEAM, KK>(av, mask);
+#pragma unroll
+                for (int k = 0; k < KK; ++k) Lv[k] = av[k];
+            }
+            return true;
+        }
+        double nn = refresh_velocity_normals();
+        if (!p.gaussian_velocity) {
+            nn = 1.0 / sqrt(team_sum<TEAM>(nn, mask));
+            for_owned([&](int j) { VS(j) = VS(j) * nn; });
+        }
+        return false;
+    }
+
     __device__ void jump_boomerang() {  // BoomerangSamplers.jl:49-67
         // QUIRK: the jump uses grad U(x) - x although the rates use grad U (BoomerangSamplers.jl:38-46 vs :51-52)
         double r2[2] = {0.0, 0.0};
@@ -1896,6 +1958,7 @@ struct Chain {
         constexpr bool kDefer = kFast && !kRot && !kZZ;
         double pend = 0.0;        // flow time not yet applied to x
         bool line_valid = false;  // (la, lb, Lx) already describe the point x + pend v
+        bool funcs_valid = false; // (Lx, Lv) are the functionals of the current (x, v) (computed along with the jump)
         auto horizon_move = [&](double h) {
             if constexpr (kDefer) {
                 pend += h;
@@ -1920,9 +1983,10 @@ struct Chain {
                     double h = horizon;
                     if (!half) {  // one_step_of_thinning!, :65-85
                         if (!(kDefer && line_valid)) {
-                            compute_functionals();
+                            if (!(kDefer && funcs_valid)) compute_functionals();
                             prepare_line();
                         }
+                        funcs_valid = false;
                     } else h = horizon / 2;  // erroneous_acceptance_rate!, :131-151 (same x, v: line model still valid)
                     build_bound(h);
                     const double e = rand_exp();
@@ -1977,7 +2041,10 @@ struct Chain {
                             live = false;
                         } else {
                         if constexpr (kZZ && !kSticky && !kSpeedUp) accept_zigzag(tp, lt);
-                        else {
+                        else if constexpr (kDefer && SAMPLER == PDMPFLUX_BPS) {
+                            funcs_valid = accept_bps_fused(tp + pend);
+                            pend = 0.0; line_valid = false;
+                        } else {
                             flow_inplace(tp + pend);
                             pend = 0.0; line_valid = false;
                             velocity_jump();
