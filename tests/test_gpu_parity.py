@@ -446,7 +446,7 @@ def test_sample_from_skeleton_dt_methods(p):
         p.sample_from_skeleton(s, -0.1, h)
 
 
-@pytest.mark.parametrize("kind", ["zigzag", "bps", "boomerang", "fecmc"])
+@pytest.mark.parametrize("kind", ["zigzag", "zigzag_brent", "bps", "boomerang", "fecmc"])
 def test_fused_moments_match_skeleton_integrals(p, kind):
     """In-kernel running integrals of x and x^2 (no stored skeleton needed) equal the closed-form integrals over the
     stored skeleton, also across several advance() calls, with a NULL history and in the time-horizon mode."""
@@ -454,8 +454,9 @@ def test_fused_moments_match_skeleton_integrals(p, kind):
     d, nch, n_ev = 12, 40, 300
     g = np.random.default_rng(8)
     x0 = g.standard_normal((nch, d))
-    v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0) if kind == "zigzag" else g.standard_normal((nch, d))
-    s = {"zigzag": lambda: p.ZigZagAD(d, p.Banana()), "bps": lambda: p.BPS(d, p.GaussEquicorr(0.5), refresh_rate=0.3),
+    v0 = np.where(g.random((nch, d)) < 0.5, -1.0, 1.0) if kind.startswith("zigzag") else g.standard_normal((nch, d))
+    s = {"zigzag": lambda: p.ZigZagAD(d, p.Banana()), "zigzag_brent": lambda: p.ZigZag(d, p.Banana(), grid_size=0),
+         "bps": lambda: p.BPS(d, p.GaussEquicorr(0.5), refresh_rate=0.3),
          "boomerang": lambda: p.Boomerang(d, p.GaussDiag(np.linspace(0.5, 2, d)), refresh_rate=0.4),
          "fecmc": lambda: p.ForwardECMC(d, p.GaussStd())}[kind]()
     dev = torch.device("cuda")
