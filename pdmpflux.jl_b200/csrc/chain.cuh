@@ -418,16 +418,31 @@ struct Chain {
             }
         } else {  // BPS / FECMC
             double r2[2] = {0.0, 0.0};
-            for_owned([&](int j) {
-                if (NS == 0 || coord(j) >= NS) {
+            if constexpr (P::kSplit) {
+                // coordinate-local parts only; the functional parts are added from (Lx, Lv) after the reduction --
+                // the same sums the pass that writes a new velocity accumulates (accept_bps_fused), bit for bit
+                for_owned([&](int j) {
                     const double vi = VS(j);
-                    double g, hv;
-                    P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
-                    r2[0] += g * vi; r2[1] += hv * vi;
-                }
-            });
-            team_sum_n<TEAM, 2>(r2, mask);
-            la = r2[0]; lb = r2[1];
+                    double gl, hl;
+                    P::eval_local(p.pot, coord(j), XS(j), vi, gl, hl);
+                    r2[0] += gl * vi; r2[1] += hl * vi;
+                });
+                team_sum_n<TEAM, 2>(r2, mask);
+                double ca_, cb_;
+                P::line_corr(p.pot, Lx, Lv, ca_, cb_);
+                la = r2[0] + ca_; lb = r2[1] + cb_;
+            } else {
+                for_owned([&](int j) {
+                    if (NS == 0 || coord(j) >= NS) {
+                        const double vi = VS(j);
+                        double g, hv;
+                        P::eval(p.pot, coord(j), XS(j), vi, Lx, Lv, g, hv);
+                        r2[0] += g * vi; r2[1] += hv * vi;
+                    }
+                });
+                team_sum_n<TEAM, 2>(r2, mask);
+                la = r2[0]; lb = r2[1];
+            }
         }
     }
 
@@ -1513,9 +1528,12 @@ struct Chain {
     // Here the functionals ride along: those of the moved x with the flow pass, those of the reflected v with the pass
     // that writes it (same summation order as compute_functionals, so the values are bit-identical and everything after
     // an event stays a pure function of the recorded (x, v): resuming from a history column reproduces the run bit for
-    // bit).  Four passes for a reflection.  Returns true when (Lx, Lv) are the functionals of the new state.
+    // bit).  For `kSplit` potentials the line model (a, b) of the new state is accumulated in that last pass too -- the
+    // very sums prepare_line() would form from the stored (x, v') -- so a reflection is three passes and the next bound
+    // starts right away (`line_ready`).  Returns true when (Lx, Lv) are the functionals of the new state.
     // `T`: total flow time (deferred horizon moves included).
-    __device__ bool accept_bps_fused(double T) {
+    __device__ bool accept_bps_fused(double T, bool& line_ready) {
+        line_ready = false;
         wait_row_stores();  // x / v are about to change: the TMA engine must have read the previous row
         if (p.accumulate_moments) accumulate_segment(T, flow_coef(T));
         double ax[KK];
@@ -1545,6 +1563,29 @@ struct Chain {
         if (u < prob) {
             if (gg == 0) return true;   // v unchanged: Lv still valid
             const double scale = 2 * gv / gg;
+            if constexpr (P::kSplit) {   // functionals AND line model of the new velocity in the pass that writes it
+                double av[KK + 2];
+#pragma unroll
+                for (int k = 0; k < KK + 2; ++k) av[k] = 0.0;
+                for_owned([&](int j) {
+                    const double xj = XS(j);
+                    const double g = P::grad(p.pot, coord(j), xj, Lx);
+                    const double vn = VS(j) - scale * g;
+                    VS(j) = vn;
+                    double gl, hl;
+                    P::eval_local(p.pot, coord(j), xj, vn, gl, hl);
+                    av[0] += gl * vn; av[1] += hl * vn;
+                    if constexpr (K > 0) P::accum(p.pot, coord(j), vn, av + 2);
+                });
+                team_sum_n<TEAM, KK + 2>(av, mask);
+#pragma unroll
+                for (int k = 0; k < KK; ++k) Lv[k] = K > 0 ? av[2 + k] : Lv[k];
+                double ca_, cb_;
+                P::line_corr(p.pot, Lx, Lv, ca_, cb_);
+                la = av[0] + ca_; lb = av[1] + cb_;
+                line_ready = true;
+                return true;
+            }
             double av[KK];
 #pragma unroll
             for (int k = 0; k < KK; ++k) av[k] = 0.0;
@@ -2042,8 +2083,8 @@ struct Chain {
                         } else {
                         if constexpr (kZZ && !kSticky && !kSpeedUp) accept_zigzag(tp, lt);
                         else if constexpr (kDefer && SAMPLER == PDMPFLUX_BPS) {
-                            funcs_valid = accept_bps_fused(tp + pend);
-                            pend = 0.0; line_valid = false;
+                            funcs_valid = accept_bps_fused(tp + pend, line_valid);
+                            pend = 0.0;
                         } else {
                             flow_inplace(tp + pend);
                             pend = 0.0; line_valid = false;

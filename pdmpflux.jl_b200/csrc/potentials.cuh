@@ -15,6 +15,12 @@
 // A_i + t B_i with A_i = g_i(x) v_i, B_i = (H v)_i v_i; the first kSpecial coordinates are functions of the
 // functionals L_0..L_{kSpecial-1} (= those coordinates themselves) and are evaluated per time by every lane.
 //
+// `kSplit` potentials also expose the line sums in split form (BPS / ForwardECMC: <grad U(x), d> and <H d, d>):
+//   eval_local(pp, i, xi, di, gl, hl)     the parts of g_i, (H d)_i that do not involve the functionals
+//   line_corr (pp, Lx, Ld, ca, cb)        sum_i (g_i - gl_i) d_i and sum_i ((H d)_i - hl_i) d_i, from the functionals alone
+// so that one pass can accumulate the functionals of a new direction AND its line model (chain.cuh: prepare_line,
+// accept_bps_fused).
+//
 // Formulas: SURVEY.md Appendix A (GAUSS_STD README.md:36-38; BANANA test/test_config.jl:33-36;
 // BANANA_README_SCALAR README.md:62-65; the others are not defined upstream).
 #pragma once
@@ -36,6 +42,9 @@ struct Pot<PDMPFLUX_GAUSS_STD> {
                                 double& g, double& hd) {
         g = xi; hd = di;
     }
+    static constexpr bool kSplit = true;
+    __device__ static void eval_local(const PotParams&, int, double xi, double di, double& gl, double& hl) { gl = xi; hl = di; }
+    __device__ static void line_corr(const PotParams&, const double*, const double*, double& ca, double& cb) { ca = 0.0; cb = 0.0; }
 };
 
 template <>
@@ -52,6 +61,12 @@ struct Pot<PDMPFLUX_GAUSS_DIAG> {
         const double p = __ldg(pp.vec + i);
         g = p * xi; hd = p * di;
     }
+    static constexpr bool kSplit = true;
+    __device__ static void eval_local(const PotParams& pp, int i, double xi, double di, double& gl, double& hl) {
+        const double p = __ldg(pp.vec + i);
+        gl = p * xi; hl = p * di;
+    }
+    __device__ static void line_corr(const PotParams&, const double*, const double*, double& ca, double& cb) { ca = 0.0; cb = 0.0; }
 };
 
 template <>
@@ -68,10 +83,19 @@ struct Pot<PDMPFLUX_GAUSS_EQUICORR> {  // P = alpha I - beta 1 1^T
         g = pp.alpha * xi - pp.beta * Lx[0];
         hd = pp.alpha * di - pp.beta * Ld[0];
     }
+    static constexpr bool kSplit = true;   // sum_i g_i d_i = alpha <x, d> - beta L(x) L(d), sum_i (H d)_i d_i = alpha <d, d> - beta L(d)^2
+    __device__ static void eval_local(const PotParams& pp, int, double xi, double di, double& gl, double& hl) {
+        gl = pp.alpha * xi; hl = pp.alpha * di;
+    }
+    __device__ static void line_corr(const PotParams& pp, const double* Lx, const double* Ld, double& ca, double& cb) {
+        ca = -pp.beta * Lx[0] * Ld[0];
+        cb = -pp.beta * Ld[0] * Ld[0];
+    }
 };
 
 template <>
 struct Pot<PDMPFLUX_BANANA> {  // L0 = x_1, L1 = x_2 (1-based); r = x2 - x1^2 + 1
+    static constexpr bool kSplit = false;
     static constexpr int K = 2;
     static constexpr bool kAffine = true;   // coordinates >= 2 are standard-Gaussian
     static constexpr int kSpecial = 2;      // coordinates 0, 1 are polynomial in t and functions of (L0, L1) only
@@ -100,6 +124,7 @@ struct Pot<PDMPFLUX_BANANA> {  // L0 = x_1, L1 = x_2 (1-based); r = x2 - x1^2 + 
 
 template <>
 struct Pot<PDMPFLUX_BANANA_README_SCALAR> {  // every coordinate = x1 + (x2 - (x1^2 - 1)) + sum_{i>=3} x_i
+    static constexpr bool kSplit = false;
     static constexpr int K = 3;
     static constexpr bool kAffine = false;
     static constexpr int kSpecial = 0;

@@ -208,19 +208,22 @@ def test_resume_and_host_slicing_are_bit_identical(p):
     d, n_sk, nch = 6, 401, 9
     g = np.random.default_rng(3)
     x0 = g.standard_normal((nch, d)); v0 = g.standard_normal((nch, d)); v0 /= np.linalg.norm(v0, axis=1, keepdims=True)
-    s = p.BPS(d, p.Banana(), refresh_rate=0.3)
-    h = p.sample_skeleton(s, n_sk, x0, v0, seed=5)
-    os.environ["PDMPFLUX_SLAB_BYTES"] = str(1 << 20 >> 4)  # force many small device slabs
-    try:
-        hs = p.sample_skeleton(s, n_sk, x0, v0, seed=5)
-    finally:
-        os.environ.pop("PDMPFLUX_SLAB_BYTES")
-    for f in ("X", "V", "t", "horizon", "ar", "error_value_ar", "errored_bound", "rejected", "hitting_horizon"):
-        assert np.array_equal(getattr(h, f), getattr(hs, f)), f
-    k = 150  # checkpoint = column k of the first run
-    h2 = p.sample_skeleton(s, n_sk - k, h.X[:, k], h.V[:, k], seed=5, t0=h.t[:, k], horizon0=h.horizon[:, k], event0=k)
-    assert np.array_equal(h2.X[:, 1:], h.X[:, k + 1:]) and np.array_equal(h2.t[:, 1:], h.t[:, k + 1:])
-    assert np.array_equal(h2.V[:, 1:], h.V[:, k + 1:])
+    # Banana: the literal passes after an event; the Gaussians: the accept that accumulates the functionals and the line
+    # model of the new state along with its own passes -- which must be exactly what a fresh launch computes from (x, v)
+    for s in (p.BPS(d, p.Banana(), refresh_rate=0.3), p.BPS(d, p.GaussEquicorr(0.6), refresh_rate=0.3),
+              p.BPS(d, p.GaussDiag(np.linspace(0.5, 2, d)), refresh_rate=0.1), p.ForwardECMC(d, p.GaussEquicorr(0.4))):
+        h = p.sample_skeleton(s, n_sk, x0, v0, seed=5)
+        os.environ["PDMPFLUX_SLAB_BYTES"] = str(1 << 20 >> 4)  # force many small device slabs
+        try:
+            hs = p.sample_skeleton(s, n_sk, x0, v0, seed=5)
+        finally:
+            os.environ.pop("PDMPFLUX_SLAB_BYTES")
+        for f in ("X", "V", "t", "horizon", "ar", "error_value_ar", "errored_bound", "rejected", "hitting_horizon"):
+            assert np.array_equal(getattr(h, f), getattr(hs, f)), f
+        k = 150  # checkpoint = column k of the first run
+        h2 = p.sample_skeleton(s, n_sk - k, h.X[:, k], h.V[:, k], seed=5, t0=h.t[:, k], horizon0=h.horizon[:, k], event0=k)
+        assert np.array_equal(h2.X[:, 1:], h.X[:, k + 1:]) and np.array_equal(h2.t[:, 1:], h.t[:, k + 1:])
+        assert np.array_equal(h2.V[:, 1:], h.V[:, k + 1:])
 
 
 def test_sample_from_skeleton_and_moments(p):
