@@ -1060,8 +1060,13 @@ struct Chain {
         if constexpr (kTeamSpec) { classify_line_team(h); return; }
         double al = 0.0, be = 0.0;
         int n = 0;
-#pragma unroll
-        for (int k = 0; k < kCrossMax; ++k) { ca[k] = 0.0; cb[k] = 0.0; }
+        // The sign-changing coordinates are remembered as 6-bit indices packed into two words (d <= 64 on this path;
+        // newest in the low bits, the oldest fall off the end) and their (A, B) are re-evaluated into the register list
+        // afterwards with static slot indices.  Pushing (A, B) themselves through the 12-slot register list by
+        // shift-insert was 48 register moves per sign change, executed by the whole warp for the two lanes that needed
+        // them: 19 % of this kernel's instructions at 2.2 active lanes.
+        unsigned long long idx_lo = 0ull;   // entries 0 .. 9
+        unsigned idx_hi = 0u;               // entries 10, 11
 #pragma unroll 2
         for (int j = NS; j < nown; ++j) {
             const double vi = VS(j);
@@ -1071,12 +1076,23 @@ struct Chain {
             const double yh = fma(h, B, A);
             const bool p0 = A > 0.0, ph = yh > 0.0;
             if (p0 && ph) { al += A; be += B; }
-            else if (p0 || ph) {  // push onto the register list (static indices only: shift, then slot 0)
-#pragma unroll
-                for (int k = kCrossMax - 1; k > 0; --k) { ca[k] = ca[k - 1]; cb[k] = cb[k - 1]; }
-                ca[0] = A; cb[0] = B;
+            else if (p0 || ph) {
+                idx_hi = (idx_hi << 6) | (unsigned)(idx_lo >> 54);
+                idx_lo = (idx_lo << 6) | (unsigned long long)j;
                 ++n;    // more than kCrossMax: the oldest entries fall off the end and rate_unsigned() takes the full pass
             }
+        }
+#pragma unroll
+        for (int k = 0; k < kCrossMax; ++k) {
+            const int j = (int)((k < 10 ? (idx_lo >> (6 * (k < 10 ? k : 0))) : (unsigned long long)(idx_hi >> (6 * (k < 10 ? 0 : k - 10)))) & 63ull);
+            double A = 0.0, B = 0.0;
+            if (k < n) {
+                const double vi = VS(j);
+                double g, hv;
+                P::eval(p.pot, j, XS(j), vi, Lx, Lv, g, hv);
+                A = g * vi; B = hv * vi;
+            }
+            ca[k] = A; cb[k] = B;
         }
         cl_al = al; cl_be = be; cl_n = n;
     }
